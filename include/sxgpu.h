@@ -1,0 +1,194 @@
+/*
+ * sxgpu.h -- C ABI of the B200 IQ sample-path library (libsxgpu.so).
+ *
+ * This is the drop-in boundary for the one data-parallel hot path of tejeez/sxxcvr's
+ * SoapySX driver: the per-block conversion between S32_LE I2S frames ([I:int32][Q:int32],
+ * I = left slot) and SoapySDR CF32 stream buffers ([re:f32][im:f32]).  Each entry point
+ * names the reference interface it replaces (file:line under the reference tree).  The
+ * binding a maintainer adds to SoapySX.cpp is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain C types only; no exceptions cross this boundary; every function returns
+ *    SXGPU_OK (0) or a negative SXGPU_ERR_* code (sxgpu_strerror() names it, and
+ *    sxgpu_last_error() carries the CUDA text when the code is SXGPU_ERR_CUDA);
+ *  - offsets and lengths are in FRAMES (one I/Q pair), exactly as in the reference's
+ *    converters; a frame is 8 bytes on the I2S side and 8 bytes as CF32 (4 as CS16);
+ *  - `d_` pointers are device memory on the context's GPU, `h_` pointers host memory;
+ *    the caller owns every buffer; src and dest must not overlap unless identical
+ *    (in-place is allowed for the equal-width CF32 paths);
+ *  - functions taking an `sxgpu_stream` are asynchronous with respect to it (NULL = the
+ *    context's own stream) and may be called concurrently from several host threads as
+ *    long as each thread uses its own stream; the *_host functions are synchronous and
+ *    serialise on an internal lock;
+ *  - there is no CPU fallback: without a usable sm_100 device sxgpu_init() fails.
+ */
+#ifndef SXGPU_H
+#define SXGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SXGPU_ABI_VERSION 1
+
+#define SXGPU_OK 0
+#define SXGPU_ERR_INVALID (-1)     /* NULL/misaligned pointer, overflowing length, bad option */
+#define SXGPU_ERR_CUDA (-2)        /* a CUDA call failed; see sxgpu_last_error() */
+#define SXGPU_ERR_NO_DEVICE (-3)   /* no such GPU, or not a Blackwell sm_100 part */
+#define SXGPU_ERR_NOMEM (-4)       /* device or pinned allocation failed */
+#define SXGPU_ERR_UNSUPPORTED (-5) /* valid request this build does not implement */
+
+typedef struct sxgpu_ctx sxgpu_ctx;
+typedef void *sxgpu_stream; /* a cudaStream_t */
+
+/* ---- lifetime ------------------------------------------------------------------------ */
+
+/* One context per GPU.  Replaces nothing in the reference (which has no device state for
+ * this path beyond its two staging vectors, SoapySX.cpp:552-557, :706-707); the staging
+ * buffers become the context's pinned-host + device ring. */
+int sxgpu_init(int device, sxgpu_ctx **out);
+int sxgpu_destroy(sxgpu_ctx *ctx);
+int sxgpu_abi_version(void);
+const char *sxgpu_strerror(int code);
+const char *sxgpu_last_error(sxgpu_ctx *ctx);
+
+typedef struct {
+    int device;
+    int sm_count;
+    int cc_major, cc_minor;
+    uint64_t l2_bytes;
+    uint64_t hbm_bytes;
+    char name[64];
+} sxgpu_info;
+int sxgpu_device_info(sxgpu_ctx *ctx, sxgpu_info *out);
+
+/* ---- the hot path, device-resident buffers --------------------------------------------- */
+
+/* Replaces convert_rx_buffer(src, src_offset, dest, dest_offset, length),
+ * SoapySX.cpp:103-112 (called from readStream, :957): dest[i] = 2^-31 * (float)src[i] for
+ * the 2*length words of `length` frames.  Bit-exact for every input word. */
+int sxgpu_convert_rx_buffer(sxgpu_ctx *ctx, const void *d_src, size_t src_offset, void *d_dest,
+                            size_t dest_offset, size_t length, sxgpu_stream stream);
+
+/* Replaces convert_tx_buffer(src, src_offset, dest, dest_offset, length, tx_threshold2),
+ * SoapySX.cpp:116-137 (called from writeStream, :1090): clamp to [-1,1], scale by 2^31,
+ * truncate toward zero, clear the two low bits of I and Q, then set both low bits of I
+ * when fi*fi + fq*fq >= tx_threshold2 (un-fused, on the un-clamped inputs).
+ * Inputs >= +1.0 and NaN, where the reference is undefined C++, follow the reference's
+ * ARM deployment target: saturate to 0x7FFFFFFC, NaN -> 0 ("Parity policy"). */
+int sxgpu_convert_tx_buffer(sxgpu_ctx *ctx, const void *d_src, size_t src_offset, void *d_dest,
+                            size_t dest_offset, size_t length, float tx_threshold2,
+                            sxgpu_stream stream);
+
+/* EXTENSIONS -- the reference supports CF32 only (SoapySX.cpp:752-753, :1610-1616); these
+ * have no reference behaviour and are specified in DESIGN.md.  CS16 frame = 2 x int16.
+ * RX: out = (int16)(word >> 16).  TX: word = s << 16, flag on (s*2^-15)^2 sums. */
+int sxgpu_convert_rx_buffer_cs16(sxgpu_ctx *ctx, const void *d_src, size_t src_offset,
+                                 void *d_dest, size_t dest_offset, size_t length,
+                                 sxgpu_stream stream);
+int sxgpu_convert_tx_buffer_cs16(sxgpu_ctx *ctx, const void *d_src, size_t src_offset,
+                                 void *d_dest, size_t dest_offset, size_t length,
+                                 float tx_threshold2, sxgpu_stream stream);
+
+/* Many independent blocks in one launch: what a bank of SoapySX devices would do as one
+ * convert_*_buffer call each per period (256 frames by default, SoapySX.cpp:451).
+ * `blocks` is read on the host when blocks_on_device == 0 (it is then copied into the
+ * stream-ordered staging memory), or is a device pointer when blocks_on_device != 0.
+ * max_length = longest block in frames; it picks the work split (a warp per block up to
+ * 4096 frames, slices of CTAs per block above) and may be 0 for host-resident lists. */
+typedef struct {
+    const void *src;      /* device pointer, first frame of the block */
+    void *dest;           /* device pointer, first frame of the block */
+    uint64_t length;      /* frames */
+    float tx_threshold2;  /* TX only */
+    uint32_t reserved;
+} sxgpu_block;
+int sxgpu_convert_rx_batch(sxgpu_ctx *ctx, const sxgpu_block *blocks, uint32_t nblocks,
+                           int blocks_on_device, size_t max_length, sxgpu_stream stream);
+int sxgpu_convert_tx_batch(sxgpu_ctx *ctx, const sxgpu_block *blocks, uint32_t nblocks,
+                           int blocks_on_device, size_t max_length, sxgpu_stream stream);
+
+/* Repeater path (example/linear_repeater.py:50-71 with an identity process()): RX-convert
+ * `length` frames and TX-convert the result in one pass.  The CF32 intermediate is an
+ * API-visible buffer in the reference, so it is written to d_cf32 unless that is NULL. */
+int sxgpu_convert_loopback(sxgpu_ctx *ctx, const void *d_i2s_in, void *d_cf32, void *d_i2s_out,
+                           size_t length, float tx_threshold2, sxgpu_stream stream);
+
+/* Silence for the gaps between timed TX bursts: what ALSA plays for regions that were
+ * forwarded over (silence_size = boundary, SoapySX.cpp:493-496) -- all-zero I2S words. */
+int sxgpu_fill_silence(sxgpu_ctx *ctx, void *d_i2s, size_t offset, size_t length,
+                       sxgpu_stream stream);
+
+/* ---- the hot path, host buffers ---------------------------------------------------------- */
+
+/* Same contracts as the two converters above, but src and dest are HOST memory, as they
+ * are at the reference's call sites (buffer_rx/buffs[0], SoapySX.cpp:957, :1090).  The
+ * host->device copy, the kernel and the device->host copy all happen inside the call,
+ * pipelined in chunks over the context's ring.  Pinned (cudaHostAlloc / registered)
+ * buffers are used in place; pageable buffers are bounced through pinned staging. */
+int sxgpu_convert_rx_buffer_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset,
+                                 void *h_dest, size_t dest_offset, size_t length);
+int sxgpu_convert_tx_buffer_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset,
+                                 void *h_dest, size_t dest_offset, size_t length,
+                                 float tx_threshold2);
+
+/* ---- statistics (off the hot path) ------------------------------------------------------- */
+
+/* Order-sensitive checksum and flag counts over 32-bit words; every field is a sum mod 2^64
+ * (or an xor), so shards reduce in any order.  Used for full-size parity checks and for the
+ * cross-GPU gather.  Synchronous: returns with *h_out filled. */
+typedef struct {
+    uint64_t sum;    /* sum of words */
+    uint64_t wsum;   /* sum of word * (2*(base_index+i)+1) */
+    uint64_t x;      /* xor of words */
+    uint64_t count;  /* words */
+    uint64_t tx_on;  /* even-index words with bit 1 set: TX-enable flag, SoapySX.cpp:126-133 */
+    uint64_t rail;   /* words whose upper 30 bits are 0x7FFFFFFC or 0x80000000 */
+} sxgpu_stats;
+int sxgpu_stats_words(sxgpu_ctx *ctx, const void *d_words, size_t nwords, uint64_t base_index,
+                      sxgpu_stats *h_out, sxgpu_stream stream);
+
+/* ---- synthetic capture source (stands in for the SX1255 ADC) ------------------------------ */
+
+/* Frame k = sx_synth_frame(seed, k): identical to what the host-side ALSA stub produces. */
+int sxgpu_synth_frames(sxgpu_ctx *ctx, void *d_i2s, uint64_t first_frame, size_t nframes,
+                       uint64_t seed, sxgpu_stream stream);
+
+/* ---- memory and stream plumbing for C/C++ hosts ------------------------------------------- */
+
+int sxgpu_malloc(sxgpu_ctx *ctx, void **d_ptr, size_t bytes);
+int sxgpu_free(sxgpu_ctx *ctx, void *d_ptr);
+int sxgpu_malloc_host(sxgpu_ctx *ctx, void **h_ptr, size_t bytes); /* pinned */
+int sxgpu_free_host(sxgpu_ctx *ctx, void *h_ptr);
+int sxgpu_host_register(sxgpu_ctx *ctx, void *h_ptr, size_t bytes); /* pin caller memory */
+int sxgpu_host_unregister(sxgpu_ctx *ctx, void *h_ptr);
+int sxgpu_memcpy_h2d(sxgpu_ctx *ctx, void *d_dst, const void *h_src, size_t bytes,
+                     sxgpu_stream stream);
+int sxgpu_memcpy_d2h(sxgpu_ctx *ctx, void *h_dst, const void *d_src, size_t bytes,
+                     sxgpu_stream stream);
+int sxgpu_stream_create(sxgpu_ctx *ctx, sxgpu_stream *out);
+int sxgpu_stream_destroy(sxgpu_ctx *ctx, sxgpu_stream stream);
+int sxgpu_stream_sync(sxgpu_ctx *ctx, sxgpu_stream stream); /* NULL = context stream */
+
+/* ---- tuning and accounting ---------------------------------------------------------------- */
+
+/* Options (all have measured defaults):
+ *   "rx_variant", "tx_variant"  0 = auto, 1 = 128-bit vector, 2 = 256-bit vector,
+ *                               3 = bulk-async (TMA) staged through shared memory
+ *   "ctas_per_sm"               persistent grid = sm_count * ctas_per_sm (0 = auto)
+ *   "host_chunk_frames"         chunk size of the *_host pipeline
+ *   "host_mode"                 0 = auto, 1 = copy-engine pipeline, 2 = zero-copy kernel
+ */
+int sxgpu_set_option(sxgpu_ctx *ctx, const char *key, int64_t value);
+int sxgpu_get_option(sxgpu_ctx *ctx, const char *key, int64_t *value);
+/* Counters: "launches" (kernels launched by this context), "frames_rx", "frames_tx",
+ * "h2d_bytes", "d2h_bytes". */
+int sxgpu_get_counter(sxgpu_ctx *ctx, const char *key, uint64_t *value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SXGPU_H */

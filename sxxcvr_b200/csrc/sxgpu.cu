@@ -1,0 +1,986 @@
+// sxgpu.cu -- implementation of the C ABI in include/sxgpu.h (libsxgpu.so).
+//
+// Host-side responsibilities: pick the widest access the caller's pointers allow, size the
+// persistent grid from the SM count and the kernel's occupancy, and -- for host buffers --
+// run the H2D / convert / D2H pipeline over a ring of device chunks on three streams.
+// There is no CPU implementation of any conversion in this file or anywhere in the product.
+#include "../../include/sxgpu.h"
+
+#include "sx_kernels.cuh"
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+using namespace sx;
+
+// ---------------------------------------------------------------------------------------
+// Context
+// ---------------------------------------------------------------------------------------
+namespace {
+
+constexpr int kRingSlots = 4;
+
+struct HostRing {
+    size_t chunk_frames = 0; // capacity of every slot, in frames of 8 bytes per side
+    void *d_in[kRingSlots] = {};
+    void *d_out[kRingSlots] = {};
+    void *h_in[kRingSlots] = {};  // pinned bounce, only allocated for pageable callers
+    void *h_out[kRingSlots] = {};
+    cudaEvent_t copied_in[kRingSlots] = {};
+    cudaEvent_t converted[kRingSlots] = {};
+    cudaEvent_t done[kRingSlots] = {};
+    bool events = false;
+};
+
+} // namespace
+
+struct sxgpu_ctx {
+    int device = 0;
+    cudaDeviceProp prop;
+    cudaStream_t stream = nullptr;
+
+    // options
+    int64_t rx_variant = 0, tx_variant = 0; // 0 auto, 1 vec128, 2 vec256, 3 bulk
+    int64_t unroll = 0;                     // 0 auto, else 1/2/4/8
+    int64_t block = 0;                      // 0 auto, threads per CTA
+    int64_t ctas_per_sm = 0;                // 0 auto
+    int64_t bulk_tile = 0, bulk_stages = 0; // 0 auto
+    int64_t host_chunk_frames = 1 << 21;    // 16 MiB per side per slot
+    int64_t host_mode = 0;                  // 0 auto, 1 copy engines, 2 zero-copy
+    int64_t zero_copy_max_frames = 1 << 15;
+
+    // host pipeline
+    std::mutex host_mutex;
+    cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
+    HostRing ring;
+
+    // statistics scratch
+    StatsAcc *d_stats = nullptr;
+    StatsAcc *h_stats = nullptr;
+    std::mutex stats_mutex;
+
+    // counters
+    std::atomic<uint64_t> launches{0}, frames_rx{0}, frames_tx{0}, h2d_bytes{0}, d2h_bytes{0};
+
+    std::mutex err_mutex;
+    std::string last_error;
+
+    int fail(cudaError_t e, const char *what)
+    {
+        std::lock_guard<std::mutex> lock(err_mutex);
+        last_error = std::string(what) + ": " + cudaGetErrorString(e);
+        cudaGetLastError(); // clear the sticky-free error state
+        return (e == cudaErrorMemoryAllocation) ? SXGPU_ERR_NOMEM : SXGPU_ERR_CUDA;
+    }
+    int invalid(const char *what)
+    {
+        std::lock_guard<std::mutex> lock(err_mutex);
+        last_error = what;
+        return SXGPU_ERR_INVALID;
+    }
+};
+
+#define SX_CUDA(ctx, call)                                                                     \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return (ctx)->fail(e_, #call);                                                     \
+    } while (0)
+
+#define SX_TRY(expr)                                                                           \
+    do {                                                                                       \
+        int r_ = (expr);                                                                       \
+        if (r_ != SXGPU_OK)                                                                    \
+            return r_;                                                                         \
+    } while (0)
+
+namespace {
+
+// ---------------------------------------------------------------------------------------
+// Kernel tables
+// ---------------------------------------------------------------------------------------
+typedef void (*StreamKernel)(const StreamArgs);
+typedef void (*BulkKernel)(const BulkArgs);
+
+template <class Op, int FR, int BLOCK> StreamKernel stream_kernel_for_unroll(int unroll)
+{
+    switch (unroll) {
+    case 2: return stream_convert_kernel<Op, FR, 2, BLOCK>;
+    case 8: return stream_convert_kernel<Op, FR, 8, BLOCK>;
+    default: return stream_convert_kernel<Op, FR, 4, BLOCK>;
+    }
+}
+
+// Instantiated shapes: FR in {2, 4} x UNROLL in {2, 4, 8} x BLOCK in {256, 512}; the
+// frame-at-a-time shape (FR = 1, for pointers whose two sides can never be vector-aligned
+// together) exists once.
+template <class Op> StreamKernel stream_kernel(int fr, int unroll, int block)
+{
+    if (fr == 4)
+        return block == 512 ? stream_kernel_for_unroll<Op, 4, 512>(unroll)
+                            : stream_kernel_for_unroll<Op, 4, 256>(unroll);
+    if (fr == 2)
+        return block == 512 ? stream_kernel_for_unroll<Op, 2, 512>(unroll)
+                            : stream_kernel_for_unroll<Op, 2, 256>(unroll);
+    return stream_convert_kernel<Op, 1, 4, 256>;
+}
+
+struct BulkShape {
+    int tile, stages;
+};
+
+template <class Op> BulkKernel bulk_kernel(BulkShape s)
+{
+    if (s.tile == 2048 && s.stages == 4) return bulk_convert_kernel<Op, 2048, 4>;
+    if (s.tile == 2048 && s.stages == 3) return bulk_convert_kernel<Op, 2048, 3>;
+    if (s.tile == 1024 && s.stages == 6) return bulk_convert_kernel<Op, 1024, 6>;
+    if (s.tile == 1024 && s.stages == 4) return bulk_convert_kernel<Op, 1024, 4>;
+    if (s.tile == 512 && s.stages == 4) return bulk_convert_kernel<Op, 512, 4>;
+    return nullptr;
+}
+
+template <class Op> size_t bulk_smem_bytes(BulkShape s)
+{
+    return size_t(s.stages) * s.tile * (Op::kSrcWords + Op::kDstWords) * 4 + size_t(s.stages) * 8;
+}
+
+int normalise_unroll(int64_t u)
+{
+    return (u == 2 || u == 4 || u == 8) ? int(u) : 4;
+}
+
+// Persistent grid: enough CTAs to fill every SM at the kernel's occupancy, never more than
+// there are tiles of work.
+template <class K>
+int persistent_grid(sxgpu_ctx *ctx, K kernel, int block, size_t smem, uint64_t work_items)
+{
+    int per_sm = int(ctx->ctas_per_sm);
+    if (per_sm <= 0) {
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, block, smem) != cudaSuccess ||
+            occ <= 0)
+            occ = 1;
+        per_sm = occ;
+    }
+    uint64_t grid = uint64_t(ctx->prop.multiProcessorCount) * uint64_t(per_sm);
+    grid = std::min<uint64_t>(grid, std::max<uint64_t>(work_items, 1));
+    return int(grid);
+}
+
+// ---------------------------------------------------------------------------------------
+// Alignment analysis: the widest access both sides allow, and the head that reaches it
+// ---------------------------------------------------------------------------------------
+struct Plan {
+    int fr = 0;        // frames per access; 0 = word kernel
+    uint64_t head = 0; // frames before the aligned middle
+};
+
+template <class Op> Plan plan_access(const char *src, const char *dst, uint64_t total, int want_fr)
+{
+    constexpr uintptr_t SFB = Op::kSrcWords * 4, DFB = Op::kDstWords * 4;
+    uintptr_t s = reinterpret_cast<uintptr_t>(src), d = reinterpret_cast<uintptr_t>(dst);
+    Plan p;
+    if (s % SFB != 0 || d % DFB != 0)
+        return p; // frames themselves are misaligned: word accesses
+    for (int fr = want_fr; fr >= 1; fr >>= 1) {
+        uintptr_t a = (s / SFB) % fr, b = (d / DFB) % fr;
+        if (a != b)
+            continue; // the two sides can never be vector-aligned at the same frame
+        p.fr = fr;
+        p.head = std::min<uint64_t>((fr - a) % fr, total);
+        return p;
+    }
+    p.fr = 1;
+    return p;
+}
+
+// ---------------------------------------------------------------------------------------
+// One conversion call on device pointers
+// ---------------------------------------------------------------------------------------
+template <class Op>
+int launch_bulk(sxgpu_ctx *ctx, const char *src, const char *dst_c, uint64_t total, float thr2,
+                cudaStream_t st, bool *handled)
+{
+    char *dst = const_cast<char *>(dst_c);
+    constexpr uintptr_t SFB = Op::kSrcWords * 4, DFB = Op::kDstWords * 4;
+    constexpr uint64_t G = 16 / (SFB < DFB ? SFB : DFB); // frames per 16 bytes on the narrow side
+    *handled = false;
+
+    uint64_t head = 0;
+    bool found = false;
+    for (; head < G; head++) {
+        if ((reinterpret_cast<uintptr_t>(src) + head * SFB) % 16 == 0 &&
+            (reinterpret_cast<uintptr_t>(dst) + head * DFB) % 16 == 0) {
+            found = true;
+            break;
+        }
+    }
+    if (!found || total < head + G)
+        return SXGPU_OK; // caller falls back to the vector kernel
+
+    BulkShape shape = {int(ctx->bulk_tile ? ctx->bulk_tile : 2048),
+                       int(ctx->bulk_stages ? ctx->bulk_stages : 4)};
+    BulkKernel k = bulk_kernel<Op>(shape);
+    if (!k)
+        return ctx->invalid("unsupported bulk_tile/bulk_stages combination");
+    size_t smem = bulk_smem_bytes<Op>(shape);
+    int block = int(ctx->block ? ctx->block : 256);
+
+    uint64_t mid = (total - head) / G * G;
+    BulkArgs a = {src + head * SFB, dst + head * DFB, mid, thr2};
+    uint64_t ntiles = (mid + shape.tile - 1) / shape.tile;
+    int grid = persistent_grid(ctx, k, block, smem, ntiles);
+    k<<<grid, block, smem, st>>>(a);
+    SX_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+
+    // Up to G-1 frames on either side of the 16-byte-aligned middle.
+    uint64_t tail = total - head - mid;
+    if (head) {
+        StreamArgs e = {src, dst, head, head, 0, thr2};
+        stream_convert_kernel<Op, 1, 4, 256><<<1, 256, 0, st>>>(e);
+        SX_CUDA(ctx, cudaGetLastError());
+        ctx->launches++;
+    }
+    if (tail) {
+        StreamArgs e = {src + (head + mid) * SFB, dst + (head + mid) * DFB, tail, tail, 0, thr2};
+        stream_convert_kernel<Op, 1, 4, 256><<<1, 256, 0, st>>>(e);
+        SX_CUDA(ctx, cudaGetLastError());
+        ctx->launches++;
+    }
+    *handled = true;
+    return SXGPU_OK;
+}
+
+template <class Op>
+int launch_convert(sxgpu_ctx *ctx, const void *src_v, void *dst_v, uint64_t total, float thr2,
+                   int64_t variant, cudaStream_t st)
+{
+    if (total == 0)
+        return SXGPU_OK; // reference: convert_tx_buffer is called with length 0 (:1090)
+    const char *src = static_cast<const char *>(src_v);
+    char *dst = static_cast<char *>(dst_v);
+    if (reinterpret_cast<uintptr_t>(src) % 4 || reinterpret_cast<uintptr_t>(dst) % 4)
+        return ctx->invalid("sample buffers must be at least 4-byte aligned");
+
+    if (variant == 0)
+        variant = 2; // measured default, see DESIGN.md
+    if (variant == 3) {
+        bool handled = false;
+        SX_TRY(launch_bulk<Op>(ctx, src, dst, total, thr2, st, &handled));
+        if (handled)
+            return SXGPU_OK;
+        variant = 1;
+    }
+
+    Plan p = plan_access<Op>(src, dst, total, variant == 2 ? 4 : 2);
+    if (p.fr == 0) {
+        const int block = 256;
+        uint64_t ctas = (total + block - 1) / block;
+        int grid = persistent_grid(ctx, word_convert_kernel<Op>, block, 0, ctas);
+        word_convert_kernel<Op><<<grid, block, 0, st>>>(src, dst, total, thr2);
+        SX_CUDA(ctx, cudaGetLastError());
+        ctx->launches++;
+        return SXGPU_OK;
+    }
+
+    int unroll = p.fr == 1 ? 4 : normalise_unroll(ctx->unroll);
+    int block = (p.fr != 1 && ctx->block == 512) ? 512 : 256;
+    StreamArgs a = {src, dst, total, p.head, (total - p.head) / uint64_t(p.fr), thr2};
+    StreamKernel k = stream_kernel<Op>(p.fr, unroll, block);
+    uint64_t tiles = (a.nvec + uint64_t(block) * unroll - 1) / (uint64_t(block) * unroll);
+    int grid = persistent_grid(ctx, k, block, 0, tiles);
+    k<<<grid, block, 0, st>>>(a);
+    SX_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+    return SXGPU_OK;
+}
+
+bool frames_overflow(size_t offset, size_t length)
+{
+    // 2^60 frames of 8 bytes already overflow a 64-bit byte count.
+    const size_t cap = size_t(1) << 60;
+    return offset > cap || length > cap || offset + length > cap;
+}
+
+template <class Op>
+int convert_entry(sxgpu_ctx *ctx, const void *d_src, size_t src_offset, void *d_dest,
+                  size_t dest_offset, size_t length, float thr2, int64_t variant,
+                  sxgpu_stream stream)
+{
+    if (!ctx)
+        return SXGPU_ERR_INVALID;
+    if (length == 0)
+        return SXGPU_OK;
+    if (!d_src || !d_dest)
+        return ctx->invalid("null sample buffer");
+    if (frames_overflow(src_offset, length) || frames_overflow(dest_offset, length))
+        return ctx->invalid("offset + length overflows");
+    SX_CUDA(ctx, cudaSetDevice(ctx->device));
+    const char *src = static_cast<const char *>(d_src) + src_offset * (Op::kSrcWords * 4);
+    char *dst = static_cast<char *>(d_dest) + dest_offset * (Op::kDstWords * 4);
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    return launch_convert<Op>(ctx, src, dst, length, thr2, variant, st);
+}
+
+// ---------------------------------------------------------------------------------------
+// Host-buffer pipeline
+// ---------------------------------------------------------------------------------------
+struct HostPtrInfo {
+    bool pinned = false;
+    void *device_alias = nullptr; // device-visible address of the same memory, if mapped
+};
+
+HostPtrInfo classify_host_pointer(const void *p)
+{
+    HostPtrInfo info;
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return info;
+    }
+    if (attr.type == cudaMemoryTypeHost) {
+        info.pinned = true;
+        info.device_alias = attr.devicePointer;
+    }
+    return info;
+}
+
+int ensure_ring(sxgpu_ctx *ctx, size_t frames, bool bounce_in, bool bounce_out)
+{
+    HostRing &r = ctx->ring;
+    if (!ctx->s_h2d) {
+        SX_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
+        SX_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking));
+        SX_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+    }
+    if (!r.events) {
+        for (int i = 0; i < kRingSlots; i++) {
+            SX_CUDA(ctx, cudaEventCreateWithFlags(&r.copied_in[i], cudaEventDisableTiming));
+            SX_CUDA(ctx, cudaEventCreateWithFlags(&r.converted[i], cudaEventDisableTiming));
+            SX_CUDA(ctx, cudaEventCreateWithFlags(&r.done[i], cudaEventDisableTiming));
+        }
+        r.events = true;
+    }
+    if (frames > r.chunk_frames) { // grow-only, like the reference's staging vectors (:944, :1087)
+        for (int i = 0; i < kRingSlots; i++) {
+            if (r.d_in[i]) cudaFree(r.d_in[i]);
+            if (r.d_out[i]) cudaFree(r.d_out[i]);
+            if (r.h_in[i]) cudaFreeHost(r.h_in[i]);
+            if (r.h_out[i]) cudaFreeHost(r.h_out[i]);
+            r.d_in[i] = r.d_out[i] = r.h_in[i] = r.h_out[i] = nullptr;
+        }
+        r.chunk_frames = 0;
+        for (int i = 0; i < kRingSlots; i++) {
+            SX_CUDA(ctx, cudaMalloc(&r.d_in[i], frames * 8));
+            SX_CUDA(ctx, cudaMalloc(&r.d_out[i], frames * 8));
+        }
+        r.chunk_frames = frames;
+    }
+    for (int i = 0; i < kRingSlots; i++) {
+        if (bounce_in && !r.h_in[i])
+            SX_CUDA(ctx, cudaHostAlloc(&r.h_in[i], r.chunk_frames * 8, cudaHostAllocDefault));
+        if (bounce_out && !r.h_out[i])
+            SX_CUDA(ctx, cudaHostAlloc(&r.h_out[i], r.chunk_frames * 8, cudaHostAllocDefault));
+    }
+    return SXGPU_OK;
+}
+
+template <class Op>
+int convert_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset, void *h_dest,
+                 size_t dest_offset, size_t length, float thr2, int64_t variant)
+{
+    static_assert(Op::kSrcWords == 2 && Op::kDstWords == 2, "host pipeline carries 8-byte frames");
+    if (!ctx)
+        return SXGPU_ERR_INVALID;
+    if (length == 0)
+        return SXGPU_OK;
+    if (!h_src || !h_dest)
+        return ctx->invalid("null sample buffer");
+    if (frames_overflow(src_offset, length) || frames_overflow(dest_offset, length))
+        return ctx->invalid("offset + length overflows");
+    const char *src = static_cast<const char *>(h_src) + src_offset * 8;
+    char *dst = static_cast<char *>(h_dest) + dest_offset * 8;
+
+    std::lock_guard<std::mutex> lock(ctx->host_mutex);
+    SX_CUDA(ctx, cudaSetDevice(ctx->device));
+
+    HostPtrInfo si = classify_host_pointer(src), di = classify_host_pointer(dst);
+
+    // Zero-copy: the kernel reads and writes pinned host memory across PCIe directly.  One
+    // launch and no staging -- the right shape for period-sized blocks (256 frames).
+    bool zero_copy = si.device_alias && di.device_alias &&
+                     (ctx->host_mode == 2 ||
+                      (ctx->host_mode == 0 && length <= size_t(ctx->zero_copy_max_frames)));
+    if (zero_copy) {
+        if (!ctx->s_comp)
+            SX_TRY(ensure_ring(ctx, 0, false, false));
+        SX_TRY(launch_convert<Op>(ctx, si.device_alias, di.device_alias, length, thr2, 1,
+                                  ctx->s_comp));
+        SX_CUDA(ctx, cudaStreamSynchronize(ctx->s_comp));
+        ctx->h2d_bytes += length * 8;
+        ctx->d2h_bytes += length * 8;
+        return SXGPU_OK;
+    }
+
+    size_t chunk = std::min<size_t>(length, size_t(std::max<int64_t>(ctx->host_chunk_frames, 1024)));
+    SX_TRY(ensure_ring(ctx, chunk, !si.pinned, !di.pinned));
+    HostRing &r = ctx->ring;
+    chunk = std::min(chunk, r.chunk_frames);
+    const size_t nchunks = (length + chunk - 1) / chunk;
+
+    auto chunk_len = [&](size_t i) { return std::min(chunk, length - i * chunk); };
+    auto retire = [&](size_t i) -> int { // chunk i's D2H has been issued into slot i % K
+        int slot = int(i % kRingSlots);
+        SX_CUDA(ctx, cudaEventSynchronize(r.done[slot]));
+        if (!di.pinned)
+            std::memcpy(dst + i * chunk * 8, r.h_out[slot], chunk_len(i) * 8);
+        return SXGPU_OK;
+    };
+
+    for (size_t i = 0; i < nchunks; i++) {
+        int slot = int(i % kRingSlots);
+        if (i >= size_t(kRingSlots))
+            SX_TRY(retire(i - kRingSlots)); // frees d_in/d_out/h_in/h_out of this slot
+        size_t n = chunk_len(i), bytes = n * 8;
+        const void *from = src + i * chunk * 8;
+        if (!si.pinned) {
+            std::memcpy(r.h_in[slot], from, bytes);
+            from = r.h_in[slot];
+        }
+        SX_CUDA(ctx, cudaMemcpyAsync(r.d_in[slot], from, bytes, cudaMemcpyHostToDevice, ctx->s_h2d));
+        SX_CUDA(ctx, cudaEventRecord(r.copied_in[slot], ctx->s_h2d));
+        SX_CUDA(ctx, cudaStreamWaitEvent(ctx->s_comp, r.copied_in[slot], 0));
+        SX_TRY(launch_convert<Op>(ctx, r.d_in[slot], r.d_out[slot], n, thr2, variant, ctx->s_comp));
+        SX_CUDA(ctx, cudaEventRecord(r.converted[slot], ctx->s_comp));
+        SX_CUDA(ctx, cudaStreamWaitEvent(ctx->s_d2h, r.converted[slot], 0));
+        void *to = di.pinned ? static_cast<void *>(dst + i * chunk * 8) : r.h_out[slot];
+        SX_CUDA(ctx, cudaMemcpyAsync(to, r.d_out[slot], bytes, cudaMemcpyDeviceToHost, ctx->s_d2h));
+        SX_CUDA(ctx, cudaEventRecord(r.done[slot], ctx->s_d2h));
+    }
+    for (size_t i = (nchunks > size_t(kRingSlots) ? nchunks - kRingSlots : 0); i < nchunks; i++)
+        SX_TRY(retire(i));
+
+    ctx->h2d_bytes += length * 8;
+    ctx->d2h_bytes += length * 8;
+    return SXGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Batched blocks
+// ---------------------------------------------------------------------------------------
+static_assert(sizeof(sxgpu_block) == sizeof(BlockDesc), "descriptor layouts must match");
+
+template <class Op>
+int convert_batch(sxgpu_ctx *ctx, const sxgpu_block *blocks, uint32_t nblocks, int on_device,
+                  size_t max_length, sxgpu_stream stream)
+{
+    if (!ctx)
+        return SXGPU_ERR_INVALID;
+    if (nblocks == 0)
+        return SXGPU_OK;
+    if (!blocks)
+        return ctx->invalid("null block list");
+    SX_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+
+    const BlockDesc *d_blocks = reinterpret_cast<const BlockDesc *>(blocks);
+    void *staged = nullptr;
+    if (!on_device) {
+        for (uint32_t i = 0; i < nblocks; i++) {
+            if (blocks[i].length && (!blocks[i].src || !blocks[i].dest))
+                return ctx->invalid("null sample buffer in block list");
+            if (reinterpret_cast<uintptr_t>(blocks[i].src) % (Op::kSrcWords * 4) ||
+                reinterpret_cast<uintptr_t>(blocks[i].dest) % (Op::kDstWords * 4))
+                return ctx->invalid("batched blocks must be frame-aligned");
+            max_length = std::max<size_t>(max_length, blocks[i].length);
+        }
+        // Stream-ordered staging: safe against back-to-back batches on any stream.
+        SX_CUDA(ctx, cudaMallocAsync(&staged, size_t(nblocks) * sizeof(BlockDesc), st));
+        SX_CUDA(ctx, cudaMemcpyAsync(staged, blocks, size_t(nblocks) * sizeof(BlockDesc),
+                                     cudaMemcpyHostToDevice, st));
+        d_blocks = static_cast<const BlockDesc *>(staged);
+    } else if (max_length == 0) {
+        return ctx->invalid("max_length is required for device-resident block lists");
+    }
+
+    const int sms = ctx->prop.multiProcessorCount;
+    if (max_length <= 4096) {
+        // One warp per block: a 256-frame period is 128 x 16 bytes = 4 accesses per lane.
+        int block = 256, warps = block / 32;
+        uint64_t ctas = (uint64_t(nblocks) + warps - 1) / warps;
+        int grid = int(std::min<uint64_t>(ctas, uint64_t(sms) * 8));
+        batch_warp_kernel<Op><<<grid, block, 0, st>>>(d_blocks, nblocks);
+    } else {
+        int block = 256;
+        uint64_t slices = (max_length + 16383) / 16384; // ~128 KiB of frames per CTA pass
+        uint64_t want = uint64_t(sms) * 8;
+        uint32_t gy = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(slices, (want + nblocks - 1) / nblocks)));
+        uint32_t gx = uint32_t(std::min<uint64_t>(nblocks, std::max<uint64_t>(1, want / gy)));
+        batch_slice_kernel<Op><<<dim3(gx, gy), block, 0, st>>>(d_blocks, nblocks);
+    }
+    SX_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+    if (staged)
+        SX_CUDA(ctx, cudaFreeAsync(staged, st));
+    return SXGPU_OK;
+}
+
+int64_t *option_slot(sxgpu_ctx *ctx, const char *key)
+{
+    struct {
+        const char *name;
+        int64_t *slot;
+    } table[] = {
+        {"rx_variant", &ctx->rx_variant},
+        {"tx_variant", &ctx->tx_variant},
+        {"unroll", &ctx->unroll},
+        {"block", &ctx->block},
+        {"ctas_per_sm", &ctx->ctas_per_sm},
+        {"bulk_tile", &ctx->bulk_tile},
+        {"bulk_stages", &ctx->bulk_stages},
+        {"host_chunk_frames", &ctx->host_chunk_frames},
+        {"host_mode", &ctx->host_mode},
+        {"zero_copy_max_frames", &ctx->zero_copy_max_frames},
+    };
+    for (auto &e : table)
+        if (std::strcmp(e.name, key) == 0)
+            return e.slot;
+    return nullptr;
+}
+
+template <class Op> int prepare_bulk_kernels(sxgpu_ctx *ctx)
+{
+    const BulkShape shapes[] = {{2048, 4}, {2048, 3}, {1024, 6}, {1024, 4}, {512, 4}};
+    for (BulkShape s : shapes)
+        SX_CUDA(ctx, cudaFuncSetAttribute(bulk_kernel<Op>(s),
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          int(bulk_smem_bytes<Op>(s))));
+    return SXGPU_OK;
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------
+extern "C" {
+
+int sxgpu_abi_version(void) { return SXGPU_ABI_VERSION; }
+
+const char *sxgpu_strerror(int code)
+{
+    switch (code) {
+    case SXGPU_OK: return "ok";
+    case SXGPU_ERR_INVALID: return "invalid argument";
+    case SXGPU_ERR_CUDA: return "CUDA error";
+    case SXGPU_ERR_NO_DEVICE: return "no usable sm_100 device";
+    case SXGPU_ERR_NOMEM: return "out of memory";
+    case SXGPU_ERR_UNSUPPORTED: return "unsupported";
+    default: return "unknown error";
+    }
+}
+
+const char *sxgpu_last_error(sxgpu_ctx *ctx)
+{
+    if (!ctx)
+        return "";
+    std::lock_guard<std::mutex> lock(ctx->err_mutex);
+    return ctx->last_error.c_str();
+}
+
+int sxgpu_init(int device, sxgpu_ctx **out)
+{
+    if (!out)
+        return SXGPU_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+        cudaGetLastError();
+        return SXGPU_ERR_NO_DEVICE;
+    }
+    sxgpu_ctx *ctx = new sxgpu_ctx();
+    ctx->device = device;
+    auto bail = [&](int code) {
+        delete ctx;
+        return code;
+    };
+    if (cudaGetDeviceProperties(&ctx->prop, device) != cudaSuccess)
+        return bail(SXGPU_ERR_NO_DEVICE);
+    // The library carries sm_100a code only (no PTX, no other architectures).
+    if (ctx->prop.major != 10)
+        return bail(SXGPU_ERR_NO_DEVICE);
+    if (cudaSetDevice(device) != cudaSuccess)
+        return bail(SXGPU_ERR_CUDA);
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess)
+        return bail(SXGPU_ERR_CUDA);
+    if (cudaMalloc(&ctx->d_stats, sizeof(StatsAcc)) != cudaSuccess ||
+        cudaHostAlloc(&ctx->h_stats, sizeof(StatsAcc), cudaHostAllocDefault) != cudaSuccess)
+        return bail(SXGPU_ERR_NOMEM);
+    if (prepare_bulk_kernels<RxCf32>(ctx) != SXGPU_OK || prepare_bulk_kernels<TxCf32>(ctx) != SXGPU_OK ||
+        prepare_bulk_kernels<RxCs16>(ctx) != SXGPU_OK || prepare_bulk_kernels<TxCs16>(ctx) != SXGPU_OK)
+        return bail(SXGPU_ERR_CUDA);
+    *out = ctx;
+    return SXGPU_OK;
+}
+
+int sxgpu_destroy(sxgpu_ctx *ctx)
+{
+    if (!ctx)
+        return SXGPU_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    HostRing &r = ctx->ring;
+    for (int i = 0; i < kRingSlots; i++) {
+        if (r.d_in[i]) cudaFree(r.d_in[i]);
+        if (r.d_out[i]) cudaFree(r.d_out[i]);
+        if (r.h_in[i]) cudaFreeHost(r.h_in[i]);
+        if (r.h_out[i]) cudaFreeHost(r.h_out[i]);
+        if (r.events) {
+            cudaEventDestroy(r.copied_in[i]);
+            cudaEventDestroy(r.converted[i]);
+            cudaEventDestroy(r.done[i]);
+        }
+    }
+    if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
+    if (ctx->s_comp) cudaStreamDestroy(ctx->s_comp);
+    if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
+    if (ctx->d_stats) cudaFree(ctx->d_stats);
+    if (ctx->h_stats) cudaFreeHost(ctx->h_stats);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return SXGPU_OK;
+}
+
+int sxgpu_device_info(sxgpu_ctx *ctx, sxgpu_info *out)
+{
+    if (!ctx || !out)
+        return SXGPU_ERR_INVALID;
+    std::memset(out, 0, sizeof *out);
+    out->device = ctx->device;
+    out->sm_count = ctx->prop.multiProcessorCount;
+    out->cc_major = ctx->prop.major;
+    out->cc_minor = ctx->prop.minor;
+    out->l2_bytes = uint64_t(ctx->prop.l2CacheSize);
+    out->hbm_bytes = uint64_t(ctx->prop.totalGlobalMem);
+    std::snprintf(out->name, sizeof out->name, "%.63s", ctx->prop.name);
+    return SXGPU_OK;
+}
+
+int sxgpu_convert_rx_buffer(sxgpu_ctx *ctx, const void *d_src, size_t src_offset, void *d_dest,
+                            size_t dest_offset, size_t length, sxgpu_stream stream)
+{
+    int r = convert_entry<RxCf32>(ctx, d_src, src_offset, d_dest, dest_offset, length, 0.0f,
+                                  ctx ? ctx->rx_variant : 0, stream);
+    if (r == SXGPU_OK)
+        ctx->frames_rx += length;
+    return r;
+}
+
+int sxgpu_convert_tx_buffer(sxgpu_ctx *ctx, const void *d_src, size_t src_offset, void *d_dest,
+                            size_t dest_offset, size_t length, float tx_threshold2,
+                            sxgpu_stream stream)
+{
+    int r = convert_entry<TxCf32>(ctx, d_src, src_offset, d_dest, dest_offset, length,
+                                  tx_threshold2, ctx ? ctx->tx_variant : 0, stream);
+    if (r == SXGPU_OK)
+        ctx->frames_tx += length;
+    return r;
+}
+
+int sxgpu_convert_rx_buffer_cs16(sxgpu_ctx *ctx, const void *d_src, size_t src_offset,
+                                 void *d_dest, size_t dest_offset, size_t length,
+                                 sxgpu_stream stream)
+{
+    int r = convert_entry<RxCs16>(ctx, d_src, src_offset, d_dest, dest_offset, length, 0.0f,
+                                  ctx ? ctx->rx_variant : 0, stream);
+    if (r == SXGPU_OK)
+        ctx->frames_rx += length;
+    return r;
+}
+
+int sxgpu_convert_tx_buffer_cs16(sxgpu_ctx *ctx, const void *d_src, size_t src_offset,
+                                 void *d_dest, size_t dest_offset, size_t length,
+                                 float tx_threshold2, sxgpu_stream stream)
+{
+    int r = convert_entry<TxCs16>(ctx, d_src, src_offset, d_dest, dest_offset, length,
+                                  tx_threshold2, ctx ? ctx->tx_variant : 0, stream);
+    if (r == SXGPU_OK)
+        ctx->frames_tx += length;
+    return r;
+}
+
+int sxgpu_convert_rx_batch(sxgpu_ctx *ctx, const sxgpu_block *blocks, uint32_t nblocks,
+                           int blocks_on_device, size_t max_length, sxgpu_stream stream)
+{
+    return convert_batch<RxCf32>(ctx, blocks, nblocks, blocks_on_device, max_length, stream);
+}
+
+int sxgpu_convert_tx_batch(sxgpu_ctx *ctx, const sxgpu_block *blocks, uint32_t nblocks,
+                           int blocks_on_device, size_t max_length, sxgpu_stream stream)
+{
+    return convert_batch<TxCf32>(ctx, blocks, nblocks, blocks_on_device, max_length, stream);
+}
+
+int sxgpu_convert_loopback(sxgpu_ctx *ctx, const void *d_i2s_in, void *d_cf32, void *d_i2s_out,
+                           size_t length, float tx_threshold2, sxgpu_stream stream)
+{
+    if (!ctx)
+        return SXGPU_ERR_INVALID;
+    if (length == 0)
+        return SXGPU_OK;
+    if (!d_i2s_in || !d_i2s_out)
+        return ctx->invalid("null sample buffer");
+    auto misaligned = [](const void *p) { return reinterpret_cast<uintptr_t>(p) % 16 != 0; };
+    if (misaligned(d_i2s_in) || misaligned(d_i2s_out) || (d_cf32 && misaligned(d_cf32)))
+        return ctx->invalid("loopback buffers must be 16-byte aligned");
+    SX_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    LoopbackArgs a = {static_cast<const char *>(d_i2s_in), static_cast<char *>(d_cf32),
+                      static_cast<char *>(d_i2s_out), length / 2, length, tx_threshold2};
+    int block = int(ctx->block ? ctx->block : 256);
+    constexpr int U = 4;
+    uint64_t tiles = (a.nvec + uint64_t(block) * U - 1) / (uint64_t(block) * U);
+    int grid = persistent_grid(ctx, loopback_kernel<U>, block, 0, tiles);
+    loopback_kernel<U><<<grid, block, 0, st>>>(a);
+    SX_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+    ctx->frames_rx += length;
+    ctx->frames_tx += length;
+    return SXGPU_OK;
+}
+
+int sxgpu_fill_silence(sxgpu_ctx *ctx, void *d_i2s, size_t offset, size_t length,
+                       sxgpu_stream stream)
+{
+    if (!ctx)
+        return SXGPU_ERR_INVALID;
+    if (length == 0)
+        return SXGPU_OK;
+    if (!d_i2s || reinterpret_cast<uintptr_t>(d_i2s) % 8)
+        return ctx->invalid("I2S buffer must be 8-byte aligned");
+    if (frames_overflow(offset, length))
+        return ctx->invalid("offset + length overflows");
+    SX_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    int block = 256;
+    uint64_t ctas = (length + block - 1) / block;
+    int grid = int(std::min<uint64_t>(ctas, uint64_t(ctx->prop.multiProcessorCount) * 8));
+    fill_silence_kernel<<<grid, block, 0, st>>>(static_cast<char *>(d_i2s) + offset * 8, length);
+    SX_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+    return SXGPU_OK;
+}
+
+int sxgpu_convert_rx_buffer_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset,
+                                 void *h_dest, size_t dest_offset, size_t length)
+{
+    int r = convert_host<RxCf32>(ctx, h_src, src_offset, h_dest, dest_offset, length, 0.0f,
+                                 ctx ? ctx->rx_variant : 0);
+    if (r == SXGPU_OK)
+        ctx->frames_rx += length;
+    return r;
+}
+
+int sxgpu_convert_tx_buffer_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset,
+                                 void *h_dest, size_t dest_offset, size_t length,
+                                 float tx_threshold2)
+{
+    int r = convert_host<TxCf32>(ctx, h_src, src_offset, h_dest, dest_offset, length,
+                                 tx_threshold2, ctx ? ctx->tx_variant : 0);
+    if (r == SXGPU_OK)
+        ctx->frames_tx += length;
+    return r;
+}
+
+int sxgpu_stats_words(sxgpu_ctx *ctx, const void *d_words, size_t nwords, uint64_t base_index,
+                      sxgpu_stats *h_out, sxgpu_stream stream)
+{
+    if (!ctx || !h_out)
+        return SXGPU_ERR_INVALID;
+    std::memset(h_out, 0, sizeof *h_out);
+    if (nwords == 0)
+        return SXGPU_OK;
+    if (!d_words || reinterpret_cast<uintptr_t>(d_words) % 4)
+        return ctx->invalid("word buffer must be 4-byte aligned");
+    std::lock_guard<std::mutex> lock(ctx->stats_mutex);
+    SX_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    SX_CUDA(ctx, cudaMemsetAsync(ctx->d_stats, 0, sizeof(StatsAcc), st));
+    int block = 256;
+    uint64_t ctas = (nwords + block - 1) / block;
+    int grid = int(std::min<uint64_t>(ctas, uint64_t(ctx->prop.multiProcessorCount) * 8));
+    stats_kernel<<<grid, block, 0, st>>>(static_cast<const uint32_t *>(d_words), nwords,
+                                        base_index, ctx->d_stats);
+    SX_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+    SX_CUDA(ctx, cudaMemcpyAsync(ctx->h_stats, ctx->d_stats, sizeof(StatsAcc),
+                                 cudaMemcpyDeviceToHost, st));
+    SX_CUDA(ctx, cudaStreamSynchronize(st));
+    h_out->sum = ctx->h_stats->sum;
+    h_out->wsum = ctx->h_stats->wsum;
+    h_out->x = ctx->h_stats->x;
+    h_out->count = nwords;
+    h_out->tx_on = ctx->h_stats->tx_on;
+    h_out->rail = ctx->h_stats->rail;
+    return SXGPU_OK;
+}
+
+int sxgpu_synth_frames(sxgpu_ctx *ctx, void *d_i2s, uint64_t first_frame, size_t nframes,
+                       uint64_t seed, sxgpu_stream stream)
+{
+    if (!ctx)
+        return SXGPU_ERR_INVALID;
+    if (nframes == 0)
+        return SXGPU_OK;
+    if (!d_i2s || reinterpret_cast<uintptr_t>(d_i2s) % 8)
+        return ctx->invalid("I2S buffer must be 8-byte aligned");
+    SX_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    int block = 256;
+    uint64_t ctas = (nframes + block - 1) / block;
+    int grid = int(std::min<uint64_t>(ctas, uint64_t(ctx->prop.multiProcessorCount) * 8));
+    synth_frames_kernel<<<grid, block, 0, st>>>(static_cast<char *>(d_i2s), first_frame, nframes, seed);
+    SX_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+    return SXGPU_OK;
+}
+
+// ---- plumbing ---------------------------------------------------------------------------
+int sxgpu_malloc(sxgpu_ctx *ctx, void **d_ptr, size_t bytes)
+{
+    if (!ctx || !d_ptr)
+        return SXGPU_ERR_INVALID;
+    SX_CUDA(ctx, cudaSetDevice(ctx->device));
+    SX_CUDA(ctx, cudaMalloc(d_ptr, bytes));
+    return SXGPU_OK;
+}
+int sxgpu_free(sxgpu_ctx *ctx, void *d_ptr)
+{
+    if (!ctx)
+        return SXGPU_ERR_INVALID;
+    SX_CUDA(ctx, cudaSetDevice(ctx->device));
+    SX_CUDA(ctx, cudaFree(d_ptr));
+    return SXGPU_OK;
+}
+int sxgpu_malloc_host(sxgpu_ctx *ctx, void **h_ptr, size_t bytes)
+{
+    if (!ctx || !h_ptr)
+        return SXGPU_ERR_INVALID;
+    SX_CUDA(ctx, cudaSetDevice(ctx->device));
+    SX_CUDA(ctx, cudaHostAlloc(h_ptr, bytes, cudaHostAllocPortable | cudaHostAllocMapped));
+    return SXGPU_OK;
+}
+int sxgpu_free_host(sxgpu_ctx *ctx, void *h_ptr)
+{
+    if (!ctx)
+        return SXGPU_ERR_INVALID;
+    SX_CUDA(ctx, cudaFreeHost(h_ptr));
+    return SXGPU_OK;
+}
+int sxgpu_host_register(sxgpu_ctx *ctx, void *h_ptr, size_t bytes)
+{
+    if (!ctx || !h_ptr)
+        return SXGPU_ERR_INVALID;
+    SX_CUDA(ctx, cudaSetDevice(ctx->device));
+    SX_CUDA(ctx, cudaHostRegister(h_ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+    return SXGPU_OK;
+}
+int sxgpu_host_unregister(sxgpu_ctx *ctx, void *h_ptr)
+{
+    if (!ctx || !h_ptr)
+        return SXGPU_ERR_INVALID;
+    SX_CUDA(ctx, cudaHostUnregister(h_ptr));
+    return SXGPU_OK;
+}
+int sxgpu_memcpy_h2d(sxgpu_ctx *ctx, void *d_dst, const void *h_src, size_t bytes,
+                     sxgpu_stream stream)
+{
+    if (!ctx)
+        return SXGPU_ERR_INVALID;
+    SX_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    SX_CUDA(ctx, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, st));
+    ctx->h2d_bytes += bytes;
+    return SXGPU_OK;
+}
+int sxgpu_memcpy_d2h(sxgpu_ctx *ctx, void *h_dst, const void *d_src, size_t bytes,
+                     sxgpu_stream stream)
+{
+    if (!ctx)
+        return SXGPU_ERR_INVALID;
+    SX_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    SX_CUDA(ctx, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, st));
+    ctx->d2h_bytes += bytes;
+    return SXGPU_OK;
+}
+int sxgpu_stream_create(sxgpu_ctx *ctx, sxgpu_stream *out)
+{
+    if (!ctx || !out)
+        return SXGPU_ERR_INVALID;
+    SX_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st;
+    SX_CUDA(ctx, cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    *out = st;
+    return SXGPU_OK;
+}
+int sxgpu_stream_destroy(sxgpu_ctx *ctx, sxgpu_stream stream)
+{
+    if (!ctx || !stream)
+        return SXGPU_ERR_INVALID;
+    SX_CUDA(ctx, cudaStreamDestroy(static_cast<cudaStream_t>(stream)));
+    return SXGPU_OK;
+}
+int sxgpu_stream_sync(sxgpu_ctx *ctx, sxgpu_stream stream)
+{
+    if (!ctx)
+        return SXGPU_ERR_INVALID;
+    SX_CUDA(ctx, cudaSetDevice(ctx->device));
+    SX_CUDA(ctx, cudaStreamSynchronize(stream ? static_cast<cudaStream_t>(stream) : ctx->stream));
+    return SXGPU_OK;
+}
+
+int sxgpu_set_option(sxgpu_ctx *ctx, const char *key, int64_t value)
+{
+    if (!ctx || !key)
+        return SXGPU_ERR_INVALID;
+    int64_t *slot = option_slot(ctx, key);
+    if (!slot)
+        return ctx->invalid("unknown option");
+    if (value < 0)
+        return ctx->invalid("option values are non-negative");
+    std::lock_guard<std::mutex> lock(ctx->host_mutex);
+    *slot = value;
+    return SXGPU_OK;
+}
+
+int sxgpu_get_option(sxgpu_ctx *ctx, const char *key, int64_t *value)
+{
+    if (!ctx || !key || !value)
+        return SXGPU_ERR_INVALID;
+    int64_t *slot = option_slot(ctx, key);
+    if (!slot)
+        return ctx->invalid("unknown option");
+    *value = *slot;
+    return SXGPU_OK;
+}
+
+int sxgpu_get_counter(sxgpu_ctx *ctx, const char *key, uint64_t *value)
+{
+    if (!ctx || !key || !value)
+        return SXGPU_ERR_INVALID;
+    if (!std::strcmp(key, "launches")) *value = ctx->launches;
+    else if (!std::strcmp(key, "frames_rx")) *value = ctx->frames_rx;
+    else if (!std::strcmp(key, "frames_tx")) *value = ctx->frames_tx;
+    else if (!std::strcmp(key, "h2d_bytes")) *value = ctx->h2d_bytes;
+    else if (!std::strcmp(key, "d2h_bytes")) *value = ctx->d2h_bytes;
+    else return ctx->invalid("unknown counter");
+    return SXGPU_OK;
+}
+
+} // extern "C"
