@@ -1,0 +1,423 @@
+#!/usr/bin/env python
+"""bench.py -- RX unpack + TX pack throughput of the SoapySX IQ sample path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one RX block (S32_LE I2S frames -> CF32) and one TX block (CF32 -> I2S frames
+with clamp/truncate/flag bits) of 2^27 frames each per GPU: 1 GiB in and 1 GiB out per
+conversion, the 1 GiB point of BASELINE config 5's sweep and ~8x the L2, so every byte
+comes from and goes to HBM.  Blocks are independent, so ranks shard them with no collective
+on the data path ("weak" scaling); NCCL only gathers the output checksums afterwards.
+
+The JSON line carries
+  value     Msamples/s, whole job, inputs resident in HBM (CUDA events, max over ranks)
+  e2e       the same metric through the host-buffer C-ABI entry points (pinned host in,
+            pinned host out, both PCIe copies inside the timed region)
+  roofline  achieved HBM GB/s of the dominant kernel vs MEASURED_PEAKS.json
+  cpu_baseline  the reference's own converters (oracle/_ref) timed on this box's host cores
+
+`--impl reference` times only the reference's CPU converters, on all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "rx_unpack+tx_pack throughput"
+UNIT = "Msamples/s"
+SEED = 0x53581255
+THR2 = 1.0e-6  # (1e-3)^2, the driver's default TX-enable threshold (SoapySX.cpp:767-773)
+BYTES_PER_FRAME = 16  # 8 read + 8 written, RX and TX alike
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the reference's own converters on host cores.  This is the only place bench.py
+# touches oracle/.
+# ---------------------------------------------------------------------------------------------
+def load_cpu_converters():
+    """(kind, rx, tx): oracle/_ref (the unmodified reference, kind 'reference') if it was built,
+    else the plain-C restatement (kind 'port')."""
+    P, S = C.c_void_p, C.c_size_t
+    ref = ROOT / "oracle" / "_ref" / "libsx_ref.so"
+    if ref.exists():
+        lib = C.CDLL(str(ref))
+        rx, tx, kind = lib.sxref_convert_rx_buffer, lib.sxref_convert_tx_buffer, "reference"
+    else:
+        port = ROOT / "oracle" / "libsx_oracle.so"
+        if not port.exists():
+            subprocess.run(["make", "-C", str(ROOT / "oracle"), "libsx_oracle.so"], check=True, capture_output=True)
+        lib = C.CDLL(str(port))
+        rx, tx, kind = lib.sxo_convert_rx_buffer, lib.sxo_convert_tx_buffer, "port"
+    rx.argtypes, rx.restype = [P, S, P, S, S], None
+    tx.argtypes, tx.restype = [P, S, P, S, S, C.c_float], None
+    return kind, rx, tx
+
+
+class CpuArm:
+    """Splits one RX block and one TX block across `threads` host threads (ctypes releases the
+    GIL), each thread converting a contiguous slice with the reference's scalar loop."""
+
+    def __init__(self, frames: int, threads: int):
+        import numpy as np
+        self.kind, self.rx, self.tx = load_cpu_converters()
+        self.frames, self.threads = frames, threads
+        rng = np.random.default_rng(SEED)
+        self.i2s = rng.integers(-2**31, 2**31, size=2 * frames, dtype=np.int64).astype(np.int32)
+        self.cf = np.empty(2 * frames, np.float32)
+        self.txin = (rng.random(2 * frames, dtype=np.float32) * 1.98 - 0.99).astype(np.float32)
+        self.out = np.empty(2 * frames, np.int32)
+        per = (frames + threads - 1) // threads
+        self.slices = [(t * per, min(per, frames - t * per)) for t in range(threads) if t * per < frames]
+
+    def _run(self, fn):
+        if len(self.slices) == 1:
+            fn(*self.slices[0])
+            return
+        ts = [threading.Thread(target=fn, args=s) for s in self.slices]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+
+    def step(self):
+        a, b, c, d = self.i2s.ctypes.data, self.cf.ctypes.data, self.txin.ctypes.data, self.out.ctypes.data
+        self._run(lambda off, n: self.rx(a, off, b, off, n))
+        self._run(lambda off, n: self.tx(c, off, d, off, n, THR2))
+
+    def time_steps(self, steps: int, warmup: int):
+        for _ in range(warmup):
+            self.step()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            self.step()
+        return (time.perf_counter() - t0) / steps
+
+
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_reference_arm(args, rank: int):
+    if rank != 0:
+        return
+    threads = host_threads()
+    frames = 1 << args.cpu_log2_frames
+    arm = CpuArm(frames, threads)
+    sec = arm.time_steps(args.steps, args.warmup)
+    value = 2 * frames / sec / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "s32<->f32", "data": "synthetic",
+        "config": workload_config(args, per_gpu_frames=frames),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": arm.kind,
+                         "sample": f"RX 2^{args.cpu_log2_frames} + TX 2^{args.cpu_log2_frames} frames per step, "
+                                   f"split over {threads} host threads"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, per_gpu_frames):
+    return {
+        "workload": "SoapySX RX convert (S32_LE I2S -> CF32) + TX convert (CF32 -> S32_LE I2S, clamp/trunc/flag bits), "
+                    "one block each per step per GPU (BASELINE config 5, 1 GiB point)",
+        "frames_per_block": per_gpu_frames, "blocks_per_step_per_gpu": 2,
+        "bytes_per_frame": BYTES_PER_FRAME, "tx_threshold2": THR2,
+        "cache": "each buffer is 8*frames bytes (1 GiB at 2^27), >> 126 MB L2; no flush needed",
+        "parallelism": f"independent blocks sharded over {args.gpus} GPU(s), no data-path collective",
+    }
+
+
+# ---------------------------------------------------------------------------------------------
+# Clock sampling during the timed region
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, power, reasons = [], None, [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax = float(parts[2])
+                power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for name, state in zip(names, parts[4:8]):
+                if state.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def measured_peak():
+    path = ROOT / "MEASURED_PEAKS.json"
+    if path.exists():
+        try:
+            return float(json.loads(path.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except (KeyError, ValueError):
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md, 6.65 TB/s)"
+
+
+def run_gpu_arm(args, rank: int, local_rank: int, world: int):
+    import torch
+    import torch.distributed as dist
+    from sxxcvr_b200 import Context
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the sample path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ctx = Context(local_rank)
+    frames = 1 << args.log2_frames
+    side = torch.cuda.Stream()  # a real stream handle: 0 would mean "the context's own stream"
+    torch.cuda.set_stream(side)
+    st = side.cuda_stream
+
+    i2s_in = torch.empty(2 * frames, dtype=torch.int32, device="cuda")
+    cf = torch.empty(2 * frames, dtype=torch.float32, device="cuda")
+    i2s_out = torch.empty(2 * frames, dtype=torch.int32, device="cuda")
+    ctx.synth_frames(i2s_in.data_ptr(), 0, frames, SEED + rank, st)  # the stubbed ADC, per-rank seed
+
+    def rx():
+        ctx.convert_rx_buffer(i2s_in.data_ptr(), 0, cf.data_ptr(), 0, frames, st)
+
+    def tx():
+        ctx.convert_tx_buffer(cf.data_ptr(), 0, i2s_out.data_ptr(), 0, frames, THR2, st)
+
+    for _ in range(max(args.warmup, 3)):
+        rx()
+        tx()
+    barrier()
+
+    # ---- timed region: K steps, an event between every launch ---------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 1)]
+    launches0 = ctx.counter("launches")
+    barrier()
+    ev[0].record(side)
+    for k in range(args.steps):
+        rx()
+        ev[2 * k + 1].record(side)
+        tx()
+        ev[2 * k + 2].record(side)
+    barrier()
+    launches = ctx.counter("launches") - launches0
+    clocks = sampler.stop()
+
+    total_ms = ev[0].elapsed_time(ev[-1])
+    rx_ms = [ev[2 * k].elapsed_time(ev[2 * k + 1]) for k in range(args.steps)]
+    tx_ms = [ev[2 * k + 1].elapsed_time(ev[2 * k + 2]) for k in range(args.steps)]
+    step_ms = max_over_ranks(total_ms / args.steps)
+    value = world * 2 * frames / (step_ms * 1e-3) / 1e6
+
+    peak, peak_src = measured_peak()
+
+    def roof(ms_list, name):
+        avg = sum(ms_list) / len(ms_list)
+        achieved = frames * BYTES_PER_FRAME / (avg * 1e-3) / 1e9
+        return {"kernel": name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "avg_launch_ms": avg, "best_launch_ms": min(ms_list),
+                "algorithmic_bytes_per_launch": frames * BYTES_PER_FRAME, "peak_source": peak_src}
+
+    roof_rx = roof(rx_ms, "bulk_convert_kernel<RxCf32>")
+    roof_tx = roof(tx_ms, "bulk_convert_kernel<TxCf32>")
+    dominant = roof_tx if sum(tx_ms) >= sum(rx_ms) else roof_rx
+    traffic_file = ROOT / "profiles" / "r01_traffic.json"   # dram bytes per launch from the ncu --set full capture
+    if traffic_file.exists():
+        try:
+            t = json.loads(traffic_file.read_text())
+            roof_rx["traffic"], roof_tx["traffic"] = t.get("rx_bytes_per_launch"), t.get("tx_bytes_per_launch")
+        except ValueError:
+            pass
+
+    # ---- checksums of what the timed kernels produced, gathered over NCCL ----------------------
+    stats = ctx.stats_words(i2s_out.data_ptr(), 2 * frames, 0, st)
+    checks = [list(stats)]
+    if world > 1:
+        t = torch.tensor([s if s < 2**63 else s - 2**64 for s in stats], dtype=torch.int64, device="cuda")
+        gathered = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(gathered, t)
+        checks = [[int(v) & (2**64 - 1) for v in g.tolist()] for g in gathered]
+
+    # ---- end to end: host buffers through the C ABI, PCIe copies inside the timed region -------
+    e2e_frames = 1 << args.e2e_log2_frames
+    h_i2s = torch.empty(2 * e2e_frames, dtype=torch.int32).pin_memory()
+    h_cf_out = torch.empty(2 * e2e_frames, dtype=torch.float32).pin_memory()
+    h_cf_in = torch.empty(2 * e2e_frames, dtype=torch.float32).pin_memory()
+    h_i2s_out = torch.empty(2 * e2e_frames, dtype=torch.int32).pin_memory()
+    h_i2s.copy_(i2s_in[: 2 * e2e_frames].cpu())
+    h_cf_in.copy_(cf[: 2 * e2e_frames].cpu())
+
+    def e2e_step():
+        ctx.convert_rx_buffer_host(h_i2s.data_ptr(), 0, h_cf_out.data_ptr(), 0, e2e_frames)
+        ctx.convert_tx_buffer_host(h_cf_in.data_ptr(), 0, h_i2s_out.data_ptr(), 0, e2e_frames, THR2)
+        return int(h_i2s_out[-1])  # the step's result is read on the host
+
+    for _ in range(max(args.warmup, 3)):
+        e2e_step()
+    barrier()
+    l0 = ctx.counter("launches")
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_sec = (time.perf_counter() - t0) / args.steps
+    barrier()
+    e2e_launches = ctx.counter("launches") - l0
+    e2e_sec = max_over_ranks(e2e_sec)
+    e2e_value = world * 2 * e2e_frames / e2e_sec / 1e6
+
+    # ---- small-block latency rows (period-sized calls, the reference's native regime) ----------
+    small = {}
+    for nf in (256, 4096, 65536):
+        for _ in range(5):
+            ctx.convert_rx_buffer_host(h_i2s.data_ptr(), 0, h_cf_out.data_ptr(), 0, nf)
+        reps = 200
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            ctx.convert_rx_buffer_host(h_i2s.data_ptr(), 0, h_cf_out.data_ptr(), 0, nf)
+        small[f"rx_host_{nf}_frames_us_per_call"] = (time.perf_counter() - t0) / reps * 1e6
+
+    # ---- CPU baseline beside it (rank 0, N=1 only) ---------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = host_threads()
+        arm_all = CpuArm(1 << args.cpu_log2_frames, threads)
+        sec_all = arm_all.time_steps(3, 1)
+        arm_one = CpuArm(1 << (args.cpu_log2_frames - 2), 1)
+        sec_one = arm_one.time_steps(2, 1)
+        cpu = {"value": 2 * arm_all.frames / sec_all / 1e6, "unit": UNIT, "cores": threads, "kind": arm_all.kind,
+               "sample": f"3 steps of RX 2^{args.cpu_log2_frames} + TX 2^{args.cpu_log2_frames} frames over "
+                         f"{threads} host threads",
+               "single_thread": {"value": 2 * arm_one.frames / sec_one / 1e6, "cores": 1,
+                                 "sample": f"2 steps of RX+TX 2^{args.cpu_log2_frames - 2} frames, one thread "
+                                           f"(the reference converts on the calling thread)"}}
+
+    if rank == 0:
+        info = ctx.info()
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "s32<->f32", "data": "synthetic",
+            "config": workload_config(args, frames),
+            "roofline": dominant, "roofline_rx": roof_rx, "roofline_tx": roof_tx,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * 8 * e2e_frames,
+                    "d2h_bytes_per_step": 2 * 8 * e2e_frames, "frames_per_block": e2e_frames,
+                    "ms_per_step": e2e_sec * 1e3, "gpu_launches": e2e_launches,
+                    "api": "sxgpu_convert_rx_buffer_host + sxgpu_convert_tx_buffer_host, pinned host buffers",
+                    "bound": "PCIe: 16 B/frame cross the link each way"},
+            "gpu_launches": launches, "clocks": clocks, "cpu_baseline": cpu, "small_blocks": small,
+            "checksums": {"fields": ["sum", "wsum", "xor", "count", "tx_on", "rail"], "per_rank": checks,
+                          "gathered_with": "nccl all_gather" if world > 1 else "local"},
+            "device": info.name.decode(), "sm_count": info.sm_count,
+        }
+        print(json.dumps(line), flush=True)
+
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--log2-frames", type=int, default=27, help="frames per block per GPU (2^27 = 1 GiB in)")
+    ap.add_argument("--e2e-log2-frames", type=int, default=26)
+    ap.add_argument("--cpu-log2-frames", type=int, default=26)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
+    if world == 1 and args.gpus > 1:
+        # Launched without torchrun: re-exec under it so there is one process per GPU.
+        port = 29500 + os.getpid() % 2000
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(port), __file__] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+    else:
+        run_gpu_arm(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,708 @@
+// SoapySXB200.cpp -- see SoapySXB200.hpp.  Host-side only: every sample conversion in this
+// file is a call into the sxgpu C ABI; there is no CPU conversion path.
+#include "SoapySXB200.hpp"
+
+#include <SoapySDR/Formats.h>
+#include <SoapySDR/Logger.hpp>
+#include <SoapySDR/Registry.hpp>
+#include <SoapySDR/Time.hpp>
+
+#include "sxgpu.h"
+
+#include <cerrno>
+#include <climits>
+#include <cmath>
+#include <cstdlib>
+#include <stdexcept>
+
+namespace sxhost {
+
+namespace {
+
+// SX1255 sample-rate dividers that work over I2S with 32-bit slots (reference table,
+// SoapySX.cpp:196-208; the 24- and 16-bit entries are commented out there as broken).
+const unsigned kRateDividers[] = {1536, 768, 512, 256, 128, 64};
+
+// ALSA error -> SoapySDR stream error (reference :339-360): -EPIPE is an xrun, named by
+// direction; anything else is a generic stream error.
+int stream_error_from_alsa(const Endpoint &ep, long alsa_error)
+{
+    if (alsa_error == -EPIPE)
+        return ep.is_tx() ? SOAPY_SDR_UNDERFLOW : SOAPY_SDR_OVERFLOW;
+    return SOAPY_SDR_STREAM_ERROR;
+}
+
+std::string kwarg(const SoapySDR::Kwargs &args, const char *key, const std::string &fallback)
+{
+    auto it = args.find(key);
+    return it == args.end() ? fallback : it->second;
+}
+
+int check_alsa(int ret, const char *what)
+{
+    if (ret < 0)
+        SoapySDR_logf(SOAPY_SDR_ERROR, "ALSA error in %s: %s", what, snd_strerror(ret));
+    return ret;
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------
+// Endpoint
+// ---------------------------------------------------------------------------------------
+Endpoint::~Endpoint()
+{
+    if (pcm)
+        snd_pcm_close(pcm);
+}
+
+void Endpoint::open()
+{
+    if (check_alsa(snd_pcm_open(&pcm, pcm_name, direction, 0), "snd_pcm_open") < 0) {
+        pcm = nullptr;
+        throw std::runtime_error("Error opening ALSA device");
+    }
+}
+
+// Stops the stream, rewinds the frame counter and forgets queued frames (reference :419-432).
+int Endpoint::reset()
+{
+    snd_pcm_drop(pcm); // fails harmlessly when already stopped
+    int ret = snd_pcm_prepare(pcm);
+    if (ret < 0)
+        return ret;
+    position = 0;
+    return snd_pcm_reset(pcm);
+}
+
+// S32_LE, two interleaved channels, the largest ring the I2S DMA allows for the requested
+// period; software parameters depend on the stream mode (reference :434-517).
+void Endpoint::configure(unsigned long requested_period)
+{
+    if (!pcm)
+        return;
+    ring = sxplan::geometry_for_period(requested_period);
+
+    snd_pcm_hw_params_t *hw = nullptr;
+    snd_pcm_sw_params_t *sw = nullptr;
+    auto fail = [&]() {
+        if (hw)
+            snd_pcm_hw_params_free(hw);
+        if (sw)
+            snd_pcm_sw_params_free(sw);
+        throw std::runtime_error("Error configuring ALSA device");
+    };
+#define SX_ALSA(call)                                                                          \
+    if (check_alsa((call), #call) < 0)                                                         \
+    fail()
+
+    unsigned periods = 0;
+    SX_ALSA(snd_pcm_hw_params_malloc(&hw));
+    SX_ALSA(snd_pcm_hw_params_any(pcm, hw));
+    SX_ALSA(snd_pcm_hw_params_set_access(pcm, hw, SND_PCM_ACCESS_RW_INTERLEAVED));
+    SX_ALSA(snd_pcm_hw_params_set_format(pcm, hw, SND_PCM_FORMAT_S32_LE));
+    // The I2S clock comes from the SX1255, not from ALSA; the rate given here is a dummy.
+    SX_ALSA(snd_pcm_hw_params_set_rate(pcm, hw, 192000, 0));
+    SX_ALSA(snd_pcm_hw_params_set_channels(pcm, hw, 2));
+    SX_ALSA(snd_pcm_hw_params_set_buffer_size_near(pcm, hw, &ring.buffer));
+    SX_ALSA(snd_pcm_hw_params_set_period_size_near(pcm, hw, &ring.period, 0));
+    SX_ALSA(snd_pcm_hw_params_get_periods(hw, &periods, 0));
+    SX_ALSA(snd_pcm_hw_params(pcm, hw));
+    snd_pcm_hw_params_free(hw);
+    hw = nullptr;
+    SoapySDR_logf(SOAPY_SDR_DEBUG, "I2S ring: %lu frames in %u periods of %lu", ring.buffer,
+                  periods, ring.period);
+
+    snd_pcm_uframes_t boundary = 0;
+    SX_ALSA(snd_pcm_sw_params_malloc(&sw));
+    SX_ALSA(snd_pcm_sw_params_current(pcm, sw));
+    SX_ALSA(snd_pcm_sw_params_get_boundary(sw, &boundary));
+    if (mode == Mode::Normal) {
+        // Never stop on xrun; gaps in playback are played as silence.
+        SX_ALSA(snd_pcm_sw_params_set_stop_threshold(pcm, sw, boundary));
+        SX_ALSA(snd_pcm_sw_params_set_silence_threshold(pcm, sw, 0));
+        SX_ALSA(snd_pcm_sw_params_set_silence_size(pcm, sw, boundary));
+    } else {
+        // Plain ALSA behaviour: an xrun stops the (linked) streams.
+        SX_ALSA(snd_pcm_sw_params_set_stop_threshold(pcm, sw, ring.buffer));
+        SX_ALSA(snd_pcm_sw_params_set_silence_threshold(pcm, sw, 0));
+        SX_ALSA(snd_pcm_sw_params_set_silence_size(pcm, sw, 0));
+    }
+    SX_ALSA(snd_pcm_sw_params(pcm, sw));
+    snd_pcm_sw_params_free(sw);
+    sw = nullptr;
+
+    SX_ALSA(reset());
+#undef SX_ALSA
+}
+
+// ---------------------------------------------------------------------------------------
+// PinnedFrames
+// ---------------------------------------------------------------------------------------
+PinnedFrames::~PinnedFrames()
+{
+    if (data_)
+        sxgpu_free_host(gpu_, data_);
+}
+
+void PinnedFrames::reserve(size_t frames)
+{
+    if (frames <= capacity_)
+        return;
+    // Contents never need to survive: both directions fill the staging buffer afresh on
+    // every call (reference :944-948, :1087-1093).
+    if (data_)
+        sxgpu_free_host(gpu_, data_);
+    data_ = nullptr;
+    capacity_ = 0;
+    if (sxgpu_malloc_host(gpu_, &data_, frames * sizeof(uint64_t)) != SXGPU_OK)
+        throw std::runtime_error(std::string("pinned staging allocation failed: ") +
+                                 sxgpu_last_error(gpu_));
+    capacity_ = frames;
+}
+
+// ---------------------------------------------------------------------------------------
+// Construction
+// ---------------------------------------------------------------------------------------
+SoapySXB200::SoapySXB200(const SoapySDR::Kwargs &args)
+    : rx_("hw:CARD=SX1255,DEV=1", SND_PCM_STREAM_CAPTURE),
+      tx_("hw:CARD=SX1255,DEV=0", SND_PCM_STREAM_PLAYBACK)
+{
+    SoapySDR_logf(SOAPY_SDR_INFO, "Initializing SoapySX (B200 stream path)");
+
+    // Which GPU: device argument gpu=N, else LOCAL_RANK (one process per GPU), else 0.
+    const char *local_rank = std::getenv("LOCAL_RANK");
+    gpu_ordinal_ = std::atoi(kwarg(args, "gpu", local_rank ? local_rank : "0").c_str());
+    int rc = sxgpu_init(gpu_ordinal_, &gpu_);
+    if (rc != SXGPU_OK)
+        throw std::runtime_error(std::string("SoapySXB200: cannot use GPU ") +
+                                 std::to_string(gpu_ordinal_) + ": " + sxgpu_strerror(rc) +
+                                 " (there is no CPU fallback for the sample path)");
+
+    // With no SX1255 to probe, start from what the reference concludes when its clock
+    // detection is inconclusive: 38.4 MHz (SoapySX.cpp:656-659).  clock=32e6 selects the
+    // other board variant.  The initial rate is masterClock/256 (:662).
+    master_clock_ = std::stod(kwarg(args, "clock", "38.4e6"));
+    sample_rate_ = master_clock_ / 256.0;
+    antenna_[SOAPY_SDR_RX] = "RX";
+    antenna_[SOAPY_SDR_TX] = "TX";
+    setFrequency(SOAPY_SDR_RX, 0, 433.92e6, SoapySDR::Kwargs());
+    setFrequency(SOAPY_SDR_TX, 0, 433.92e6, SoapySDR::Kwargs());
+
+    stage_rx_ = new PinnedFrames(gpu_);
+    stage_tx_ = new PinnedFrames(gpu_);
+    try {
+        // Same initial staging size as the reference (:704-707).
+        stage_rx_->reserve(8192);
+        stage_tx_->reserve(8192);
+        rx_.open();
+        tx_.open();
+    } catch (...) {
+        delete stage_rx_;
+        delete stage_tx_;
+        sxgpu_destroy(gpu_);
+        throw;
+    }
+}
+
+SoapySXB200::~SoapySXB200()
+{
+    SoapySDR_logf(SOAPY_SDR_INFO, "Uninitializing SoapySX (B200 stream path)");
+    delete stage_rx_;
+    delete stage_tx_;
+    sxgpu_destroy(gpu_);
+}
+
+SoapySDR::Kwargs SoapySXB200::getHardwareInfo() const
+{
+    SoapySDR::Kwargs info;
+    info["soapysx_tag"] = "sxxcvr-b200";
+    info["soapysx_commit"] = "abi" + std::to_string(sxgpu_abi_version());
+    info["hardware_version"] = "unknown"; // no HAT EEPROM on a GPU box (reference :1582-1587)
+    sxgpu_info gi;
+    if (sxgpu_device_info(gpu_, &gi) == SXGPU_OK) {
+        info["gpu"] = gi.name;
+        info["gpu_ordinal"] = std::to_string(gi.device);
+        info["gpu_sm_count"] = std::to_string(gi.sm_count);
+    }
+    return info;
+}
+
+// ---------------------------------------------------------------------------------------
+// Stream formats
+// ---------------------------------------------------------------------------------------
+std::vector<std::string> SoapySXB200::getStreamFormats(const int, const size_t) const
+{
+    return std::vector<std::string>{SOAPY_SDR_CF32}; // reference :1610-1616
+}
+
+std::string SoapySXB200::getNativeStreamFormat(const int, const size_t, double &fullScale) const
+{
+    fullScale = 1.0; // reference :1597-1608
+    return SOAPY_SDR_CF32;
+}
+
+// ---------------------------------------------------------------------------------------
+// Stream lifecycle
+// ---------------------------------------------------------------------------------------
+SoapySDR::Stream *SoapySXB200::setupStream(const int direction, const std::string &format,
+                                           const std::vector<size_t> &,
+                                           const SoapySDR::Kwargs &args)
+{
+    std::scoped_lock lock(rx_.mutex, tx_.mutex);
+
+    if (format != SOAPY_SDR_CF32)
+        throw std::runtime_error("Only CF32 format is currently supported");
+    if (snd_pcm_state(rx_.pcm) == SND_PCM_STATE_RUNNING ||
+        snd_pcm_state(tx_.pcm) == SND_PCM_STATE_RUNNING)
+        throw std::runtime_error("Streams can be setup only if none of the streams are running");
+
+    Endpoint &ep = (direction == SOAPY_SDR_RX) ? rx_ : tx_;
+    if (ep.configured)
+        throw std::runtime_error("Stream has been setup already");
+
+    if (ep.is_tx()) {
+        // The PA is keyed by the samples themselves: a frame whose |z| reaches `threshold`
+        // carries the TX-enable bits.  Stored squared, in single precision (reference :766-774).
+        float threshold = args.count("threshold") ? std::stof(args.at("threshold")) : 1.0e-3f;
+        tx_threshold2_ = threshold * threshold;
+    }
+
+    ep.mode = (kwarg(args, "link", "") == "1") ? Endpoint::Mode::Linked : Endpoint::Mode::Normal;
+    ep.configure(args.count("period") ? std::stoul(args.at("period")) : 0);
+    ep.configured = true;
+
+    // Once both directions exist they share one sample clock: same start, same counter origin.
+    if (!linked_ && rx_.configured && tx_.configured) {
+        SoapySDR_logf(SOAPY_SDR_DEBUG, "Linking RX and TX PCMs");
+        if (check_alsa(snd_pcm_link(rx_.pcm, tx_.pcm), "snd_pcm_link") < 0)
+            throw std::runtime_error("ALSA error");
+        linked_ = true;
+    }
+    return reinterpret_cast<SoapySDR::Stream *>(&ep);
+}
+
+void SoapySXB200::closeStream(SoapySDR::Stream *stream)
+{
+    Endpoint *ep = endpoint_of(stream);
+    std::scoped_lock lock(ep->mutex);
+    ep->configured = false;
+}
+
+size_t SoapySXB200::getStreamMTU(SoapySDR::Stream *stream) const
+{
+    Endpoint *ep = endpoint_of(stream);
+    std::scoped_lock lock(ep->mutex);
+    return ep->ring.period;
+}
+
+int SoapySXB200::activateStream(SoapySDR::Stream *stream, const int, const long long, const size_t)
+{
+    std::scoped_lock lock(rx_.mutex, tx_.mutex);
+    Endpoint *ep = endpoint_of(stream);
+    if (ep->active) {
+        SoapySDR_logf(SOAPY_SDR_ERROR, "Stream was already activated");
+        return SOAPY_SDR_STREAM_ERROR;
+    }
+    ep->active = true;
+    // Linked-mode streams start on the first TX write instead (reference :36-39, :821-825).
+    if (ep->mode == Endpoint::Mode::Normal && snd_pcm_state(ep->pcm) == SND_PCM_STATE_PREPARED) {
+        if (check_alsa(snd_pcm_start(ep->pcm), "snd_pcm_start") < 0)
+            return SOAPY_SDR_STREAM_ERROR;
+    }
+    return 0;
+}
+
+int SoapySXB200::deactivateStream(SoapySDR::Stream *stream, const int, const long long)
+{
+    std::scoped_lock lock(rx_.mutex, tx_.mutex);
+    Endpoint *ep = endpoint_of(stream);
+    if (!ep->active) {
+        SoapySDR_logf(SOAPY_SDR_ERROR, "Stream was already deactivated");
+        return SOAPY_SDR_STREAM_ERROR;
+    }
+    ep->active = false;
+    if (!rx_.active && !tx_.active) {
+        SoapySDR_logf(SOAPY_SDR_INFO, "Stopping and resetting streams");
+        if (check_alsa(rx_.reset(), "rx reset") < 0 || check_alsa(tx_.reset(), "tx reset") < 0)
+            return SOAPY_SDR_STREAM_ERROR;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// RX
+// ---------------------------------------------------------------------------------------
+int SoapySXB200::readStream(SoapySDR::Stream *stream, void *const *buffs, const size_t numElems,
+                            int &flags, long long &timeNs, const long timeoutUs)
+{
+    Endpoint &ep = *endpoint_of(stream);
+    std::scoped_lock lock(ep.mutex);
+
+    flags = 0;
+    if (ep.is_tx())
+        throw std::runtime_error("Wrong direction");
+    if (!ep.active)
+        return 0; // an inactive capture PCM would block forever (reference :887-894)
+
+    snd_pcm_sframes_t pending = 0, delay = 0;
+    int ret = snd_pcm_avail_delay(ep.pcm, &pending, &delay);
+    if (ret < 0) {
+        SoapySDR_logf(SOAPY_SDR_ERROR, "rx snd_pcm_avail_delay: %d", ret);
+        return stream_error_from_alsa(ep, ret);
+    }
+
+    if (unsigned long skip = sxplan::overrun_skip(pending, ep.ring)) {
+        snd_pcm_sframes_t skipped = snd_pcm_forward(ep.pcm, skip);
+        if (skipped < 0) {
+            SoapySDR_logf(SOAPY_SDR_ERROR, "rx snd_pcm_forward: %ld", long(skipped));
+            return stream_error_from_alsa(ep, skipped);
+        }
+        ep.position += skipped;
+        pending -= skipped;
+        SoapySDR_logf(SOAPY_SDR_WARNING, "RX buffer overrun. Skipped %ld samples", long(skipped));
+    }
+
+    unsigned long length = (unsigned long)std::min(numElems, (size_t)ULONG_MAX);
+    length = sxplan::trim_nonblocking(length, pending, timeoutUs);
+    if (length == 0)
+        return 0;
+
+    stage_rx_->reserve(length);
+    snd_pcm_sframes_t got = snd_pcm_readi(ep.pcm, stage_rx_->data(), length);
+    if (got < 0)
+        return stream_error_from_alsa(ep, got);
+
+    // The block's timestamp is the counter value of its first frame.
+    timeNs = SoapySDR::ticksToTimeNs(ep.position, sample_rate_);
+    flags |= SOAPY_SDR_HAS_TIME;
+    ep.position += got;
+
+    // I2S words -> CF32 on the GPU, straight out of pinned staging into the caller's buffer.
+    int rc = sxgpu_convert_rx_buffer_host(gpu_, stage_rx_->data(), 0, buffs[0], 0, size_t(got));
+    if (rc != SXGPU_OK) {
+        SoapySDR_logf(SOAPY_SDR_ERROR, "rx GPU conversion failed: %s (%s)", sxgpu_strerror(rc),
+                      sxgpu_last_error(gpu_));
+        return SOAPY_SDR_STREAM_ERROR;
+    }
+    return int(got);
+}
+
+// ---------------------------------------------------------------------------------------
+// TX
+// ---------------------------------------------------------------------------------------
+int SoapySXB200::writeStream(SoapySDR::Stream *stream, const void *const *buffs,
+                             const size_t numElems, int &flags, const long long timeNs,
+                             const long timeoutUs)
+{
+    Endpoint &ep = *endpoint_of(stream);
+    std::scoped_lock lock(ep.mutex);
+
+    if (!ep.is_tx())
+        throw std::runtime_error("Wrong direction");
+    if (!ep.active)
+        return 0;
+
+    snd_pcm_sframes_t room = 0, queued = 0;
+    int ret = snd_pcm_avail_delay(ep.pcm, &room, &queued);
+    if (ret < 0) {
+        SoapySDR_logf(SOAPY_SDR_ERROR, "tx snd_pcm_avail_delay: %d", ret);
+        return stream_error_from_alsa(ep, ret);
+    }
+
+    unsigned long length = (unsigned long)std::min(numElems, (size_t)ULONG_MAX);
+
+    const bool timed = (flags & SOAPY_SDR_HAS_TIME) != 0;
+    const int64_t time_ticks = timed ? SoapySDR::timeNsToTicks(timeNs, sample_rate_) : 0;
+    sxplan::TxPlacement where =
+        sxplan::place_tx_block(ep.position, queued, timed, time_ticks, ep.ring.period);
+    if (where.discard) {
+        // Late bursts are dropped whole and reported as sent, as most SDR drivers do
+        // (reference :1013-1023).
+        SoapySDR_logf(SOAPY_SDR_WARNING, "Discarding %lu TX samples timed in the past", length);
+        return int(length);
+    }
+    if (where.underrun_jump > 0)
+        SoapySDR_logf(SOAPY_SDR_WARNING, "TX buffer underrun. Forwarding TX stream by %lld samples",
+                      (long long)where.underrun_jump);
+
+    // Move the ring's write pointer up to the block's position; what is skipped plays as
+    // silence.  When the ring cannot take the whole gap yet, take what fits and wait.
+    int64_t gap = where.write_position - ep.position;
+    while (gap > 0) {
+        snd_pcm_sframes_t step = (snd_pcm_sframes_t)std::min(gap, (int64_t)LONG_MAX);
+        snd_pcm_sframes_t fits = snd_pcm_forwardable(ep.pcm);
+        if (fits < 0) {
+            SoapySDR_logf(SOAPY_SDR_ERROR, "tx snd_pcm_forwardable: %ld", long(fits));
+            return stream_error_from_alsa(ep, fits);
+        }
+        snd_pcm_sframes_t moved;
+        if (step < fits) {
+            moved = snd_pcm_forward(ep.pcm, step);
+        } else {
+            moved = snd_pcm_forward(ep.pcm, fits);
+            snd_pcm_wait(ep.pcm, -10001);
+        }
+        if (moved < 0) {
+            SoapySDR_logf(SOAPY_SDR_ERROR, "tx snd_pcm_forward: %ld", long(moved));
+            return stream_error_from_alsa(ep, moved);
+        }
+        ep.position += moved;
+        gap -= moved;
+        room -= moved;
+    }
+
+    length = sxplan::trim_nonblocking(length, room, timeoutUs);
+    if (length == 0)
+        return 0;
+
+    // CF32 -> I2S words on the GPU, from the caller's buffer into pinned staging.
+    stage_tx_->reserve(length);
+    int rc = sxgpu_convert_tx_buffer_host(gpu_, buffs[0], 0, stage_tx_->data(), 0, length,
+                                          tx_threshold2_);
+    if (rc != SXGPU_OK) {
+        SoapySDR_logf(SOAPY_SDR_ERROR, "tx GPU conversion failed: %s (%s)", sxgpu_strerror(rc),
+                      sxgpu_last_error(gpu_));
+        return SOAPY_SDR_STREAM_ERROR;
+    }
+
+    snd_pcm_sframes_t sent = snd_pcm_writei(ep.pcm, stage_tx_->data(), length);
+    if (sent < 0)
+        return stream_error_from_alsa(ep, sent);
+    ep.position += sent;
+    return int(sent);
+}
+
+// ---------------------------------------------------------------------------------------
+// Hardware time: the frame being played right now, read off the TX side so that a TX
+// thread never contends with the RX thread's lock (reference :1107-1139).
+// ---------------------------------------------------------------------------------------
+long long SoapySXB200::getHardwareTime(const std::string &what) const
+{
+    if (!what.empty())
+        throw std::runtime_error("Unsupported time");
+    std::scoped_lock lock(tx_.mutex);
+    snd_pcm_sframes_t room = 0, queued = 0;
+    if (snd_pcm_avail_delay(tx_.pcm, &room, &queued) < 0)
+        throw std::runtime_error("ALSA error");
+    return SoapySDR::ticksToTimeNs(tx_.position - int64_t(queued), sample_rate_);
+}
+
+// ---------------------------------------------------------------------------------------
+// Sample rate: state only, but the SAME set of legal rates, because the rate feeds every
+// timestamp (reference :1145-1219).
+// ---------------------------------------------------------------------------------------
+std::vector<double> SoapySXB200::listSampleRates(const int, const size_t) const
+{
+    std::vector<double> rates;
+    for (unsigned div : kRateDividers)
+        rates.push_back(master_clock_ / double(div));
+    return rates;
+}
+
+SoapySDR::RangeList SoapySXB200::getSampleRateRange(const int direction, const size_t channel) const
+{
+    SoapySDR::RangeList ranges;
+    for (double r : listSampleRates(direction, channel))
+        ranges.push_back(SoapySDR::Range(r, r, 0));
+    return ranges;
+}
+
+void SoapySXB200::setSampleRate(const int, const size_t, const double rate)
+{
+    std::scoped_lock lock(settings_mutex_);
+    if (!(rate > 0))
+        throw std::runtime_error("Sample rate must be positive");
+    const double divider = std::round(master_clock_ / rate);
+    for (unsigned div : kRateDividers) {
+        if (double(div) == divider) {
+            sample_rate_ = master_clock_ / divider;
+            return;
+        }
+    }
+    throw std::runtime_error("Unsupported sample rate");
+}
+
+double SoapySXB200::getSampleRate(const int, const size_t) const
+{
+    std::scoped_lock lock(settings_mutex_);
+    return sample_rate_;
+}
+
+// ---------------------------------------------------------------------------------------
+// RF settings: quantised like the SX1255 registers would (so get-after-set agrees with the
+// reference), stored in plain members.
+// ---------------------------------------------------------------------------------------
+void SoapySXB200::setFrequency(const int direction, const size_t, const double frequency,
+                               const SoapySDR::Kwargs &)
+{
+    std::scoped_lock lock(settings_mutex_);
+    // 24-bit synthesiser word in steps of masterClock / 2^20 (reference :1236-1239).
+    const double step = master_clock_ / double(1L << 20);
+    const double top = step * double((1L << 24) - 1);
+    const double clamped = std::min(std::max(frequency, 0.0), top);
+    frequency_word_[direction == SOAPY_SDR_RX ? SOAPY_SDR_RX : SOAPY_SDR_TX] =
+        uint32_t(int(std::round(clamped / step)));
+}
+
+double SoapySXB200::getFrequency(const int direction, const size_t) const
+{
+    std::scoped_lock lock(settings_mutex_);
+    const double step = master_clock_ / double(1L << 20);
+    return step * double(frequency_word_[direction == SOAPY_SDR_RX ? SOAPY_SDR_RX : SOAPY_SDR_TX]);
+}
+
+std::vector<std::string> SoapySXB200::listGains(const int direction, const size_t) const
+{
+    if (direction == SOAPY_SDR_RX)
+        return {"LNA", "PGA"};
+    return {"DAC", "MIXER"};
+}
+
+SoapySDR::Range SoapySXB200::getGainRange(const int direction, const size_t,
+                                          const std::string &name) const
+{
+    // Reference :1291-1306.
+    if (direction == SOAPY_SDR_RX) {
+        if (name == "LNA") return SoapySDR::Range(0.0, 48.0, 6.0);
+        if (name == "PGA") return SoapySDR::Range(0.0, 30.0, 2.0);
+    } else {
+        if (name == "DAC") return SoapySDR::Range(0.0, 9.0, 3.0);
+        if (name == "MIXER") return SoapySDR::Range(0.0, 30.0, 2.0);
+    }
+    return SoapySDR::Range(0, 0, 0);
+}
+
+void SoapySXB200::setGain(const int direction, const size_t channel, const std::string &name,
+                          const double value)
+{
+    std::scoped_lock lock(settings_mutex_);
+    const auto names = listGains(direction, channel);
+    for (size_t i = 0; i < names.size(); i++) {
+        if (names[i] != name)
+            continue;
+        SoapySDR::Range r = getGainRange(direction, channel, name);
+        double steps = std::round((std::min(std::max(value, r.minimum()), r.maximum()) - r.minimum()) / r.step());
+        // The SX1255 LNA register only has every other 6 dB step below 36 dB, so odd steps
+        // up to 6 read back one lower (register encoding at reference :1319-1327, :1354-1356).
+        if (name == "LNA" && steps <= 6)
+            steps -= std::fmod(steps, 2.0);
+        gain_[direction == SOAPY_SDR_RX ? 1 : 0][i] = r.minimum() + r.step() * steps;
+    }
+}
+
+double SoapySXB200::getGain(const int direction, const size_t channel, const std::string &name) const
+{
+    std::scoped_lock lock(settings_mutex_);
+    const auto names = listGains(direction, channel);
+    for (size_t i = 0; i < names.size(); i++)
+        if (names[i] == name)
+            return gain_[direction == SOAPY_SDR_RX ? 1 : 0][i];
+    return 0.0;
+}
+
+void SoapySXB200::setGain(const int direction, const size_t channel, const double value)
+{
+    std::scoped_lock lock(settings_mutex_);
+    // Same distribution rule as the reference (:1370-1394): park the fine-stepped stage near
+    // a target and let the coarse stage cover the range.
+    if (direction == SOAPY_SDR_RX) {
+        setGain(direction, channel, "LNA", value - 12.0);
+        setGain(direction, channel, "PGA", value - getGain(direction, channel, "LNA"));
+    } else {
+        setGain(direction, channel, "DAC", value - 26.0);
+        setGain(direction, channel, "MIXER", value - getGain(direction, channel, "DAC"));
+    }
+}
+
+std::vector<std::string> SoapySXB200::listAntennas(const int direction, const size_t) const
+{
+    if (direction == SOAPY_SDR_RX)
+        return {"RX", "LB"};
+    return {"TX", "NONE"};
+}
+
+void SoapySXB200::setAntenna(const int direction, const size_t, const std::string &name)
+{
+    std::scoped_lock lock(settings_mutex_);
+    if (direction == SOAPY_SDR_RX) {
+        if (name == "RX" || name == "LB" || name == "DLB")
+            antenna_[SOAPY_SDR_RX] = name;
+    } else if (name == "TX" || name == "NONE") {
+        antenna_[SOAPY_SDR_TX] = name;
+    }
+}
+
+std::string SoapySXB200::getAntenna(const int direction, const size_t) const
+{
+    std::scoped_lock lock(settings_mutex_);
+    return antenna_[direction == SOAPY_SDR_RX ? SOAPY_SDR_RX : SOAPY_SDR_TX];
+}
+
+void SoapySXB200::writeSetting(const std::string &key, const std::string &value)
+{
+    std::scoped_lock lock(settings_mutex_);
+    if (key == "PA" && (value == "ON" || value == "OFF" || value == "AUTO"))
+        pa_mode_ = value; // reference :1472-1493 drives two GPIO lines here
+}
+
+std::string SoapySXB200::readSetting(const std::string &key) const
+{
+    std::scoped_lock lock(settings_mutex_);
+    return key == "PA" ? pa_mode_ : "";
+}
+
+} // namespace sxhost
+
+// ---------------------------------------------------------------------------------------
+// Registration: the same probe result as the reference (SoapySX.cpp:1629-1656).
+// ---------------------------------------------------------------------------------------
+static SoapySDR::KwargsList findSXB200(const SoapySDR::Kwargs &)
+{
+    SoapySDR::Kwargs found;
+    found["label"] = "sx";
+    found["driver"] = "sx";
+    return SoapySDR::KwargsList{found};
+}
+
+static SoapySDR::Device *makeSXB200(const SoapySDR::Kwargs &args)
+{
+    return new sxhost::SoapySXB200(args);
+}
+
+static SoapySDR::Registry registerSXB200("sx", &findSXB200, &makeSXB200, SOAPY_SDR_ABI_VERSION);
+
+// ---------------------------------------------------------------------------------------
+// The bookkeeping rules, exported flat so they can be unit-tested without a GPU.
+// ---------------------------------------------------------------------------------------
+extern "C" {
+
+void sxplan_geometry(unsigned long requested_period, unsigned long *period, unsigned long *buffer)
+{
+    sxplan::Geometry g = sxplan::geometry_for_period(requested_period);
+    *period = g.period;
+    *buffer = g.buffer;
+}
+
+unsigned long sxplan_overrun_skip(long pending, unsigned long buffer, unsigned long period)
+{
+    sxplan::Geometry g = {period, buffer};
+    return sxplan::overrun_skip(pending, g);
+}
+
+unsigned long sxplan_trim_nonblocking(unsigned long wanted, long available, long timeoutUs)
+{
+    return sxplan::trim_nonblocking(wanted, available, timeoutUs);
+}
+
+void sxplan_place_tx_block(int64_t position, long queued, int has_time, int64_t time_ticks,
+                           unsigned long period, int *discard, int64_t *write_position,
+                           int64_t *underrun_jump)
+{
+    sxplan::TxPlacement p = sxplan::place_tx_block(position, queued, has_time != 0, time_ticks, period);
+    *discard = p.discard ? 1 : 0;
+    *write_position = p.write_position;
+    *underrun_jump = p.underrun_jump;
+}
+
+} // extern "C"

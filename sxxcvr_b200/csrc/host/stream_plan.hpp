@@ -1,0 +1,81 @@
+// stream_plan.hpp -- the sample-counter bookkeeping of the SoapySX stream path as pure
+// functions: no ALSA, no CUDA, no locks.  The device (SoapySXB200.cpp) asks these what to do
+// and then does it; tests ask them directly (exported as sxplan_* in SoapySXB200.cpp).
+//
+// Every rule here restates observable behaviour of the reference's readStream/writeStream
+// (SoapySX.cpp:868-1105); the line each one comes from is cited.  "Position" is the stream's
+// running frame counter since the last reset (AlsaPcm::position, :378).
+#pragma once
+
+#include <algorithm>
+#include <cstdint>
+
+namespace sxplan {
+
+// I2S ring geometry.  Period defaults to 256 frames, both are capped at 65 536 (the most
+// the Pi's I2S DMA accepts), and the buffer is the largest whole number of periods (:451,
+// :464-466).
+struct Geometry {
+    unsigned long period;
+    unsigned long buffer;
+};
+
+inline Geometry geometry_for_period(unsigned long requested_period)
+{
+    const unsigned long limit = 65536;
+    Geometry g;
+    g.period = std::min(requested_period != 0 ? requested_period : 256ul, limit);
+    g.buffer = limit / g.period * g.period;
+    return g;
+}
+
+// Capture overrun (:910-915): more frames pending than the ring holds means the oldest were
+// overwritten.  Skip them in whole periods, plus two periods of margin, so period-aligned
+// readers stay aligned.  Returns 0 when nothing was lost.
+inline unsigned long overrun_skip(long pending, const Geometry &g)
+{
+    if (pending <= long(g.buffer))
+        return 0;
+    unsigned long lost = (unsigned long)pending - g.buffer;
+    return (lost / g.period + 2) * g.period;
+}
+
+// A call with timeoutUs <= 0 must not block (:934-942, :1076-1085): trim the transfer to
+// what the ring can take or give right now.
+inline unsigned long trim_nonblocking(unsigned long wanted, long available, long timeoutUs)
+{
+    if (timeoutUs > 0)
+        return wanted;
+    if (available <= 0)
+        return 0;
+    return std::min(wanted, (unsigned long)available);
+}
+
+// Where a TX block lands (:1000-1038).
+struct TxPlacement {
+    bool discard;           // timed block already in the past: report it written, write nothing
+    int64_t write_position; // counter value of the block's first frame
+    int64_t underrun_jump;  // frames an untimed stream was moved ahead after an underrun
+};
+
+// `queued` is ALSA's playback delay: frames written but not yet played (negative after an
+// underrun), so position - queued is the frame being played now (:1000).
+inline TxPlacement place_tx_block(int64_t position, long queued, bool has_time,
+                                  int64_t time_ticks, unsigned long period)
+{
+    const int64_t now_playing = position - int64_t(queued);
+    TxPlacement p = {false, position, 0};
+    if (has_time) {
+        p.write_position = time_ticks; // :1012
+        p.discard = now_playing > time_ticks; // :1017-1023
+        return p;
+    }
+    const int64_t late = now_playing - position; // :1032
+    if (late > 0) {
+        p.underrun_jump = (late / int64_t(period) + 2) * int64_t(period); // :1034
+        p.write_position = position + p.underrun_jump;
+    }
+    return p;
+}
+
+} // namespace sxplan

@@ -135,6 +135,10 @@ struct BulkShape {
 
 template <class Op> BulkKernel bulk_kernel(BulkShape s)
 {
+    if (s.tile == 4096 && s.stages == 3) return bulk_convert_kernel<Op, 4096, 3>;
+    if (s.tile == 3072 && s.stages == 4) return bulk_convert_kernel<Op, 3072, 4>;
+    if (s.tile == 2048 && s.stages == 6) return bulk_convert_kernel<Op, 2048, 6>;
+    if (s.tile == 2048 && s.stages == 5) return bulk_convert_kernel<Op, 2048, 5>;
     if (s.tile == 2048 && s.stages == 4) return bulk_convert_kernel<Op, 2048, 4>;
     if (s.tile == 2048 && s.stages == 3) return bulk_convert_kernel<Op, 2048, 3>;
     if (s.tile == 1024 && s.stages == 6) return bulk_convert_kernel<Op, 1024, 6>;
@@ -268,7 +272,7 @@ int launch_convert(sxgpu_ctx *ctx, const void *src_v, void *dst_v, uint64_t tota
         return ctx->invalid("sample buffers must be at least 4-byte aligned");
 
     if (variant == 0)
-        variant = 2; // measured default, see DESIGN.md
+        variant = 3; // measured default (profiles/r01_sweep.md): bulk-async staging wins
     if (variant == 3) {
         bool handled = false;
         SX_TRY(launch_bulk<Op>(ctx, src, dst, total, thr2, st, &handled));
@@ -555,7 +559,8 @@ int64_t *option_slot(sxgpu_ctx *ctx, const char *key)
 
 template <class Op> int prepare_bulk_kernels(sxgpu_ctx *ctx)
 {
-    const BulkShape shapes[] = {{2048, 4}, {2048, 3}, {1024, 6}, {1024, 4}, {512, 4}};
+    const BulkShape shapes[] = {{4096, 3}, {3072, 4}, {2048, 6}, {2048, 5}, {2048, 4},
+                                {2048, 3}, {1024, 6}, {1024, 4}, {512, 4}};
     for (BulkShape s : shapes)
         SX_CUDA(ctx, cudaFuncSetAttribute(bulk_kernel<Op>(s),
                                           cudaFuncAttributeMaxDynamicSharedMemorySize,

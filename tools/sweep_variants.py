@@ -36,11 +36,17 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--out", default="gpurun_out/sweep.json")
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--bulk-only", action="store_true")
     args = ap.parse_args()
 
     n = 1 << args.log2_frames
     ctx = Context(0)
-    st = torch.cuda.current_stream().cuda_stream
+    # A non-default torch stream: handle 0 would mean "the context's own stream" to the C ABI
+    # and the CUDA events below would bracket nothing.
+    side = torch.cuda.Stream()
+    torch.cuda.set_stream(side)
+    st = side.cuda_stream
+    assert st != 0
     i2s = torch.empty(2 * n, dtype=torch.int32, device="cuda")
     cf = torch.empty(2 * n, dtype=torch.float32, device="cuda")
     out_i = torch.empty(2 * n, dtype=torch.int32, device="cuda")
@@ -70,7 +76,9 @@ def main():
     tx = lambda: ctx.convert_tx_buffer(cf.data_ptr(), 0, out_i.data_ptr(), 0, n, 1e-6, st)
 
     vec_space = list(itertools.product((1, 2), (2, 4, 8), (256, 512), (0, 2, 4, 8)))
-    bulk_space = list(itertools.product(((2048, 4), (2048, 3), (1024, 6), (1024, 4), (512, 4)), (128, 256, 512), (0, 1, 2)))
+    bulk_space = list(itertools.product(((4096, 3), (3072, 4), (2048, 6), (2048, 5), (2048, 4), (2048, 3), (1024, 6), (1024, 4)), (256, 512), (0, 2)))
+    if args.bulk_only:
+        vec_space = []
     if args.quick:
         vec_space = [(1, 4, 256, 0), (2, 4, 256, 0), (2, 8, 256, 0), (2, 2, 512, 0)]
         bulk_space = [((2048, 4), 256, 0), ((1024, 4), 256, 0)]
