@@ -306,13 +306,9 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
             pass
 
     # ---- checksums of what the timed kernels produced, gathered over NCCL ----------------------
+    from sxxcvr_b200 import sharding
     stats = ctx.stats_words(i2s_out.data_ptr(), 2 * frames, 0, st)
-    checks = [list(stats)]
-    if world > 1:
-        t = torch.tensor([s if s < 2**63 else s - 2**64 for s in stats], dtype=torch.int64, device="cuda")
-        gathered = [torch.empty_like(t) for _ in range(world)]
-        dist.all_gather(gathered, t)
-        checks = [[int(v) & (2**64 - 1) for v in g.tolist()] for g in gathered]
+    checks = [list(c) for c in sharding.gather_stats(stats, device="cuda")]
 
     # ---- end to end: host buffers through the C ABI, PCIe copies inside the timed region -------
     e2e_frames = 1 << args.e2e_log2_frames
@@ -382,7 +378,8 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
                     "api": "sxgpu_convert_rx_buffer_host + sxgpu_convert_tx_buffer_host, pinned host buffers",
                     "bound": "PCIe: 16 B/frame cross the link each way"},
             "gpu_launches": launches, "clocks": clocks, "cpu_baseline": cpu, "small_blocks": small,
-            "checksums": {"fields": ["sum", "wsum", "xor", "count", "tx_on", "rail"], "per_rank": checks,
+            "checksums": {"fields": list(sharding.STATS_FIELDS), "per_rank": checks,
+                          "combined": list(sharding.combine_stats(checks)),
                           "gathered_with": "nccl all_gather" if world > 1 else "local"},
             "device": info.name.decode(), "sm_count": info.sm_count,
         }
@@ -396,7 +393,7 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log2-frames", type=int, default=27, help="frames per block per GPU (2^27 = 1 GiB in)")

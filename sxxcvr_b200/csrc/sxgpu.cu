@@ -49,9 +49,9 @@ struct sxgpu_ctx {
     int64_t block = 0;                      // 0 auto, threads per CTA
     int64_t ctas_per_sm = 0;                // 0 auto
     int64_t bulk_tile = 0, bulk_stages = 0; // 0 auto
-    int64_t host_chunk_frames = 1 << 21;    // 16 MiB per side per slot
+    int64_t host_chunk_frames = 0;          // 0 auto (see pick_chunk_frames)
     int64_t host_mode = 0;                  // 0 auto, 1 copy engines, 2 zero-copy
-    int64_t zero_copy_max_frames = 1 << 15;
+    int64_t zero_copy_max_frames = 1 << 18; // measured crossover, profiles/r01_sweep_host_path.json
 
     // host pipeline
     std::mutex host_mutex;
@@ -354,6 +354,19 @@ HostPtrInfo classify_host_pointer(const void *p)
     return info;
 }
 
+// Chunk size of the copy-engine pipeline.  Measured on B200 / PCIe Gen5 (profiles/
+// r01_sweep_host_path.json): about an eighth of the block, between 2 MiB and 32 MiB per
+// side, keeps both copy engines busy while bounding the fill and drain of the pipeline.
+size_t pick_chunk_frames(const sxgpu_ctx *ctx, size_t length)
+{
+    if (ctx->host_chunk_frames > 0)
+        return size_t(std::max<int64_t>(ctx->host_chunk_frames, 1024));
+    size_t chunk = size_t(1) << 18;
+    while (chunk < (size_t(1) << 22) && chunk * 8 < length)
+        chunk <<= 1;
+    return chunk;
+}
+
 int ensure_ring(sxgpu_ctx *ctx, size_t frames, bool bounce_in, bool bounce_out)
 {
     HostRing &r = ctx->ring;
@@ -431,7 +444,7 @@ int convert_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset, void *h_d
         return SXGPU_OK;
     }
 
-    size_t chunk = std::min<size_t>(length, size_t(std::max<int64_t>(ctx->host_chunk_frames, 1024)));
+    size_t chunk = std::min<size_t>(length, pick_chunk_frames(ctx, length));
     SX_TRY(ensure_ring(ctx, chunk, !si.pinned, !di.pinned));
     HostRing &r = ctx->ring;
     chunk = std::min(chunk, r.chunk_frames);

@@ -315,7 +315,7 @@ def test_host_buffer_entry_points(ctx, oracle, pinned, mode, nframes):
         assert np.array_equal(hi.numpy(), sxtest.oracle_tx(oracle, f, sxtest.THR2_DEFAULT))
     finally:
         ctx.set_option("host_mode", 0)
-        ctx.set_option("host_chunk_frames", 1 << 21)
+        ctx.set_option("host_chunk_frames", 0)
 
 
 def test_full_size_block_by_properties(ctx, oracle):
