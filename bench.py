@@ -226,6 +226,8 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
         raise SystemExit("bench.py: no CUDA device; the sample path has no CPU fallback "
                          "(use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    # stdout carries exactly one JSON line: keep NCCL's version/debug banner off it.
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 

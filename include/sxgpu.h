@@ -122,6 +122,49 @@ int sxgpu_convert_loopback(sxgpu_ctx *ctx, const void *d_i2s_in, void *d_cf32, v
 int sxgpu_fill_silence(sxgpu_ctx *ctx, void *d_i2s, size_t offset, size_t length,
                        sxgpu_stream stream);
 
+/* ---- a bank of streams resident in HBM ---------------------------------------------------- */
+
+/* Thousands of independent RX/TX stream pairs served per launch.  Each stream of the bank
+ * behaves like one activated SoapySX device in its default stream mode: sxgpu_bank_read is
+ * readStream(rx, buf, period) and sxgpu_bank_write is writeStream(tx, buf, period, flags,
+ * timeNs) (SoapySX.cpp:868-1105) applied to every stream at once, with the same overrun
+ * skip, timestamping, late-burst discard, underrun forward and silence rules -- but the
+ * frame counters, the playback ring and the sample buffers all stay in device memory and the
+ * bookkeeping runs as a kernel (one thread per stream).  The I2S hardware is the same
+ * deterministic stand-in as on the host: stream s captures sx_synth_frame(seed + s, k), and
+ * its sample clock moves when a blocking transfer must wait or when sxgpu_bank_advance says so. */
+typedef struct sxgpu_bank sxgpu_bank;
+typedef struct {
+    uint32_t nstreams;
+    uint32_t period;       /* frames per block; 0 = 256, capped at 65536 (SoapySX.cpp:451, :464-466) */
+    double sample_rate;    /* Hz; feeds every timestamp */
+    float tx_threshold2;
+    uint32_t reserved;
+    uint64_t seed;
+} sxgpu_bank_config;
+int sxgpu_bank_create(sxgpu_ctx *ctx, const sxgpu_bank_config *config, sxgpu_bank **out);
+int sxgpu_bank_destroy(sxgpu_bank *bank);
+/* Let `frames` sample periods pass on every stream. */
+int sxgpu_bank_advance(sxgpu_bank *bank, int64_t frames, sxgpu_stream stream);
+/* d_cf32: [nstreams][period] CF32 samples on the device. */
+int sxgpu_bank_read(sxgpu_bank *bank, void *d_cf32, sxgpu_stream stream);
+/* flags: SOAPY_SDR_HAS_TIME (4) or 0.  With HAS_TIME, stream s is written at d_time_ns[s], or,
+ * when d_time_ns is NULL, at the timestamp its last read returned plus rx_time_offset_ns. */
+int sxgpu_bank_write(sxgpu_bank *bank, const void *d_cf32, int flags, const long long *d_time_ns,
+                     long long rx_time_offset_ns, sxgpu_stream stream);
+/* Per-stream results of the last read / write and the counters, copied to host arrays of
+ * nstreams elements (any pointer may be NULL).  These synchronise with `stream`. */
+int sxgpu_bank_last_read(sxgpu_bank *bank, int32_t *h_ret, int32_t *h_flags, int64_t *h_time_ns,
+                         sxgpu_stream stream);
+int sxgpu_bank_last_write(sxgpu_bank *bank, int32_t *h_ret, sxgpu_stream stream);
+int sxgpu_bank_positions(sxgpu_bank *bank, int64_t *h_clock, int64_t *h_rx_position,
+                         int64_t *h_tx_position, sxgpu_stream stream);
+/* Copy `nframes` I2S frames of stream `index`'s playback ring, starting at frame counter
+ * `position`, to the host.  Only the most recent ring_frames positions are still held. */
+int sxgpu_bank_playback(sxgpu_bank *bank, uint32_t index, int64_t position, size_t nframes,
+                        void *h_i2s, sxgpu_stream stream);
+int sxgpu_bank_ring_frames(sxgpu_bank *bank, uint64_t *ring_frames);
+
 /* ---- the hot path, host buffers ---------------------------------------------------------- */
 
 /* Same contracts as the two converters above, but src and dest are HOST memory, as they

@@ -33,6 +33,11 @@ class Stats(C.Structure):
         return (self.sum, self.wsum, self.x, self.count, self.tx_on, self.rail)
 
 
+class BankConfig(C.Structure):
+    _fields_ = [("nstreams", C.c_uint32), ("period", C.c_uint32), ("sample_rate", C.c_double),
+                ("tx_threshold2", C.c_float), ("reserved", C.c_uint32), ("seed", C.c_uint64)]
+
+
 class Block(C.Structure):
     _fields_ = [("src", C.c_void_p), ("dest", C.c_void_p), ("length", C.c_uint64),
                 ("tx_threshold2", C.c_float), ("reserved", C.c_uint32)]
@@ -56,6 +61,16 @@ SIGNATURES = {
     "sxgpu_convert_tx_batch": (C.c_int, [_P, _P, C.c_uint32, C.c_int, _S, _P]),
     "sxgpu_convert_loopback": (C.c_int, [_P, _P, _P, _P, _S, _F, _P]),
     "sxgpu_fill_silence": (C.c_int, [_P, _P, _S, _S, _P]),
+    "sxgpu_bank_create": (C.c_int, [_P, C.POINTER(BankConfig), C.POINTER(_P)]),
+    "sxgpu_bank_destroy": (C.c_int, [_P]),
+    "sxgpu_bank_advance": (C.c_int, [_P, C.c_int64, _P]),
+    "sxgpu_bank_read": (C.c_int, [_P, _P, _P]),
+    "sxgpu_bank_write": (C.c_int, [_P, _P, C.c_int, _P, C.c_longlong, _P]),
+    "sxgpu_bank_last_read": (C.c_int, [_P, _P, _P, _P, _P]),
+    "sxgpu_bank_last_write": (C.c_int, [_P, _P, _P]),
+    "sxgpu_bank_positions": (C.c_int, [_P, _P, _P, _P, _P]),
+    "sxgpu_bank_playback": (C.c_int, [_P, C.c_uint32, C.c_int64, _S, _P, _P]),
+    "sxgpu_bank_ring_frames": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "sxgpu_convert_rx_buffer_host": (C.c_int, [_P, _P, _S, _P, _S, _S]),
     "sxgpu_convert_tx_buffer_host": (C.c_int, [_P, _P, _S, _P, _S, _S, _F]),
     "sxgpu_stats_words": (C.c_int, [_P, _P, _S, C.c_uint64, C.POINTER(Stats), _P]),
@@ -220,4 +235,68 @@ class Context:
     def info(self) -> Info:
         out = Info()
         self.check(self.lib.sxgpu_device_info(self.handle, C.byref(out)), "sxgpu_device_info")
+        return out
+
+
+class Bank:
+    """A bank of HBM-resident stream pairs (sxgpu_bank_* in include/sxgpu.h)."""
+
+    def __init__(self, ctx: Context, nstreams: int, period: int = 0, sample_rate: float = 75000.0,
+                 tx_threshold2: float = 1.0e-6, seed: int = 0x53581255):
+        import numpy as np
+        self.np = np
+        self.ctx, self.lib = ctx, ctx.lib
+        cfg = BankConfig(nstreams, period, sample_rate, tx_threshold2, 0, seed)
+        h = _P()
+        ctx.check(self.lib.sxgpu_bank_create(ctx.handle, C.byref(cfg), C.byref(h)), "sxgpu_bank_create")
+        self.handle, self.nstreams = h, nstreams
+        r = C.c_uint64()
+        self.lib.sxgpu_bank_ring_frames(h, C.byref(r))
+        self.ring = r.value
+        self.period = period if 0 < period <= 65536 else (256 if period == 0 else 65536)
+
+    def close(self):
+        if self.handle:
+            self.lib.sxgpu_bank_destroy(self.handle)
+            self.handle = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def advance(self, frames, stream=None):
+        self.ctx.check(self.lib.sxgpu_bank_advance(self.handle, frames, stream), "sxgpu_bank_advance")
+
+    def read(self, d_cf32, stream=None):
+        self.ctx.check(self.lib.sxgpu_bank_read(self.handle, d_cf32, stream), "sxgpu_bank_read")
+
+    def write(self, d_cf32, flags=4, d_time_ns=None, rx_time_offset_ns=0, stream=None):
+        self.ctx.check(self.lib.sxgpu_bank_write(self.handle, d_cf32, flags, d_time_ns, rx_time_offset_ns, stream),
+                       "sxgpu_bank_write")
+
+    def last_read(self, stream=None):
+        np = self.np
+        ret, fl, t = np.empty(self.nstreams, np.int32), np.empty(self.nstreams, np.int32), np.empty(self.nstreams, np.int64)
+        self.ctx.check(self.lib.sxgpu_bank_last_read(self.handle, ret.ctypes.data, fl.ctypes.data, t.ctypes.data, stream),
+                       "sxgpu_bank_last_read")
+        return ret, fl, t
+
+    def last_write(self, stream=None):
+        ret = self.np.empty(self.nstreams, self.np.int32)
+        self.ctx.check(self.lib.sxgpu_bank_last_write(self.handle, ret.ctypes.data, stream), "sxgpu_bank_last_write")
+        return ret
+
+    def positions(self, stream=None):
+        np = self.np
+        c, r, t = (np.empty(self.nstreams, np.int64) for _ in range(3))
+        self.ctx.check(self.lib.sxgpu_bank_positions(self.handle, c.ctypes.data, r.ctypes.data, t.ctypes.data, stream),
+                       "sxgpu_bank_positions")
+        return c, r, t
+
+    def playback(self, index, position, nframes, stream=None):
+        out = self.np.empty(2 * nframes, self.np.int32)
+        self.ctx.check(self.lib.sxgpu_bank_playback(self.handle, index, position, nframes, out.ctypes.data, stream),
+                       "sxgpu_bank_playback")
         return out

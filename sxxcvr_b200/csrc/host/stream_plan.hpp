@@ -7,8 +7,15 @@
 // running frame counter since the last reset (AlsaPcm::position, :378).
 #pragma once
 
-#include <algorithm>
 #include <cstdint>
+
+// The same rules run per stream on the GPU (csrc/sx_bank.cuh), so they are plain functions
+// with no library calls.
+#if defined(__CUDACC__)
+#define SXPLAN_HD __host__ __device__ inline
+#else
+#define SXPLAN_HD inline
+#endif
 
 namespace sxplan {
 
@@ -20,11 +27,13 @@ struct Geometry {
     unsigned long buffer;
 };
 
-inline Geometry geometry_for_period(unsigned long requested_period)
+SXPLAN_HD Geometry geometry_for_period(unsigned long requested_period)
 {
     const unsigned long limit = 65536;
     Geometry g;
-    g.period = std::min(requested_period != 0 ? requested_period : 256ul, limit);
+    g.period = requested_period != 0 ? requested_period : 256ul;
+    if (g.period > limit)
+        g.period = limit;
     g.buffer = limit / g.period * g.period;
     return g;
 }
@@ -32,7 +41,7 @@ inline Geometry geometry_for_period(unsigned long requested_period)
 // Capture overrun (:910-915): more frames pending than the ring holds means the oldest were
 // overwritten.  Skip them in whole periods, plus two periods of margin, so period-aligned
 // readers stay aligned.  Returns 0 when nothing was lost.
-inline unsigned long overrun_skip(long pending, const Geometry &g)
+SXPLAN_HD unsigned long overrun_skip(long pending, const Geometry &g)
 {
     if (pending <= long(g.buffer))
         return 0;
@@ -42,13 +51,13 @@ inline unsigned long overrun_skip(long pending, const Geometry &g)
 
 // A call with timeoutUs <= 0 must not block (:934-942, :1076-1085): trim the transfer to
 // what the ring can take or give right now.
-inline unsigned long trim_nonblocking(unsigned long wanted, long available, long timeoutUs)
+SXPLAN_HD unsigned long trim_nonblocking(unsigned long wanted, long available, long timeoutUs)
 {
     if (timeoutUs > 0)
         return wanted;
     if (available <= 0)
         return 0;
-    return std::min(wanted, (unsigned long)available);
+    return (unsigned long)available < wanted ? (unsigned long)available : wanted;
 }
 
 // Where a TX block lands (:1000-1038).
@@ -60,7 +69,7 @@ struct TxPlacement {
 
 // `queued` is ALSA's playback delay: frames written but not yet played (negative after an
 // underrun), so position - queued is the frame being played now (:1000).
-inline TxPlacement place_tx_block(int64_t position, long queued, bool has_time,
+SXPLAN_HD TxPlacement place_tx_block(int64_t position, long queued, bool has_time,
                                   int64_t time_ticks, unsigned long period)
 {
     const int64_t now_playing = position - int64_t(queued);

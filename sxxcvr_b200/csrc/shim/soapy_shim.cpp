@@ -7,6 +7,8 @@
 #include <SoapySDR/Registry.hpp>
 #include <SoapySDR/Time.hpp>
 
+#include "../sx_time.h"
+
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -337,28 +339,16 @@ void SoapySDR::setLogLevel(const LogLevel logLevel) { g_logLevel = logLevel; }
 SoapySDR::LogLevel SoapySDR::getLogLevel(void) { return g_logLevel; }
 
 // ---------------------------------------------------------------------------------------
-// Tick/time conversion.  Restates upstream SoapySDR lib/TimeC.cpp (version unpinned by the
-// reference, SoapySX/CMakeLists.txt:45): whole seconds are converted in integers, the
-// sub-second remainder (and the fractional part of a non-integer rate) in double.
+// Tick/time conversion: one definition (csrc/sx_time.h) shared with the device code.
 // ---------------------------------------------------------------------------------------
 extern "C" long long SoapySDR_ticksToTimeNs(const long long ticks, const double rate)
 {
-    const long long wholeRate = (long long)rate;
-    const long long seconds = ticks / wholeRate;
-    const long long leftover = ticks - seconds * wholeRate;
-    const double drift = double(seconds) * (rate - double(wholeRate));
-    const double subSecondNs = ((double(leftover) - drift) * 1000000000.0) / rate;
-    return seconds * 1000000000LL + std::llround(subSecondNs);
+    return sx_ticks_to_time_ns(ticks, rate);
 }
 
 extern "C" long long SoapySDR_timeNsToTicks(const long long timeNs, const double rate)
 {
-    const long long wholeRate = (long long)rate;
-    const long long seconds = timeNs / 1000000000LL;
-    const long long leftoverNs = timeNs - seconds * 1000000000LL;
-    const double drift = double(seconds) * (rate - double(wholeRate));
-    const double subSecondTicks = drift + (double(leftoverNs) * rate) / 1000000000.0;
-    return seconds * wholeRate + std::llround(subSecondTicks);
+    return sx_time_ns_to_ticks(timeNs, rate);
 }
 
 extern "C" const char *SoapySDR_errToStr(int errorCode)

@@ -1,0 +1,227 @@
+// sx_bank.cuh -- a bank of independent SX1255 stream pairs whose state lives in HBM.
+//
+// The reference serves one front-end per process and does one readStream + one writeStream
+// of a 256-frame period per loop iteration (example/linear_repeater.py:50-71): 2 KiB each way,
+// pure latency.  On a B200 the natural unit is thousands of such streams per launch, and then
+// the per-stream bookkeeping (SoapySX.cpp:868-1105) is itself data-parallel: every stream
+// carries three counters and the rules in host/stream_plan.hpp are pure functions of them.
+// So the bank keeps, per stream, in device memory:
+//     clock        frames the (virtual) SX1255 has produced/consumed since the streams started
+//     rx_position  the RX frame counter (AlsaPcm::position of the capture side, :378)
+//     tx_position  the TX frame counter (playback side)
+// plus a playback ring of `ring` frames and a capture staging slot of one period, and runs
+//     bank_rx_plan_kernel     what readStream decides for every stream    (one thread / stream)
+//     bank_capture_kernel     stand-in for the I2S DMA: writes the planned frames into HBM
+//     batch_warp_kernel<RxCf32>  the conversion                           (one warp / stream)
+//     bank_tx_plan_kernel     what writeStream decides for every stream   (one thread / stream)
+//     bank_tx_convert_kernel  silence for forwarded-over gaps + the conversion into the ring
+// The virtual clock follows the same rule as the host-side ALSA stand-in: it moves when a
+// blocking transfer must wait (by exactly the deficit) or when the owner advances it.
+#pragma once
+
+#include "host/stream_plan.hpp"
+#include "sx_kernels.cuh"
+#include "sx_time.h"
+
+namespace sx {
+
+struct BankState {
+    uint32_t nstreams;
+    uint32_t period;
+    uint64_t ring; // playback/capture ring size in frames (sxplan::Geometry::buffer)
+    double sample_rate;
+    float thr2;
+    uint64_t seed;
+
+    long long *clock;
+    long long *rx_position;
+    long long *tx_position;
+
+    // results of the last read / write, per stream
+    int *rx_ret;
+    int *rx_flags;
+    long long *rx_time_ns;
+    int *tx_ret;
+
+    // plans handed from the plan kernels to the data kernels
+    long long *rx_first_frame; // counter value of the first frame of the block being read
+    BlockDesc *rx_blocks;      // staging slot -> caller's CF32 block
+    long long *tx_write_position;
+    long long *tx_gap_start; // forwarded-over region to be silenced
+    long long *tx_gap_length;
+
+    char *capture_stage; // [nstreams][period] I2S frames
+    char *playback_ring; // [nstreams][ring]   I2S frames
+};
+
+constexpr int SX_HAS_TIME = 1 << 2; // SOAPY_SDR_HAS_TIME
+
+// readStream(stream, buf, period, timeoutUs > 0) for stream s: SoapySX.cpp:897-959.
+__global__ void bank_rx_plan_kernel(BankState b, char *cf32_out)
+{
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= b.nstreams)
+        return;
+    const sxplan::Geometry geo = {b.period, b.ring};
+    long long clock = b.clock[s], pos = b.rx_position[s];
+    long pending = long(clock - pos);
+
+    unsigned long skip = sxplan::overrun_skip(pending, geo); // :910-915
+    if (skip) {
+        long moved = long(skip) < pending ? long(skip) : pending; // forward() moves at most what is pending
+        pos += moved;
+        pending -= moved;
+    }
+    const long length = long(b.period);
+    if (pending < length) // a blocking read waits for the I2S clock
+        clock += length - pending;
+
+    b.rx_time_ns[s] = sx_ticks_to_time_ns(pos, b.sample_rate); // timestamp of the first frame (:950)
+    b.rx_flags[s] = SX_HAS_TIME;
+    b.rx_first_frame[s] = pos;
+    b.rx_ret[s] = int(length);
+    b.rx_position[s] = pos + length;
+    b.clock[s] = clock;
+
+    BlockDesc d;
+    d.src = b.capture_stage + size_t(s) * b.period * 8;
+    d.dst = cf32_out + size_t(s) * b.period * 8;
+    d.length = uint64_t(length);
+    d.thr2 = 0.0f;
+    d.reserved = 0;
+    b.rx_blocks[s] = d;
+}
+
+// Stand-in for the I2S DMA: frame k of stream s is sx_synth_frame(seed + s, k).
+__global__ void bank_capture_kernel(BankState b)
+{
+    const uint32_t lane = threadIdx.x & 31, warps_per_cta = blockDim.x >> 5;
+    const uint64_t nwarps = uint64_t(gridDim.x) * warps_per_cta;
+    for (uint64_t s = uint64_t(blockIdx.x) * warps_per_cta + (threadIdx.x >> 5); s < b.nstreams; s += nwarps) {
+        const uint64_t first = uint64_t(b.rx_first_frame[s]);
+        char *out = b.capture_stage + s * b.period * 8;
+        for (uint32_t i = lane; i < b.period; i += 32) {
+            uint64_t z = sx_synth_frame(b.seed + s, first + i);
+            Pack<2> p;
+            p.w[0] = uint32_t(z);
+            p.w[1] = uint32_t(z >> 32);
+            st_stream<8>(out + size_t(i) * 8, p);
+        }
+    }
+}
+
+// writeStream(stream, buf, period, flags, timeNs, timeoutUs > 0) for stream s: :989-1097.
+// time_ns == nullptr means "the timestamp of this stream's last read plus rx_time_offset_ns",
+// the repeater pattern (example/linear_repeater.py:64-69).
+__global__ void bank_tx_plan_kernel(BankState b, int flags, const long long *time_ns,
+                                    long long rx_time_offset_ns)
+{
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= b.nstreams)
+        return;
+    long long clock = b.clock[s], pos = b.tx_position[s];
+    const long long ring = (long long)b.ring, period = (long long)b.period;
+    const long queued = long(pos - clock); // ALSA delay: written but not yet played
+
+    const bool timed = (flags & SX_HAS_TIME) != 0;
+    long long ticks = 0;
+    if (timed) {
+        long long t = time_ns ? time_ns[s] : b.rx_time_ns[s] + rx_time_offset_ns;
+        ticks = sx_time_ns_to_ticks(t, b.sample_rate);
+    }
+    sxplan::TxPlacement where = sxplan::place_tx_block(pos, queued, timed, ticks, b.period);
+
+    b.tx_gap_start[s] = pos;
+    b.tx_gap_length[s] = 0;
+    if (where.discard) { // :1017-1023: report written, write nothing
+        b.tx_ret[s] = int(period);
+        b.tx_write_position[s] = -1;
+        return;
+    }
+
+    // :1043-1073: forward the write pointer to the block's position, waiting for ring space.
+    long long gap = where.write_position - pos;
+    if (gap > 0)
+        b.tx_gap_length[s] = gap;
+    while (gap > 0) {
+        long long fits = clock + ring - pos;
+        if (fits < 0)
+            fits = 0;
+        long long moved;
+        if (gap < fits) {
+            moved = gap;
+        } else {
+            moved = fits;
+            long long room_after = clock + ring - (pos + moved);
+            if (room_after < period) // snd_pcm_wait: until a period of space is free
+                clock += period - room_after;
+        }
+        pos += moved;
+        gap -= moved;
+    }
+
+    // blocking snd_pcm_writei of one period (:1093)
+    long long room = clock + ring - pos;
+    if (room < period)
+        clock += period - room;
+
+    b.tx_write_position[s] = pos;
+    b.tx_ret[s] = int(period);
+    b.tx_position[s] = pos + period;
+    b.clock[s] = clock;
+}
+
+// Silence for the forwarded-over region, then the block itself, into the stream's ring.
+__global__ void bank_tx_convert_kernel(BankState b, const char *cf32_in)
+{
+    const uint32_t lane = threadIdx.x & 31, warps_per_cta = blockDim.x >> 5;
+    const uint64_t nwarps = uint64_t(gridDim.x) * warps_per_cta;
+    for (uint64_t s = uint64_t(blockIdx.x) * warps_per_cta + (threadIdx.x >> 5); s < b.nstreams; s += nwarps) {
+        const long long at = b.tx_write_position[s];
+        if (at < 0)
+            continue; // discarded
+        char *ring = b.playback_ring + s * b.ring * 8;
+
+        // ALSA plays zeros for regions the application skipped (silence_size = boundary, :493-496).
+        long long gap = b.tx_gap_length[s];
+        if (gap > 0) {
+            long long start = b.tx_gap_start[s];
+            if (gap > (long long)b.ring) { // older than one lap: only the last lap is still in the ring
+                start += gap - (long long)b.ring;
+                gap = (long long)b.ring;
+            }
+            Pack<2> zero;
+            zero.w[0] = zero.w[1] = 0;
+            for (long long i = lane; i < gap; i += 32)
+                st_stream<8>(ring + size_t(uint64_t(start + i) % b.ring) * 8, zero);
+            // A gap of a whole lap or more silences the slots the block is about to take.
+            __syncwarp();
+        }
+
+        // The block may straddle the end of the ring: at most two contiguous spans.
+        const uint64_t offset = uint64_t(at) % b.ring;
+        const uint64_t first_span = (b.ring - offset < b.period) ? b.ring - offset : b.period;
+        BlockDesc d;
+        d.thr2 = b.thr2;
+        d.reserved = 0;
+        d.src = cf32_in + s * b.period * 8;
+        d.dst = ring + offset * 8;
+        d.length = first_span;
+        convert_span<TxCf32>(d, 0, first_span, lane, 32);
+        if (first_span < b.period) {
+            d.src = cf32_in + (s * b.period + first_span) * 8;
+            d.dst = ring;
+            d.length = b.period - first_span;
+            convert_span<TxCf32>(d, 0, d.length, lane, 32);
+        }
+    }
+}
+
+__global__ void bank_advance_kernel(BankState b, long long frames)
+{
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < b.nstreams)
+        b.clock[s] += frames;
+}
+
+} // namespace sx

@@ -7,6 +7,7 @@
 #include "../../include/sxgpu.h"
 
 #include "sx_kernels.cuh"
+#include "sx_bank.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -769,6 +770,254 @@ int sxgpu_convert_loopback(sxgpu_ctx *ctx, const void *d_i2s_in, void *d_cf32, v
     ctx->launches++;
     ctx->frames_rx += length;
     ctx->frames_tx += length;
+    return SXGPU_OK;
+}
+
+// ---- stream bank ------------------------------------------------------------------------
+} // extern "C"
+
+struct sxgpu_bank {
+    sxgpu_ctx *ctx = nullptr;
+    BankState st = {};
+    void *arena = nullptr; // one allocation for every per-stream array
+};
+
+namespace {
+
+template <class T> T *carve(char *&cursor, size_t count)
+{
+    uintptr_t p = (reinterpret_cast<uintptr_t>(cursor) + 255) & ~uintptr_t(255);
+    cursor = reinterpret_cast<char *>(p) + count * sizeof(T);
+    return reinterpret_cast<T *>(p);
+}
+
+cudaStream_t bank_stream(sxgpu_bank *bank, sxgpu_stream stream)
+{
+    return stream ? static_cast<cudaStream_t>(stream) : bank->ctx->stream;
+}
+
+int per_stream_grid(uint32_t nstreams, int block)
+{
+    return int((nstreams + block - 1) / block);
+}
+
+int per_warp_grid(const sxgpu_ctx *ctx, uint32_t nstreams, int block)
+{
+    uint64_t ctas = (uint64_t(nstreams) + block / 32 - 1) / (block / 32);
+    return int(std::min<uint64_t>(ctas, uint64_t(ctx->prop.multiProcessorCount) * 8));
+}
+
+template <class T>
+int copy_out(sxgpu_bank *bank, T *h_dst, const void *d_src, cudaStream_t st)
+{
+    if (!h_dst)
+        return SXGPU_OK;
+    SX_CUDA(bank->ctx, cudaMemcpyAsync(h_dst, d_src, size_t(bank->st.nstreams) * sizeof(T),
+                                       cudaMemcpyDeviceToHost, st));
+    return SXGPU_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int sxgpu_bank_create(sxgpu_ctx *ctx, const sxgpu_bank_config *config, sxgpu_bank **out)
+{
+    if (!ctx || !out)
+        return SXGPU_ERR_INVALID;
+    *out = nullptr;
+    if (!config || config->nstreams == 0)
+        return ctx->invalid("a bank needs at least one stream");
+    if (!(config->sample_rate >= 1.0))
+        return ctx->invalid("sample rate must be at least 1 Hz");
+    SX_CUDA(ctx, cudaSetDevice(ctx->device));
+
+    sxplan::Geometry geo = sxplan::geometry_for_period(config->period);
+    const size_t n = config->nstreams;
+    sxgpu_bank *bank = new sxgpu_bank();
+    bank->ctx = ctx;
+    BankState &b = bank->st;
+    b.nstreams = config->nstreams;
+    b.period = uint32_t(geo.period);
+    b.ring = geo.buffer;
+    b.sample_rate = config->sample_rate;
+    b.thr2 = config->tx_threshold2;
+    b.seed = config->seed;
+
+    size_t bytes = 0;
+    bytes += 3 * (n * sizeof(long long) + 256);                       // clock, rx/tx position
+    bytes += 3 * (n * sizeof(int) + 256) + (n * sizeof(long long) + 256); // results
+    bytes += 4 * (n * sizeof(long long) + 256) + (n * sizeof(BlockDesc) + 256); // plans
+    bytes += n * geo.period * 8 + 256;                                // capture staging
+    bytes += n * geo.buffer * 8 + 256;                                // playback rings
+    cudaError_t e = cudaMalloc(&bank->arena, bytes);
+    if (e != cudaSuccess) {
+        delete bank;
+        return ctx->fail(e, "cudaMalloc(stream bank)");
+    }
+    // Zero everything: counters start at 0 and an untouched ring is silence.
+    e = cudaMemsetAsync(bank->arena, 0, bytes, ctx->stream);
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        cudaFree(bank->arena);
+        delete bank;
+        return ctx->fail(e, "cudaMemset(stream bank)");
+    }
+    char *cur = static_cast<char *>(bank->arena);
+    b.clock = carve<long long>(cur, n);
+    b.rx_position = carve<long long>(cur, n);
+    b.tx_position = carve<long long>(cur, n);
+    b.rx_ret = carve<int>(cur, n);
+    b.rx_flags = carve<int>(cur, n);
+    b.tx_ret = carve<int>(cur, n);
+    b.rx_time_ns = carve<long long>(cur, n);
+    b.rx_first_frame = carve<long long>(cur, n);
+    b.tx_write_position = carve<long long>(cur, n);
+    b.tx_gap_start = carve<long long>(cur, n);
+    b.tx_gap_length = carve<long long>(cur, n);
+    b.rx_blocks = carve<BlockDesc>(cur, n);
+    b.capture_stage = carve<char>(cur, n * geo.period * 8);
+    b.playback_ring = carve<char>(cur, n * geo.buffer * 8);
+    *out = bank;
+    return SXGPU_OK;
+}
+
+int sxgpu_bank_destroy(sxgpu_bank *bank)
+{
+    if (!bank)
+        return SXGPU_ERR_INVALID;
+    cudaSetDevice(bank->ctx->device);
+    cudaDeviceSynchronize();
+    cudaFree(bank->arena);
+    delete bank;
+    return SXGPU_OK;
+}
+
+int sxgpu_bank_ring_frames(sxgpu_bank *bank, uint64_t *ring_frames)
+{
+    if (!bank || !ring_frames)
+        return SXGPU_ERR_INVALID;
+    *ring_frames = bank->st.ring;
+    return SXGPU_OK;
+}
+
+int sxgpu_bank_advance(sxgpu_bank *bank, int64_t frames, sxgpu_stream stream)
+{
+    if (!bank)
+        return SXGPU_ERR_INVALID;
+    sxgpu_ctx *ctx = bank->ctx;
+    if (frames < 0)
+        return ctx->invalid("the sample clock only runs forward");
+    SX_CUDA(ctx, cudaSetDevice(ctx->device));
+    bank_advance_kernel<<<per_stream_grid(bank->st.nstreams, 256), 256, 0, bank_stream(bank, stream)>>>(
+        bank->st, frames);
+    SX_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+    return SXGPU_OK;
+}
+
+int sxgpu_bank_read(sxgpu_bank *bank, void *d_cf32, sxgpu_stream stream)
+{
+    if (!bank)
+        return SXGPU_ERR_INVALID;
+    sxgpu_ctx *ctx = bank->ctx;
+    if (!d_cf32 || reinterpret_cast<uintptr_t>(d_cf32) % 8)
+        return ctx->invalid("CF32 buffer must be 8-byte aligned device memory");
+    SX_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = bank_stream(bank, stream);
+    const BankState &b = bank->st;
+    bank_rx_plan_kernel<<<per_stream_grid(b.nstreams, 256), 256, 0, st>>>(b, static_cast<char *>(d_cf32));
+    bank_capture_kernel<<<per_warp_grid(ctx, b.nstreams, 256), 256, 0, st>>>(b);
+    batch_warp_kernel<RxCf32><<<per_warp_grid(ctx, b.nstreams, 256), 256, 0, st>>>(b.rx_blocks, b.nstreams);
+    SX_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 3;
+    ctx->frames_rx += uint64_t(b.nstreams) * b.period;
+    return SXGPU_OK;
+}
+
+int sxgpu_bank_write(sxgpu_bank *bank, const void *d_cf32, int flags, const long long *d_time_ns,
+                     long long rx_time_offset_ns, sxgpu_stream stream)
+{
+    if (!bank)
+        return SXGPU_ERR_INVALID;
+    sxgpu_ctx *ctx = bank->ctx;
+    if (!d_cf32 || reinterpret_cast<uintptr_t>(d_cf32) % 8)
+        return ctx->invalid("CF32 buffer must be 8-byte aligned device memory");
+    SX_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = bank_stream(bank, stream);
+    const BankState &b = bank->st;
+    bank_tx_plan_kernel<<<per_stream_grid(b.nstreams, 256), 256, 0, st>>>(b, flags, d_time_ns,
+                                                                       rx_time_offset_ns);
+    bank_tx_convert_kernel<<<per_warp_grid(ctx, b.nstreams, 256), 256, 0, st>>>(
+        b, static_cast<const char *>(d_cf32));
+    SX_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 2;
+    ctx->frames_tx += uint64_t(b.nstreams) * b.period;
+    return SXGPU_OK;
+}
+
+int sxgpu_bank_last_read(sxgpu_bank *bank, int32_t *h_ret, int32_t *h_flags, int64_t *h_time_ns,
+                         sxgpu_stream stream)
+{
+    if (!bank)
+        return SXGPU_ERR_INVALID;
+    sxgpu_ctx *ctx = bank->ctx;
+    SX_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = bank_stream(bank, stream);
+    SX_TRY(copy_out(bank, h_ret, bank->st.rx_ret, st));
+    SX_TRY(copy_out(bank, h_flags, bank->st.rx_flags, st));
+    SX_TRY(copy_out(bank, reinterpret_cast<long long *>(h_time_ns), bank->st.rx_time_ns, st));
+    SX_CUDA(ctx, cudaStreamSynchronize(st));
+    return SXGPU_OK;
+}
+
+int sxgpu_bank_last_write(sxgpu_bank *bank, int32_t *h_ret, sxgpu_stream stream)
+{
+    if (!bank)
+        return SXGPU_ERR_INVALID;
+    sxgpu_ctx *ctx = bank->ctx;
+    SX_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = bank_stream(bank, stream);
+    SX_TRY(copy_out(bank, h_ret, bank->st.tx_ret, st));
+    SX_CUDA(ctx, cudaStreamSynchronize(st));
+    return SXGPU_OK;
+}
+
+int sxgpu_bank_positions(sxgpu_bank *bank, int64_t *h_clock, int64_t *h_rx_position,
+                         int64_t *h_tx_position, sxgpu_stream stream)
+{
+    if (!bank)
+        return SXGPU_ERR_INVALID;
+    sxgpu_ctx *ctx = bank->ctx;
+    SX_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = bank_stream(bank, stream);
+    SX_TRY(copy_out(bank, reinterpret_cast<long long *>(h_clock), bank->st.clock, st));
+    SX_TRY(copy_out(bank, reinterpret_cast<long long *>(h_rx_position), bank->st.rx_position, st));
+    SX_TRY(copy_out(bank, reinterpret_cast<long long *>(h_tx_position), bank->st.tx_position, st));
+    SX_CUDA(ctx, cudaStreamSynchronize(st));
+    return SXGPU_OK;
+}
+
+int sxgpu_bank_playback(sxgpu_bank *bank, uint32_t index, int64_t position, size_t nframes,
+                        void *h_i2s, sxgpu_stream stream)
+{
+    if (!bank || !h_i2s)
+        return SXGPU_ERR_INVALID;
+    sxgpu_ctx *ctx = bank->ctx;
+    const BankState &b = bank->st;
+    if (index >= b.nstreams || position < 0 || nframes > b.ring)
+        return ctx->invalid("playback window outside the stream's ring");
+    SX_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = bank_stream(bank, stream);
+    const char *ring = b.playback_ring + size_t(index) * b.ring * 8;
+    uint64_t offset = uint64_t(position) % b.ring;
+    size_t first = std::min<size_t>(nframes, b.ring - offset);
+    SX_CUDA(ctx, cudaMemcpyAsync(h_i2s, ring + offset * 8, first * 8, cudaMemcpyDeviceToHost, st));
+    if (first < nframes)
+        SX_CUDA(ctx, cudaMemcpyAsync(static_cast<char *>(h_i2s) + first * 8, ring, (nframes - first) * 8,
+                                     cudaMemcpyDeviceToHost, st));
+    SX_CUDA(ctx, cudaStreamSynchronize(st));
     return SXGPU_OK;
 }
 

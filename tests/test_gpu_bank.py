@@ -1,0 +1,153 @@
+"""-m gpu: the HBM-resident stream bank (sxgpu_bank_*) against S independent driver=sx devices.
+
+BASELINE config 4: S streams x (readStream 256 -> identity DSP -> writeStream 256 with HAS_TIME at
+rx.timeNs + latency).  The comparator is the unmodified reference driver when oracle/_ref is
+present, else the product's own host-side device (itself held to the reference's golden traces in
+test_gpu_stream.py).  Everything an application could observe must agree: return codes, flags,
+timestamps, CF32 sample bits, and the I2S words left in each stream's playback ring."""
+import numpy as np
+import pytest
+
+import sxstream
+import sxtest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+HAS_TIME = sxstream.HAS_TIME
+
+
+def comparator():
+    from sxxcvr_b200 import _build
+    if sxstream.REF_LIB.exists():
+        return sxstream.Harness(sxstream.REF_LIB), "reference"
+    _build.build_soapy_module()
+    return sxstream.Harness(sxstream.PRODUCT_LIB), "product-device"
+
+
+# (advance_before, write_mode, offset_ns): write_mode in {"rx+", "untimed", "none"}
+def script(rate):
+    lat = int(round(768 * 1e9 / rate))
+    s = [(0, "rx+", lat)] * 6
+    s += [(70000, "rx+", lat)]                  # RX overrun; the TX side is now late as well
+    s += [(0, "rx+", lat)] * 3
+    s += [(0, "rx+", -1_000_000_000)]           # a burst timed a second in the past: dropped whole
+    s += [(0, "rx+", lat)] * 2
+    s += [(100000, "untimed", 0)]               # untimed write after a stall: underrun forward
+    s += [(0, "untimed", 0)] * 2
+    s += [(0, "rx+", int(2.5e9))]               # further ahead than the ring: forward-and-wait
+    s += [(0, "none", 0), (0, "rx+", lat), (5, "rx+", lat)]
+    return s
+
+
+@pytest.mark.parametrize("nstreams,period,rate,threshold", [
+    (3, 256, 75000.0, "0"),            # linear_repeater.py settings
+    (5, 1000, 300000.0, "0.001"),      # ring of 65000 frames: not a power of two, odd wrap points
+    (2, 4096, 32.0e6 / 1536, "0.5"),   # non-integer rate
+    (4, 3, 600000.0, "0"),             # odd ring (65535), tiny blocks: frame-wide accesses only
+])
+def test_bank_matches_independent_devices(ctx, nstreams, period, rate, threshold):
+    from sxxcvr_b200 import Bank
+    h, kind = comparator()
+    clock_arg = ", clock=32e6" if abs(rate * 1536 - 32.0e6) < 1 else ""
+    steps = script(rate)
+    thr2 = float(np.float32(float(threshold)) * np.float32(float(threshold)))
+
+    # ---- comparator: S separate devices driven one call at a time -------------------------------
+    devs = []
+    for s in range(nstreams):
+        d = h.device("driver=sx" + clock_arg)
+        d.set_rate(rate)
+        h.lib.sx_alsa_set_capture_seed(d.cap, sxtest.SEED + s)
+        rx = d.setup(sxstream.RX, args=f"period={period}")
+        tx = d.setup(sxstream.TX, args=f"threshold={threshold}, period={period}")
+        assert d.activate(rx) == 0 and d.activate(tx) == 0
+        devs.append((d, rx, tx))
+    want = []
+    for adv, mode, off in steps:
+        row = []
+        for d, rx, tx in devs:
+            if adv:
+                d.advance(adv)
+            r, fl, t, buf = d.read(rx, period)
+            w = None
+            if mode == "rx+":
+                w = d.write(tx, buf, period, HAS_TIME, t + off)
+            elif mode == "untimed":
+                w = d.write(tx, buf, period)
+            row.append((r, fl, t, buf.copy(), w, d.pointers()))
+        want.append(row)
+
+    # ---- the bank: every stream per launch ------------------------------------------------------
+    with Bank(ctx, nstreams, period, rate, thr2, sxtest.SEED) as bank:
+        assert bank.ring == 65536 // period * period
+        cf = torch.empty(nstreams * period * 2, dtype=torch.float32, device="cuda")
+        for i, (adv, mode, off) in enumerate(steps):
+            if adv:
+                bank.advance(adv)
+            bank.read(cf.data_ptr())
+            ret, fl, t = bank.last_read()
+            got_cf = cf.cpu().numpy().reshape(nstreams, 2 * period)
+            if mode == "rx+":
+                bank.write(cf.data_ptr(), HAS_TIME, None, off)
+            elif mode == "untimed":
+                bank.write(cf.data_ptr(), 0, None, 0)
+            wret = bank.last_write() if mode != "none" else None
+            clock, rxp, txp = bank.positions()
+            for s in range(nstreams):
+                r_, fl_, t_, buf_, w_, ptrs = want[i][s]
+                assert (int(ret[s]), int(fl[s]), int(t[s])) == (r_, fl_, t_), (kind, i, s)
+                assert np.array_equal(got_cf[s].view(np.uint32), buf_.view(np.uint32)), (kind, i, s)
+                if w_ is not None:
+                    assert int(wret[s]) == w_, (kind, i, s)
+                # stub pointers: [capture hw, capture appl, playback hw, playback appl]
+                assert (int(clock[s]), int(rxp[s]), int(clock[s]), int(txp[s])) == tuple(ptrs), (kind, i, s)
+
+        # ---- what is left in the playback rings --------------------------------------------------
+        clock, rxp, txp = bank.positions()
+        for s, (d, rx, tx) in enumerate(devs):
+            end = int(txp[s])
+            start = max(0, end - bank.ring)
+            n = end - start
+            ring = bank.playback(s, start, n)
+            ref = d.sink(start, n)
+            assert np.array_equal(ring, ref), (kind, s, int(np.flatnonzero(ring != ref)[0]))
+            assert np.count_nonzero(ref) > 0
+    for d, _, _ in devs:
+        d.close()
+
+
+def test_bank_constant_latency_at_every_rate(ctx):
+    """at every legal rate the TX block lands exactly 768 frames after the
+    RX block it answers, for every stream, forever."""
+    from sxxcvr_b200 import Bank
+    for rate in sxtest.RATES:
+        lat = int(round(768 * 1e9 / rate))
+        with Bank(ctx, 64, 256, rate, 0.0, 1) as bank:
+            cf = torch.empty(64 * 512, dtype=torch.float32, device="cuda")
+            for k in range(20):
+                bank.read(cf.data_ptr())
+                bank.write(cf.data_ptr(), HAS_TIME, None, lat)
+                _, rxp, txp = bank.positions()
+                assert (rxp == 256 * (k + 1)).all() and (txp == 256 * k + 768 + 256).all(), (rate, k)
+
+
+def test_bank_large_and_values_against_oracle(ctx, oracle):
+    from sxxcvr_b200 import Bank
+    S, P = 4096, 256
+    with Bank(ctx, S, P, 75000.0, 0.0, 77) as bank:
+        cf = torch.empty(S * P * 2, dtype=torch.float32, device="cuda")
+        for _ in range(3):
+            bank.read(cf.data_ptr())
+            bank.write(cf.data_ptr(), HAS_TIME, None, 10_240_000)
+        got = cf.cpu().numpy().reshape(S, 2 * P)
+        for s in (0, 1, 2047, 4095):
+            frames = sxtest.synth_frames(oracle, 2 * P, P, seed=77 + s)
+            want_cf = sxtest.oracle_rx(oracle, frames)
+            assert np.array_equal(got[s].view(np.uint32), want_cf.view(np.uint32))
+            ring = bank.playback(s, 2 * P + 768, P)
+            assert np.array_equal(ring, sxtest.oracle_tx(oracle, want_cf, 0.0))
+            assert not bank.playback(s, 0, 768).any()          # silence before the first burst
+        ret, fl, t = bank.last_read()
+        assert (ret == P).all() and (fl == HAS_TIME).all() and (t == 6_826_667).all()
