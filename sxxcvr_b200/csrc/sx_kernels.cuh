@@ -611,14 +611,34 @@ __device__ __forceinline__ void stats_word(StatsAcc &s, uint32_t w, uint64_t idx
     s.rail += (top == 0x7FFFFFFCu || top == 0x80000000u) ? 1 : 0;
 }
 
-// words must be 4-byte aligned; base_index is the global index of words[0].
+// words must be 4-byte aligned; base_index is the global index of words[0].  The body runs
+// on 128-bit loads; up to three leading and trailing words are taken one at a time.
 __global__ void stats_kernel(const uint32_t *__restrict__ words, uint64_t nwords,
                              uint64_t base_index, StatsAcc *acc)
 {
     StatsAcc s = {0, 0, 0, 0, 0, 0};
-    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nwords;
-         i += uint64_t(gridDim.x) * blockDim.x)
+    const uint64_t tid = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const uint64_t nthreads = uint64_t(gridDim.x) * blockDim.x;
+
+    uint64_t head = ((16 - (reinterpret_cast<uintptr_t>(words) & 15)) & 15) / 4;
+    if (head > nwords)
+        head = nwords;
+    const uint64_t nvec = (nwords - head) / 4;
+    const uint4 *vec = reinterpret_cast<const uint4 *>(words + head);
+    for (uint64_t v = tid; v < nvec; v += nthreads) {
+        uint4 q = vec[v];
+        uint64_t i = base_index + head + 4 * v;
+        stats_word(s, q.x, i);
+        stats_word(s, q.y, i + 1);
+        stats_word(s, q.z, i + 2);
+        stats_word(s, q.w, i + 3);
+    }
+    const uint64_t tail_start = head + 4 * nvec;
+    const uint64_t nedge = head + (nwords - tail_start);
+    if (tid < nedge) {
+        uint64_t i = tid < head ? tid : tail_start + (tid - head);
         stats_word(s, words[i], base_index + i);
+    }
 
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {

@@ -227,7 +227,9 @@ int launch_bulk(sxgpu_ctx *ctx, const char *src, const char *dst_c, uint64_t tot
     if (!found || total < head + G)
         return SXGPU_OK; // caller falls back to the vector kernel
 
-    BulkShape shape = {int(ctx->bulk_tile ? ctx->bulk_tile : 2048),
+    // Measured (profiles/r01_summary.md): 2048-frame tiles x 4 stages for large blocks; below
+    // 2^24 frames the 1024-frame tile spreads the fewer tiles over more SMs.
+    BulkShape shape = {int(ctx->bulk_tile ? ctx->bulk_tile : (total >= (uint64_t(1) << 24) ? 2048 : 1024)),
                        int(ctx->bulk_stages ? ctx->bulk_stages : 4)};
     BulkKernel k = bulk_kernel<Op>(shape);
     if (!k)
