@@ -156,29 +156,72 @@ def workload_config(args, per_gpu_frames):
 # Clock sampling during the timed region
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
-    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """SM clock, power and throttle reasons of one GPU, sampled in-process through NVML every
+    few milliseconds between start() and stop() (the timed region lasts tens of milliseconds,
+    too short for `nvidia-smi -lms`, which is kept as the fallback)."""
 
-    def __init__(self, gpu_index: int):
-        self.gpu_index, self.proc, self.lines = gpu_index, None, []
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
+    SMI_FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+                  "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                  "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int, pci_bus_id: str | None = None, period_s: float = 0.002):
+        self.gpu_index, self.period_s = gpu_index, period_s
+        self.samples, self.power, self.mask = [], [], 0
+        self.stop_flag = threading.Event()
+        self.thread = self.proc = self.nvml = self.handle = None
+        self.sm_max = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            try:
+                self.handle = pynvml.nvmlDeviceGetHandleByPciBusId(pci_bus_id.encode()) if pci_bus_id else None
+            except Exception:
+                self.handle = None
+            if self.handle is None:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                self.power.append(n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0)
+                self.mask |= int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+            except Exception:
+                pass
+            self.stop_flag.wait(self.period_s)
 
     def start(self):
+        if self.nvml:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
+            self.lines = []
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.SMI_FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
                  "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
+            threading.Thread(target=lambda: [self.lines.append(l.strip()) for l in self.proc.stdout], daemon=True).start()
         except OSError:
             self.proc = None
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
-
     def stop(self):
+        if self.nvml:
+            self.stop_flag.set()
+            self.thread.join(timeout=1)
+            reasons = sorted(name for bit, name in self.REASONS.items() if self.mask & bit)
+            return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.sm_max,
+                    "sm_min_mhz": min(self.samples) if self.samples else None,
+                    "power_w_max": max(self.power) if self.power else None, "samples": len(self.samples),
+                    "reasons": reasons, "source": "nvml"}
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no nvml, no nvidia-smi"], "samples": 0}
         time.sleep(0.15)
         self.proc.terminate()
         try:
@@ -201,7 +244,8 @@ class ClockSampler:
                 if state.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons),
+                "source": "nvidia-smi"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -266,7 +310,11 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
     barrier()
 
     # ---- timed region: K steps, an event between every launch ---------------------------------
-    sampler = ClockSampler(local_rank)
+    props = torch.cuda.get_device_properties(local_rank)
+    bus = None
+    if all(hasattr(props, a) for a in ("pci_domain_id", "pci_bus_id", "pci_device_id")):
+        bus = f"{props.pci_domain_id:08x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+    sampler = ClockSampler(local_rank, bus)
     sampler.start()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 1)]
     launches0 = ctx.counter("launches")
