@@ -171,7 +171,11 @@ int sxgpu_bank_ring_frames(sxgpu_bank *bank, uint64_t *ring_frames);
  * are at the reference's call sites (buffer_rx/buffs[0], SoapySX.cpp:957, :1090).  The
  * host->device copy, the kernel and the device->host copy all happen inside the call,
  * pipelined in chunks over the context's ring.  Pinned (cudaHostAlloc / registered)
- * buffers are used in place; pageable buffers are bounced through pinned staging. */
+ * buffers are used in place; pageable buffers are bounced through pinned staging; up to
+ * 2^18 frames of pinned memory are converted by one kernel that reads and writes the host
+ * buffers across PCIe itself.  Either side may also be DEVICE memory of the context's GPU
+ * (a torch / cupy buffer handed to readStream or writeStream): that side's copy is skipped
+ * and the kernel uses the buffer directly. */
 int sxgpu_convert_rx_buffer_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset,
                                  void *h_dest, size_t dest_offset, size_t length);
 int sxgpu_convert_tx_buffer_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset,

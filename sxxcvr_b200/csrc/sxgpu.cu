@@ -338,20 +338,26 @@ int convert_entry(sxgpu_ctx *ctx, const void *d_src, size_t src_offset, void *d_
 // Host-buffer pipeline
 // ---------------------------------------------------------------------------------------
 struct HostPtrInfo {
-    bool pinned = false;
-    void *device_alias = nullptr; // device-visible address of the same memory, if mapped
+    bool pinned = false;          // page-locked host memory: copy engines can use it in place
+    bool on_device = false;       // device (or managed) memory: no PCIe copy needed on this side
+    bool foreign_device = false;  // device memory of another GPU
+    void *device_alias = nullptr; // address a kernel on this GPU can use for the same memory
 };
 
-HostPtrInfo classify_host_pointer(const void *p)
+HostPtrInfo classify_pointer(const sxgpu_ctx *ctx, const void *p)
 {
     HostPtrInfo info;
     cudaPointerAttributes attr;
     if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
         cudaGetLastError();
-        return info;
+        return info; // unknown to CUDA: pageable host memory
     }
     if (attr.type == cudaMemoryTypeHost) {
         info.pinned = true;
+        info.device_alias = attr.devicePointer;
+    } else if (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged) {
+        info.on_device = true;
+        info.foreign_device = attr.type == cudaMemoryTypeDevice && attr.device != ctx->device;
         info.device_alias = attr.devicePointer;
     }
     return info;
@@ -429,35 +435,41 @@ int convert_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset, void *h_d
     std::lock_guard<std::mutex> lock(ctx->host_mutex);
     SX_CUDA(ctx, cudaSetDevice(ctx->device));
 
-    HostPtrInfo si = classify_host_pointer(src), di = classify_host_pointer(dst);
+    HostPtrInfo si = classify_pointer(ctx, src), di = classify_pointer(ctx, dst);
+    if (si.foreign_device || di.foreign_device)
+        return ctx->invalid("sample buffer lives on another GPU than the context");
+    const uint64_t in_bytes = si.on_device ? 0 : length * 8, out_bytes = di.on_device ? 0 : length * 8;
 
-    // Zero-copy: the kernel reads and writes pinned host memory across PCIe directly.  One
-    // launch and no staging -- the right shape for period-sized blocks (256 frames).
-    bool zero_copy = si.device_alias && di.device_alias &&
-                     (ctx->host_mode == 2 ||
-                      (ctx->host_mode == 0 && length <= size_t(ctx->zero_copy_max_frames)));
-    if (zero_copy) {
+    // One kernel, no staging, when both sides are visible to the GPU and the block is either
+    // already on the device or small: a period-sized block (256 frames) in pinned host memory
+    // is read and written across PCIe by the kernel itself.
+    bool direct = si.device_alias && di.device_alias &&
+                  ((si.on_device && di.on_device) || ctx->host_mode == 2 ||
+                   (ctx->host_mode == 0 && length <= size_t(ctx->zero_copy_max_frames)));
+    if (direct) {
         if (!ctx->s_comp)
             SX_TRY(ensure_ring(ctx, 0, false, false));
-        SX_TRY(launch_convert<Op>(ctx, si.device_alias, di.device_alias, length, thr2, 1,
-                                  ctx->s_comp));
+        int64_t v = (si.on_device && di.on_device) ? variant : 1;
+        SX_TRY(launch_convert<Op>(ctx, si.device_alias, di.device_alias, length, thr2, v, ctx->s_comp));
         SX_CUDA(ctx, cudaStreamSynchronize(ctx->s_comp));
-        ctx->h2d_bytes += length * 8;
-        ctx->d2h_bytes += length * 8;
+        ctx->h2d_bytes += in_bytes;
+        ctx->d2h_bytes += out_bytes;
         return SXGPU_OK;
     }
 
+    // Copy-engine pipeline over the ring.  A side that is device memory skips its copy: the
+    // kernel reads the caller's device buffer, or writes into it, directly.
     size_t chunk = std::min<size_t>(length, pick_chunk_frames(ctx, length));
-    SX_TRY(ensure_ring(ctx, chunk, !si.pinned, !di.pinned));
+    SX_TRY(ensure_ring(ctx, chunk, !si.pinned && !si.on_device, !di.pinned && !di.on_device));
     HostRing &r = ctx->ring;
     chunk = std::min(chunk, r.chunk_frames);
     const size_t nchunks = (length + chunk - 1) / chunk;
 
     auto chunk_len = [&](size_t i) { return std::min(chunk, length - i * chunk); };
-    auto retire = [&](size_t i) -> int { // chunk i's D2H has been issued into slot i % K
+    auto retire = [&](size_t i) -> int { // chunk i's last operation was issued into slot i % K
         int slot = int(i % kRingSlots);
         SX_CUDA(ctx, cudaEventSynchronize(r.done[slot]));
-        if (!di.pinned)
+        if (!di.pinned && !di.on_device)
             std::memcpy(dst + i * chunk * 8, r.h_out[slot], chunk_len(i) * 8);
         return SXGPU_OK;
     };
@@ -465,28 +477,42 @@ int convert_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset, void *h_d
     for (size_t i = 0; i < nchunks; i++) {
         int slot = int(i % kRingSlots);
         if (i >= size_t(kRingSlots))
-            SX_TRY(retire(i - kRingSlots)); // frees d_in/d_out/h_in/h_out of this slot
+            SX_TRY(retire(i - kRingSlots)); // frees the slot's device and bounce buffers
         size_t n = chunk_len(i), bytes = n * 8;
-        const void *from = src + i * chunk * 8;
-        if (!si.pinned) {
-            std::memcpy(r.h_in[slot], from, bytes);
-            from = r.h_in[slot];
+
+        const void *kernel_in = r.d_in[slot];
+        if (si.on_device) {
+            kernel_in = static_cast<const char *>(si.device_alias) + i * chunk * 8;
+        } else {
+            const void *from = src + i * chunk * 8;
+            if (!si.pinned) {
+                std::memcpy(r.h_in[slot], from, bytes);
+                from = r.h_in[slot];
+            }
+            SX_CUDA(ctx, cudaMemcpyAsync(r.d_in[slot], from, bytes, cudaMemcpyHostToDevice, ctx->s_h2d));
+            SX_CUDA(ctx, cudaEventRecord(r.copied_in[slot], ctx->s_h2d));
+            SX_CUDA(ctx, cudaStreamWaitEvent(ctx->s_comp, r.copied_in[slot], 0));
         }
-        SX_CUDA(ctx, cudaMemcpyAsync(r.d_in[slot], from, bytes, cudaMemcpyHostToDevice, ctx->s_h2d));
-        SX_CUDA(ctx, cudaEventRecord(r.copied_in[slot], ctx->s_h2d));
-        SX_CUDA(ctx, cudaStreamWaitEvent(ctx->s_comp, r.copied_in[slot], 0));
-        SX_TRY(launch_convert<Op>(ctx, r.d_in[slot], r.d_out[slot], n, thr2, variant, ctx->s_comp));
-        SX_CUDA(ctx, cudaEventRecord(r.converted[slot], ctx->s_comp));
-        SX_CUDA(ctx, cudaStreamWaitEvent(ctx->s_d2h, r.converted[slot], 0));
-        void *to = di.pinned ? static_cast<void *>(dst + i * chunk * 8) : r.h_out[slot];
-        SX_CUDA(ctx, cudaMemcpyAsync(to, r.d_out[slot], bytes, cudaMemcpyDeviceToHost, ctx->s_d2h));
-        SX_CUDA(ctx, cudaEventRecord(r.done[slot], ctx->s_d2h));
+
+        void *kernel_out = di.on_device ? static_cast<void *>(static_cast<char *>(di.device_alias) + i * chunk * 8)
+                                        : r.d_out[slot];
+        SX_TRY(launch_convert<Op>(ctx, kernel_in, kernel_out, n, thr2, variant, ctx->s_comp));
+
+        if (di.on_device) {
+            SX_CUDA(ctx, cudaEventRecord(r.done[slot], ctx->s_comp));
+        } else {
+            SX_CUDA(ctx, cudaEventRecord(r.converted[slot], ctx->s_comp));
+            SX_CUDA(ctx, cudaStreamWaitEvent(ctx->s_d2h, r.converted[slot], 0));
+            void *to = di.pinned ? static_cast<void *>(dst + i * chunk * 8) : r.h_out[slot];
+            SX_CUDA(ctx, cudaMemcpyAsync(to, r.d_out[slot], bytes, cudaMemcpyDeviceToHost, ctx->s_d2h));
+            SX_CUDA(ctx, cudaEventRecord(r.done[slot], ctx->s_d2h));
+        }
     }
     for (size_t i = (nchunks > size_t(kRingSlots) ? nchunks - kRingSlots : 0); i < nchunks; i++)
         SX_TRY(retire(i));
 
-    ctx->h2d_bytes += length * 8;
-    ctx->d2h_bytes += length * 8;
+    ctx->h2d_bytes += in_bytes;
+    ctx->d2h_bytes += out_bytes;
     return SXGPU_OK;
 }
 

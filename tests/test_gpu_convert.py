@@ -318,6 +318,34 @@ def test_host_buffer_entry_points(ctx, oracle, pinned, mode, nframes):
         ctx.set_option("host_chunk_frames", 0)
 
 
+@pytest.mark.parametrize("nframes", [256, (1 << 19) + 3, (1 << 22) + 1])
+def test_host_entry_points_accept_device_memory_on_either_side(ctx, oracle, nframes):
+    """A torch/cupy buffer handed to readStream/writeStream: that side's PCIe copy is skipped."""
+    words = sxtest.rx_uniform(nframes, seed=3)
+    want = sxtest.oracle_rx(oracle, words)
+    host_in = torch.from_numpy(words).pin_memory()
+    dev_in = host_in.cuda()
+    dev_out = torch.zeros(2 * nframes, dtype=torch.float32, device="cuda")
+    host_out = torch.zeros(2 * nframes, dtype=torch.float32).pin_memory()
+    pageable_out = torch.zeros(2 * nframes, dtype=torch.float32)
+    h2d0, d2h0 = ctx.counter("h2d_bytes"), ctx.counter("d2h_bytes")
+    ctx.convert_rx_buffer_host(host_in.data_ptr(), 0, dev_out.data_ptr(), 0, nframes)      # host -> device
+    assert np.array_equal(bits(host(dev_out)), bits(want))
+    assert (ctx.counter("h2d_bytes") - h2d0, ctx.counter("d2h_bytes") - d2h0) == (8 * nframes, 0)
+    ctx.convert_rx_buffer_host(dev_in.data_ptr(), 0, host_out.data_ptr(), 0, nframes)      # device -> pinned host
+    assert np.array_equal(bits(host_out.numpy()), bits(want))
+    ctx.convert_rx_buffer_host(dev_in.data_ptr(), 0, pageable_out.data_ptr(), 0, nframes)  # device -> pageable host
+    assert np.array_equal(bits(pageable_out.numpy()), bits(want))
+    dev_out.zero_()
+    ctx.convert_rx_buffer_host(dev_in.data_ptr(), 0, dev_out.data_ptr(), 0, nframes)       # device -> device
+    assert np.array_equal(bits(host(dev_out)), bits(want))
+    f = sxtest.tx_uniform(nframes, seed=4)
+    dev_f = torch.from_numpy(f).cuda()
+    out_i = torch.zeros(2 * nframes, dtype=torch.int32).pin_memory()
+    ctx.convert_tx_buffer_host(dev_f.data_ptr(), 0, out_i.data_ptr(), 0, nframes, sxtest.THR2_DEFAULT)
+    assert np.array_equal(out_i.numpy(), sxtest.oracle_tx(oracle, f, sxtest.THR2_DEFAULT))
+
+
 def test_full_size_block_by_properties(ctx, oracle):
     """BASELINE config 5 size (2^27 frames = 1 GiB in): too big for the scalar oracle in a test,
     so check size-independent properties: the checksum of the output equals the checksum of

@@ -118,3 +118,25 @@ def test_rx_and_tx_threads_run_concurrently(product):
             last = t
         th.join()
         assert not errors
+
+
+def test_readstream_into_a_device_buffer_and_writestream_from_one(product, oracle):
+    """The caller's buffs[0] may be device memory (a torch tensor): same values, no D2H/H2D."""
+    import torch
+    with product.device() as d:
+        d.set_rate(300000.0)
+        rx, tx = d.setup(sxstream.RX), d.setup(sxstream.TX, args="threshold=0")
+        d.activate(rx), d.activate(tx)
+        n = 4096
+        dev = torch.zeros(2 * n, dtype=torch.float32, device="cuda")
+        import ctypes as C
+        flags, t = C.c_int(-1), C.c_longlong(-1)
+        ret = product.lib.sxh_read(d.p, rx, dev.data_ptr(), n, C.byref(flags), C.byref(t), 100000)
+        assert (ret, flags.value, t.value) == (n, sxstream.HAS_TIME, 0)
+        want = sxtest.oracle_rx(oracle, sxtest.synth_frames(oracle, 0, n))
+        assert np.array_equal(dev.cpu().numpy().view(np.uint32), want.view(np.uint32))
+        f = C.c_int(sxstream.HAS_TIME)
+        when = t.value + 20_000_000
+        assert product.lib.sxh_write(d.p, tx, dev.data_ptr(), n, C.byref(f), when, 100000) == n
+        pos = product.lib.sxh_time_ns_to_ticks(when, 300000.0)
+        assert np.array_equal(d.sink(pos, n), sxtest.oracle_tx(oracle, want, 0.0))
