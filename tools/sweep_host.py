@@ -58,6 +58,8 @@ def main():
     for lg in (22, 24, args.max_log2):
         n = 1 << lg
         run("pinned", n, pin_src, pin_dst, host_mode=2)
+        run("pinned", n, pin_src, pin_dst, host_mode=0, host_chunk_frames=0)      # the defaults
+        run("pinned", n, pin_src, pin_dst, host_mode=1, host_chunk_frames=0)      # ramped schedule, forced CE
         for chunk_lg in (16, 17, 18, 19, 20, 21, 22):
             run("pinned", n, pin_src, pin_dst, host_mode=1, host_chunk_frames=1 << chunk_lg)
     for lg in (8, 16, 20, 24):
