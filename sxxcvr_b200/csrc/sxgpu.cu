@@ -440,18 +440,29 @@ int convert_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset, void *h_d
         return ctx->invalid("sample buffer lives on another GPU than the context");
     const uint64_t in_bytes = si.on_device ? 0 : length * 8, out_bytes = di.on_device ? 0 : length * 8;
 
-    // One kernel, no staging, when both sides are visible to the GPU and the block is either
-    // already on the device or small: a period-sized block (256 frames) in pinned host memory
-    // is read and written across PCIe by the kernel itself.
-    bool direct = si.device_alias && di.device_alias &&
-                  ((si.on_device && di.on_device) || ctx->host_mode == 2 ||
-                   (ctx->host_mode == 0 && length <= size_t(ctx->zero_copy_max_frames)));
-    if (direct) {
-        if (!ctx->s_comp)
-            SX_TRY(ensure_ring(ctx, 0, false, false));
-        int64_t v = (si.on_device && di.on_device) ? variant : 1;
-        SX_TRY(launch_convert<Op>(ctx, si.device_alias, di.device_alias, length, thr2, v, ctx->s_comp));
+    // One kernel, no queued copies, when the block is already on the device or is small: a
+    // period-sized block (256 frames) in pinned host memory is read and written across PCIe by
+    // the kernel itself.  Small pageable buffers take the same route through a pinned bounce
+    // slot (one memcpy each), which is cheaper than three queued operations.
+    const bool both_on_device = si.on_device && di.on_device;
+    const bool small = ctx->host_mode == 2 ||
+                       (ctx->host_mode == 0 && length <= size_t(ctx->zero_copy_max_frames));
+    if (both_on_device || small) {
+        const bool bounce_in = !si.device_alias, bounce_out = !di.device_alias;
+        SX_TRY(ensure_ring(ctx, (bounce_in || bounce_out) ? length : 0, bounce_in, bounce_out));
+        const void *kernel_in = si.device_alias;
+        void *kernel_out = di.device_alias;
+        if (bounce_in) {
+            std::memcpy(ctx->ring.h_in[0], src, length * 8);
+            kernel_in = ctx->ring.h_in[0]; // pinned memory is device-addressable at the same address (UVA)
+        }
+        if (bounce_out)
+            kernel_out = ctx->ring.h_out[0];
+        SX_TRY(launch_convert<Op>(ctx, kernel_in, kernel_out, length, thr2, both_on_device ? variant : 1,
+                                  ctx->s_comp));
         SX_CUDA(ctx, cudaStreamSynchronize(ctx->s_comp));
+        if (bounce_out)
+            std::memcpy(dst, ctx->ring.h_out[0], length * 8);
         ctx->h2d_bytes += in_bytes;
         ctx->d2h_bytes += out_bytes;
         return SXGPU_OK;
