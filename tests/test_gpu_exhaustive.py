@@ -41,6 +41,7 @@ def test_rx_every_possible_word(ctx, oracle, nthreads):
     for c in range(NCHUNKS):
         # chunk c holds the words c*CHUNK .. (c+1)*CHUNK-1 taken as unsigned 32-bit patterns
         words_dev.copy_(((base + c * CHUNK + 2**31) % 2**32 - 2**31).to(torch.int32))
+        torch.cuda.synchronize()      # the context's stream does not order after torch's default stream
         ctx.convert_rx_buffer(words_dev.data_ptr(), 0, out_dev.data_ptr(), 0, CHUNK // 2)
         ctx.stream_sync()
         words = words_dev.cpu().numpy()
@@ -71,6 +72,7 @@ def test_tx_every_possible_float(ctx, oracle, nthreads, slot, other, thr2):
     for c in range(NCHUNKS):
         bits = ((base + c * CHUNK + 2**31) % 2**32 - 2**31).to(torch.int32)
         pairs[:, sweep_col] = bits.view(torch.float32)
+        torch.cuda.synchronize()
         ctx.convert_tx_buffer(f_dev.data_ptr(), 0, out_dev.data_ptr(), 0, nframes, thr2)
         ctx.stream_sync()
         f = f_dev.cpu().numpy()
