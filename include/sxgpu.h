@@ -182,6 +182,13 @@ int sxgpu_convert_tx_buffer_host(sxgpu_ctx *ctx, const void *h_src, size_t src_o
                                  void *h_dest, size_t dest_offset, size_t length,
                                  float tx_threshold2);
 
+/* EXTENSION (no reference behaviour): the CS16 conversions with host buffers. */
+int sxgpu_convert_rx_buffer_cs16_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset,
+                                      void *h_dest, size_t dest_offset, size_t length);
+int sxgpu_convert_tx_buffer_cs16_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset,
+                                      void *h_dest, size_t dest_offset, size_t length,
+                                      float tx_threshold2);
+
 /* ---- statistics (off the hot path) ------------------------------------------------------- */
 
 /* Order-sensitive checksum and flag counts over 32-bit words; every field is a sum mod 2^64

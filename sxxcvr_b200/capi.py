@@ -73,6 +73,8 @@ SIGNATURES = {
     "sxgpu_bank_ring_frames": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "sxgpu_convert_rx_buffer_host": (C.c_int, [_P, _P, _S, _P, _S, _S]),
     "sxgpu_convert_tx_buffer_host": (C.c_int, [_P, _P, _S, _P, _S, _S, _F]),
+    "sxgpu_convert_rx_buffer_cs16_host": (C.c_int, [_P, _P, _S, _P, _S, _S]),
+    "sxgpu_convert_tx_buffer_cs16_host": (C.c_int, [_P, _P, _S, _P, _S, _S, _F]),
     "sxgpu_stats_words": (C.c_int, [_P, _P, _S, C.c_uint64, C.POINTER(Stats), _P]),
     "sxgpu_synth_frames": (C.c_int, [_P, _P, C.c_uint64, _S, C.c_uint64, _P]),
     "sxgpu_malloc": (C.c_int, [_P, C.POINTER(_P), _S]),
@@ -181,6 +183,14 @@ class Context:
     def convert_tx_buffer_host(self, h_src, src_offset, h_dest, dest_offset, length, tx_threshold2):
         self.check(self.lib.sxgpu_convert_tx_buffer_host(self.handle, h_src, src_offset, h_dest, dest_offset, length,
                                                          tx_threshold2), "sxgpu_convert_tx_buffer_host")
+
+    def convert_rx_buffer_cs16_host(self, h_src, src_offset, h_dest, dest_offset, length):
+        self.check(self.lib.sxgpu_convert_rx_buffer_cs16_host(self.handle, h_src, src_offset, h_dest, dest_offset,
+                                                              length), "sxgpu_convert_rx_buffer_cs16_host")
+
+    def convert_tx_buffer_cs16_host(self, h_src, src_offset, h_dest, dest_offset, length, tx_threshold2):
+        self.check(self.lib.sxgpu_convert_tx_buffer_cs16_host(self.handle, h_src, src_offset, h_dest, dest_offset,
+                                                              length, tx_threshold2), "sxgpu_convert_tx_buffer_cs16_host")
 
     # -- statistics, synthetic source -----------------------------------------------------------
     def stats_words(self, d_words, nwords, base_index=0, stream=None):

@@ -182,6 +182,7 @@ SoapySXB200::SoapySXB200(const SoapySDR::Kwargs &args)
     // With no SX1255 to probe, start from what the reference concludes when its clock
     // detection is inconclusive: 38.4 MHz (SoapySX.cpp:656-659).  clock=32e6 selects the
     // other board variant.  The initial rate is masterClock/256 (:662).
+    cs16_enabled_ = kwarg(args, "cs16", "0") == "1";
     master_clock_ = std::stod(kwarg(args, "clock", "38.4e6"));
     sample_rate_ = master_clock_ / 256.0;
     antenna_[SOAPY_SDR_RX] = "RX";
@@ -233,7 +234,11 @@ SoapySDR::Kwargs SoapySXB200::getHardwareInfo() const
 // ---------------------------------------------------------------------------------------
 std::vector<std::string> SoapySXB200::getStreamFormats(const int, const size_t) const
 {
-    return std::vector<std::string>{SOAPY_SDR_CF32}; // reference :1610-1616
+    // Reference :1610-1616 offers CF32 only.  CS16 is an extension with no reference behaviour
+    // (DESIGN.md), listed only when the device was opened with cs16=1.
+    if (cs16_enabled_)
+        return std::vector<std::string>{SOAPY_SDR_CF32, SOAPY_SDR_CS16};
+    return std::vector<std::string>{SOAPY_SDR_CF32};
 }
 
 std::string SoapySXB200::getNativeStreamFormat(const int, const size_t, double &fullScale) const
@@ -251,7 +256,8 @@ SoapySDR::Stream *SoapySXB200::setupStream(const int direction, const std::strin
 {
     std::scoped_lock lock(rx_.mutex, tx_.mutex);
 
-    if (format != SOAPY_SDR_CF32)
+    const bool want_cs16 = cs16_enabled_ && format == SOAPY_SDR_CS16;
+    if (format != SOAPY_SDR_CF32 && !want_cs16)
         throw std::runtime_error("Only CF32 format is currently supported");
     if (snd_pcm_state(rx_.pcm) == SND_PCM_STATE_RUNNING ||
         snd_pcm_state(tx_.pcm) == SND_PCM_STATE_RUNNING)
@@ -268,6 +274,7 @@ SoapySDR::Stream *SoapySXB200::setupStream(const int direction, const std::strin
         tx_threshold2_ = threshold * threshold;
     }
 
+    ep.cs16 = want_cs16;
     ep.mode = (kwarg(args, "link", "") == "1") ? Endpoint::Mode::Linked : Endpoint::Mode::Normal;
     ep.configure(args.count("period") ? std::stoul(args.at("period")) : 0);
     ep.configured = true;
@@ -379,7 +386,9 @@ int SoapySXB200::readStream(SoapySDR::Stream *stream, void *const *buffs, const 
     ep.position += got;
 
     // I2S words -> CF32 on the GPU, straight out of pinned staging into the caller's buffer.
-    int rc = sxgpu_convert_rx_buffer_host(gpu_, stage_rx_->data(), 0, buffs[0], 0, size_t(got));
+    int rc = ep.cs16
+                 ? sxgpu_convert_rx_buffer_cs16_host(gpu_, stage_rx_->data(), 0, buffs[0], 0, size_t(got))
+                 : sxgpu_convert_rx_buffer_host(gpu_, stage_rx_->data(), 0, buffs[0], 0, size_t(got));
     if (rc != SXGPU_OK) {
         SoapySDR_logf(SOAPY_SDR_ERROR, "rx GPU conversion failed: %s (%s)", sxgpu_strerror(rc),
                       sxgpu_last_error(gpu_));
@@ -458,8 +467,10 @@ int SoapySXB200::writeStream(SoapySDR::Stream *stream, const void *const *buffs,
 
     // CF32 -> I2S words on the GPU, from the caller's buffer into pinned staging.
     stage_tx_->reserve(length);
-    int rc = sxgpu_convert_tx_buffer_host(gpu_, buffs[0], 0, stage_tx_->data(), 0, length,
-                                          tx_threshold2_);
+    int rc = ep.cs16 ? sxgpu_convert_tx_buffer_cs16_host(gpu_, buffs[0], 0, stage_tx_->data(), 0, length,
+                                                         tx_threshold2_)
+                     : sxgpu_convert_tx_buffer_host(gpu_, buffs[0], 0, stage_tx_->data(), 0, length,
+                                                    tx_threshold2_);
     if (rc != SXGPU_OK) {
         SoapySDR_logf(SOAPY_SDR_ERROR, "tx GPU conversion failed: %s (%s)", sxgpu_strerror(rc),
                       sxgpu_last_error(gpu_));

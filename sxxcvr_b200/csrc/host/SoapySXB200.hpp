@@ -41,6 +41,7 @@ struct Endpoint {
     snd_pcm_t *pcm = nullptr;
     mutable std::mutex mutex;
     Mode mode = Mode::Normal;
+    bool cs16 = false; // EXTENSION: stream format CS16 instead of CF32 (device argument cs16=1)
     bool configured = false;
     bool active = false;
     int64_t position = 0; // frames read / written / skipped since the last reset
@@ -136,6 +137,7 @@ private:
 
     sxgpu_ctx *gpu_ = nullptr;
     int gpu_ordinal_ = 0;
+    bool cs16_enabled_ = false; // EXTENSION, off by default: the reference offers CF32 only
 
     double master_clock_;
     double sample_rate_;

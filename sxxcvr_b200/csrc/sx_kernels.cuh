@@ -307,10 +307,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
                  "r"(parity)
                  : "memory");
 }
-__device__ __forceinline__ uint64_t policy_evict_first()
+// L2 eviction policy for a once-touched stream.  Which one is best is an empirical question
+// (it changes how the L2 batches write-backs to HBM), so the kernel takes it as an argument:
+// 0 evict_first, 1 evict_normal, 2 evict_last, 3 evict_unchanged.
+__device__ __forceinline__ uint64_t make_policy(int kind)
 {
     uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    switch (kind) {
+    case 1: asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol)); break;
+    case 2: asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol)); break;
+    case 3: asm volatile("createpolicy.fractional.L2::evict_unchanged.b64 %0, 1.0;" : "=l"(pol)); break;
+    default: asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol)); break;
+    }
     return pol;
 }
 __device__ __forceinline__ void load_g2s(void *smem_dst, const void *gsrc, uint32_t bytes,
@@ -352,6 +360,8 @@ struct BulkArgs {
     char *dst;        // 16-byte aligned
     uint64_t nframes; // frames in the middle; nframes * frame bytes is a multiple of 16 on both sides
     float thr2;
+    int load_policy;  // see bulk::make_policy
+    int store_policy;
 };
 
 // Persistent CTAs; tile t of TILE frames belongs to CTA (t mod gridDim.x).  Per CTA a ring
@@ -375,7 +385,7 @@ __global__ void bulk_convert_kernel(const BulkArgs a)
     if (first >= ntiles)
         return;
     const uint64_t mine = (ntiles - first + stride - 1) / stride; // tiles this CTA owns
-    const uint64_t pol = bulk::policy_evict_first();
+    const uint64_t pol = bulk::make_policy(a.load_policy), pol_store = bulk::make_policy(a.store_policy);
 
     auto tile_frames = [&](uint64_t i) -> uint32_t {
         uint64_t t = first + i * stride;
@@ -435,7 +445,7 @@ __global__ void bulk_convert_kernel(const BulkArgs a)
         __syncthreads();
 
         if (threadIdx.x == 0) {
-            bulk::store_s2g(a.dst + (first + i * stride) * TILE * DFB, ob, nf * DFB, pol);
+            bulk::store_s2g(a.dst + (first + i * stride) * TILE * DFB, ob, nf * DFB, pol_store);
             bulk::commit_group();
             uint64_t nxt = i + STAGES;
             if (nxt < mine) {

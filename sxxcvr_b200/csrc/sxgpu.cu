@@ -50,6 +50,7 @@ struct sxgpu_ctx {
     int64_t block = 0;                      // 0 auto, threads per CTA
     int64_t ctas_per_sm = 0;                // 0 auto
     int64_t bulk_tile = 0, bulk_stages = 0; // 0 auto
+    int64_t bulk_load_policy = 0, bulk_store_policy = 0; // L2 eviction: 0 first, 1 normal, 2 last, 3 unchanged
     int64_t host_chunk_frames = 0;          // 0 auto (see pick_chunk_frames)
     int64_t host_mode = 0;                  // 0 auto, 1 copy engines, 2 zero-copy
     int64_t zero_copy_max_frames = 1 << 18; // measured crossover, profiles/r01_sweep_host_path.json
@@ -238,7 +239,8 @@ int launch_bulk(sxgpu_ctx *ctx, const char *src, const char *dst_c, uint64_t tot
     int block = int(ctx->block ? ctx->block : 256);
 
     uint64_t mid = (total - head) / G * G;
-    BulkArgs a = {src + head * SFB, dst + head * DFB, mid, thr2};
+    BulkArgs a = {src + head * SFB, dst + head * DFB, mid, thr2, int(ctx->bulk_load_policy),
+                  int(ctx->bulk_store_policy)};
     uint64_t ntiles = (mid + shape.tile - 1) / shape.tile;
     int grid = persistent_grid(ctx, k, block, smem, ntiles);
     k<<<grid, block, smem, st>>>(a);
@@ -420,7 +422,7 @@ template <class Op>
 int convert_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset, void *h_dest,
                  size_t dest_offset, size_t length, float thr2, int64_t variant)
 {
-    static_assert(Op::kSrcWords == 2 && Op::kDstWords == 2, "host pipeline carries 8-byte frames");
+    constexpr size_t SFB = Op::kSrcWords * 4, DFB = Op::kDstWords * 4; // frame bytes on each side
     if (!ctx)
         return SXGPU_ERR_INVALID;
     if (length == 0)
@@ -429,8 +431,8 @@ int convert_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset, void *h_d
         return ctx->invalid("null sample buffer");
     if (frames_overflow(src_offset, length) || frames_overflow(dest_offset, length))
         return ctx->invalid("offset + length overflows");
-    const char *src = static_cast<const char *>(h_src) + src_offset * 8;
-    char *dst = static_cast<char *>(h_dest) + dest_offset * 8;
+    const char *src = static_cast<const char *>(h_src) + src_offset * SFB;
+    char *dst = static_cast<char *>(h_dest) + dest_offset * DFB;
 
     std::lock_guard<std::mutex> lock(ctx->host_mutex);
     SX_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -438,7 +440,7 @@ int convert_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset, void *h_d
     HostPtrInfo si = classify_pointer(ctx, src), di = classify_pointer(ctx, dst);
     if (si.foreign_device || di.foreign_device)
         return ctx->invalid("sample buffer lives on another GPU than the context");
-    const uint64_t in_bytes = si.on_device ? 0 : length * 8, out_bytes = di.on_device ? 0 : length * 8;
+    const uint64_t in_bytes = si.on_device ? 0 : length * SFB, out_bytes = di.on_device ? 0 : length * DFB;
 
     // One kernel, no queued copies, when the block is already on the device or is small: a
     // period-sized block (256 frames) in pinned host memory is read and written across PCIe by
@@ -453,7 +455,7 @@ int convert_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset, void *h_d
         const void *kernel_in = si.device_alias;
         void *kernel_out = di.device_alias;
         if (bounce_in) {
-            std::memcpy(ctx->ring.h_in[0], src, length * 8);
+            std::memcpy(ctx->ring.h_in[0], src, length * SFB);
             kernel_in = ctx->ring.h_in[0]; // pinned memory is device-addressable at the same address (UVA)
         }
         if (bounce_out)
@@ -462,7 +464,7 @@ int convert_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset, void *h_d
                                   ctx->s_comp));
         SX_CUDA(ctx, cudaStreamSynchronize(ctx->s_comp));
         if (bounce_out)
-            std::memcpy(dst, ctx->ring.h_out[0], length * 8);
+            std::memcpy(dst, ctx->ring.h_out[0], length * DFB);
         ctx->h2d_bytes += in_bytes;
         ctx->d2h_bytes += out_bytes;
         return SXGPU_OK;
@@ -481,7 +483,7 @@ int convert_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset, void *h_d
         int slot = int(i % kRingSlots);
         SX_CUDA(ctx, cudaEventSynchronize(r.done[slot]));
         if (!di.pinned && !di.on_device)
-            std::memcpy(dst + i * chunk * 8, r.h_out[slot], chunk_len(i) * 8);
+            std::memcpy(dst + i * chunk * DFB, r.h_out[slot], chunk_len(i) * DFB);
         return SXGPU_OK;
     };
 
@@ -489,23 +491,23 @@ int convert_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset, void *h_d
         int slot = int(i % kRingSlots);
         if (i >= size_t(kRingSlots))
             SX_TRY(retire(i - kRingSlots)); // frees the slot's device and bounce buffers
-        size_t n = chunk_len(i), bytes = n * 8;
+        size_t n = chunk_len(i);
 
         const void *kernel_in = r.d_in[slot];
         if (si.on_device) {
-            kernel_in = static_cast<const char *>(si.device_alias) + i * chunk * 8;
+            kernel_in = static_cast<const char *>(si.device_alias) + i * chunk * SFB;
         } else {
-            const void *from = src + i * chunk * 8;
+            const void *from = src + i * chunk * SFB;
             if (!si.pinned) {
-                std::memcpy(r.h_in[slot], from, bytes);
+                std::memcpy(r.h_in[slot], from, n * SFB);
                 from = r.h_in[slot];
             }
-            SX_CUDA(ctx, cudaMemcpyAsync(r.d_in[slot], from, bytes, cudaMemcpyHostToDevice, ctx->s_h2d));
+            SX_CUDA(ctx, cudaMemcpyAsync(r.d_in[slot], from, n * SFB, cudaMemcpyHostToDevice, ctx->s_h2d));
             SX_CUDA(ctx, cudaEventRecord(r.copied_in[slot], ctx->s_h2d));
             SX_CUDA(ctx, cudaStreamWaitEvent(ctx->s_comp, r.copied_in[slot], 0));
         }
 
-        void *kernel_out = di.on_device ? static_cast<void *>(static_cast<char *>(di.device_alias) + i * chunk * 8)
+        void *kernel_out = di.on_device ? static_cast<void *>(static_cast<char *>(di.device_alias) + i * chunk * DFB)
                                         : r.d_out[slot];
         SX_TRY(launch_convert<Op>(ctx, kernel_in, kernel_out, n, thr2, variant, ctx->s_comp));
 
@@ -514,8 +516,8 @@ int convert_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset, void *h_d
         } else {
             SX_CUDA(ctx, cudaEventRecord(r.converted[slot], ctx->s_comp));
             SX_CUDA(ctx, cudaStreamWaitEvent(ctx->s_d2h, r.converted[slot], 0));
-            void *to = di.pinned ? static_cast<void *>(dst + i * chunk * 8) : r.h_out[slot];
-            SX_CUDA(ctx, cudaMemcpyAsync(to, r.d_out[slot], bytes, cudaMemcpyDeviceToHost, ctx->s_d2h));
+            void *to = di.pinned ? static_cast<void *>(dst + i * chunk * DFB) : r.h_out[slot];
+            SX_CUDA(ctx, cudaMemcpyAsync(to, r.d_out[slot], n * DFB, cudaMemcpyDeviceToHost, ctx->s_d2h));
             SX_CUDA(ctx, cudaEventRecord(r.done[slot], ctx->s_d2h));
         }
     }
@@ -600,6 +602,8 @@ int64_t *option_slot(sxgpu_ctx *ctx, const char *key)
         {"ctas_per_sm", &ctx->ctas_per_sm},
         {"bulk_tile", &ctx->bulk_tile},
         {"bulk_stages", &ctx->bulk_stages},
+        {"bulk_load_policy", &ctx->bulk_load_policy},
+        {"bulk_store_policy", &ctx->bulk_store_policy},
         {"host_chunk_frames", &ctx->host_chunk_frames},
         {"host_mode", &ctx->host_mode},
         {"zero_copy_max_frames", &ctx->zero_copy_max_frames},
@@ -1097,6 +1101,27 @@ int sxgpu_convert_tx_buffer_host(sxgpu_ctx *ctx, const void *h_src, size_t src_o
                                  float tx_threshold2)
 {
     int r = convert_host<TxCf32>(ctx, h_src, src_offset, h_dest, dest_offset, length,
+                                 tx_threshold2, ctx ? ctx->tx_variant : 0);
+    if (r == SXGPU_OK)
+        ctx->frames_tx += length;
+    return r;
+}
+
+int sxgpu_convert_rx_buffer_cs16_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset,
+                                      void *h_dest, size_t dest_offset, size_t length)
+{
+    int r = convert_host<RxCs16>(ctx, h_src, src_offset, h_dest, dest_offset, length, 0.0f,
+                                 ctx ? ctx->rx_variant : 0);
+    if (r == SXGPU_OK)
+        ctx->frames_rx += length;
+    return r;
+}
+
+int sxgpu_convert_tx_buffer_cs16_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset,
+                                      void *h_dest, size_t dest_offset, size_t length,
+                                      float tx_threshold2)
+{
+    int r = convert_host<TxCs16>(ctx, h_src, src_offset, h_dest, dest_offset, length,
                                  tx_threshold2, ctx ? ctx->tx_variant : 0);
     if (r == SXGPU_OK)
         ctx->frames_tx += length;

@@ -276,6 +276,22 @@ def test_cs16_extensions_match_their_specification(ctx, oracle):
             assert np.array_equal(host(idst), sxtest.oracle_tx_cs16(oracle, s, sxtest.THR2_DEFAULT)), (n, variant)
 
 
+@pytest.mark.parametrize("pinned", [True, False])
+@pytest.mark.parametrize("nframes", [255, 4096, (1 << 21) + 5])
+def test_cs16_extension_host_entry_points(ctx, oracle, pinned, nframes):
+    words = sxtest.rx_uniform(nframes, seed=9)
+    hw = torch.from_numpy(words)
+    ho = torch.zeros(2 * nframes, dtype=torch.int16)
+    hi = torch.zeros(2 * nframes, dtype=torch.int32)
+    if pinned:
+        hw, ho, hi = hw.pin_memory(), ho.pin_memory(), hi.pin_memory()
+    ctx.convert_rx_buffer_cs16_host(hw.data_ptr(), 0, ho.data_ptr(), 0, nframes)
+    want = sxtest.oracle_rx_cs16(oracle, words)
+    assert np.array_equal(ho.numpy(), want)
+    ctx.convert_tx_buffer_cs16_host(ho.data_ptr(), 0, hi.data_ptr(), 0, nframes, sxtest.THR2_DEFAULT)
+    assert np.array_equal(hi.numpy(), sxtest.oracle_tx_cs16(oracle, want, sxtest.THR2_DEFAULT))
+
+
 def test_synth_frames_and_stats_match_the_host_definitions(ctx, oracle):
     n = 100001
     buf = torch.empty(2 * n, dtype=torch.int32, device="cuda")

@@ -140,3 +140,32 @@ def test_readstream_into_a_device_buffer_and_writestream_from_one(product, oracl
         assert product.lib.sxh_write(d.p, tx, dev.data_ptr(), n, C.byref(f), when, 100000) == n
         pos = product.lib.sxh_time_ns_to_ticks(when, 300000.0)
         assert np.array_equal(d.sink(pos, n), sxtest.oracle_tx(oracle, want, 0.0))
+
+
+def test_cs16_stream_format_is_an_opt_in_extension(product, oracle):
+    """EXTENSION, no reference behaviour: BASELINE config 2 names a CS16 readStream path, the
+    reference has none (SoapySX.cpp:752-753).  Off by default; with cs16=1 the values follow our
+    own specification in oracle/sx_oracle.c."""
+    import ctypes as C
+    with product.device() as d:
+        assert product.lib.sxh_stream_formats(d.p, sxstream.RX) == b"CF32"
+        with pytest.raises(sxstream.Threw):
+            d.setup(sxstream.RX, "CS16")
+    with product.device("driver=sx, cs16=1") as d:
+        assert product.lib.sxh_stream_formats(d.p, sxstream.RX) == b"CF32,CS16"
+        d.set_rate(75000.0)
+        rx, tx = d.setup(sxstream.RX, "CS16"), d.setup(sxstream.TX, "CS16", "threshold=0.25")
+        d.activate(rx), d.activate(tx)
+        for n in (256, 4096, 70001):
+            first = d.pointers()[1]
+            buf = np.zeros(2 * n, np.int16)
+            flags, t = C.c_int(-1), C.c_longlong(-1)
+            ret = product.lib.sxh_read(d.p, rx, buf.ctypes.data, n, C.byref(flags), C.byref(t), 100000)
+            assert ret == n and flags.value == sxstream.HAS_TIME
+            assert np.array_equal(buf, sxtest.oracle_rx_cs16(oracle, sxtest.synth_frames(oracle, first, n)))
+            f = C.c_int(sxstream.HAS_TIME)
+            when = t.value + 1_000_000_000
+            assert product.lib.sxh_write(d.p, tx, buf.ctypes.data, n, C.byref(f), when, 100000) == n
+            pos = product.lib.sxh_time_ns_to_ticks(when, 75000.0)
+            thr2 = float(np.float32(0.25) * np.float32(0.25))
+            assert np.array_equal(d.sink(pos, n), sxtest.oracle_tx_cs16(oracle, buf, thr2))
