@@ -81,6 +81,21 @@ def build_soapy_module(force: bool = False) -> Path:
     return SOAPY_LIB
 
 
+EXAMPLE_BIN = LIB / "sx_repeater"
+
+
+def build_examples(force: bool = False) -> Path:
+    """examples/repeater.cpp: a C++ application on the SoapySDR API, linked against the module."""
+    build_soapy_module(force)
+    src = ROOT / "examples" / "repeater.cpp"
+    if force or _stale(EXAMPLE_BIN, [src, SOAPY_LIB]):
+        _run([os.environ.get("CXX", "g++"), "-std=c++17", "-O2", "-Wall", "-Wextra",
+              "-I", CSRC / "shim", "-o", EXAMPLE_BIN, src,
+              "-L", LIB, "-lsxsoapy", "-lsxgpu", "-pthread", "-Wl,-rpath,$ORIGIN"])
+    return EXAMPLE_BIN
+
+
 def build_all(force: bool = False) -> None:
     build_gpu_library(force)
     build_soapy_module(force)
+    build_examples(force)

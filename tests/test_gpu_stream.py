@@ -169,3 +169,13 @@ def test_cs16_stream_format_is_an_opt_in_extension(product, oracle):
             pos = product.lib.sxh_time_ns_to_ticks(when, 75000.0)
             thr2 = float(np.float32(0.25) * np.float32(0.25))
             assert np.array_equal(d.sink(pos, n), sxtest.oracle_tx_cs16(oracle, buf, thr2))
+
+
+@pytest.mark.parametrize("args", [["100"], ["50", "1024", "300000"], ["30", "1000", "20833.333333333332", "clock=32e6"]])
+def test_cpp_repeater_example(args):
+    """examples/repeater.cpp: a C++ application written against the SoapySDR API only."""
+    import subprocess
+    from sxxcvr_b200 import _build
+    exe = _build.build_examples()
+    p = subprocess.run([str(exe)] + args, capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0 and p.stdout.startswith("OK"), (p.stdout, p.stderr[-500:])
