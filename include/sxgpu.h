@@ -93,6 +93,17 @@ int sxgpu_convert_tx_buffer_cs16(sxgpu_ctx *ctx, const void *d_src, size_t src_o
                                  void *d_dest, size_t dest_offset, size_t length,
                                  float tx_threshold2, sxgpu_stream stream);
 
+/* EXTENSION -- 16-bit I2S slots: frame = [I:int16][Q:int16].  The reference only runs the
+ * SX1255's 32-bit modes (its 16-bit entries are commented out as "did not work",
+ * SoapySX.cpp:200-207, and ALSA is opened as S32_LE, :474), so these too have no reference
+ * behaviour.  RX: f = s * 2^-15.  TX: v = trunc(2^15 * f) saturated to int16, low two bits
+ * cleared, both low bits of I set when fi*fi + fq*fq >= tx_threshold2. */
+int sxgpu_convert_rx_buffer_s16(sxgpu_ctx *ctx, const void *d_src, size_t src_offset, void *d_dest,
+                                size_t dest_offset, size_t length, sxgpu_stream stream);
+int sxgpu_convert_tx_buffer_s16(sxgpu_ctx *ctx, const void *d_src, size_t src_offset, void *d_dest,
+                                size_t dest_offset, size_t length, float tx_threshold2,
+                                sxgpu_stream stream);
+
 /* Many independent blocks in one launch: what a bank of SoapySX devices would do as one
  * convert_*_buffer call each per period (256 frames by default, SoapySX.cpp:451).
  * `blocks` is read on the host when blocks_on_device == 0 (it is then copied into the

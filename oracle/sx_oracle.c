@@ -107,6 +107,47 @@ void sxo_convert_tx_buffer_cs16(const void *src, size_t src_offset,
     }
 }
 
+/* Extension (no reference): S16_LE I2S frames <-> CF32. */
+void sxo_convert_rx_buffer_s16(const void *src, size_t src_offset,
+                               void *dest, size_t dest_offset, size_t length)
+{
+    const int16_t *in = (const int16_t *)src + 2 * src_offset;
+    float *out = (float *)dest + 2 * dest_offset;
+    for (size_t w = 0; w < 2 * length; w++)
+        out[w] = 3.0517578125e-05f * (float)in[w]; /* 2^-15, exact */
+}
+
+static uint16_t trunc_sat_s16(float p)
+{
+    if (p != p)
+        return 0;
+    if (p >= 32768.0f)
+        return 0x7FFF;
+    if (p <= -32768.0f)
+        return 0x8000;
+    return (uint16_t)(int16_t)(int32_t)p;
+}
+
+void sxo_convert_tx_buffer_s16(const void *src, size_t src_offset,
+                               void *dest, size_t dest_offset, size_t length,
+                               float tx_threshold2)
+{
+    const float *in = (const float *)src + 2 * src_offset;
+    uint16_t *out = (uint16_t *)dest + 2 * dest_offset;
+    for (size_t n = 0; n < length; n++) {
+        float fi = in[2 * n], fq = in[2 * n + 1];
+        uint16_t vi = trunc_sat_s16(32768.0f * fi) & 0xFFFCu;
+        uint16_t vq = trunc_sat_s16(32768.0f * fq) & 0xFFFCu;
+        float ii = fi * fi;
+        float qq = fq * fq;
+        float mag2 = ii + qq;
+        if (mag2 >= tx_threshold2)
+            vi |= 3u;
+        out[2 * n] = vi;
+        out[2 * n + 1] = vq;
+    }
+}
+
 /* SoapySDR lib/TimeC.cpp (external, unpinned): whole seconds in integers, the
  * remainder in double, llround. */
 long long sxo_ticks_to_time_ns(long long ticks, double rate)

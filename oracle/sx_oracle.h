@@ -45,6 +45,17 @@ void sxo_convert_tx_buffer_cs16(const void *src, size_t src_offset,
                                 void *dest, size_t dest_offset, size_t length,
                                 float tx_threshold2);
 
+/* Extension with NO reference implementation: 16-bit I2S slots.  The reference's sample-rate
+ * table lists the 16-bit SX1255 modes only as commented-out entries that "did not work"
+ * (SoapySX.cpp:200-207) and hard-wires SND_PCM_FORMAT_S32_LE (:474).  Specification (ours):
+ * an S16 frame is [I:int16][Q:int16]; RX: f = s * 2^-15; TX: v = trunc(2^15 * f) saturated to
+ * int16, low two bits cleared, TX-enable = both low bits of I, same un-fused threshold test. */
+void sxo_convert_rx_buffer_s16(const void *src, size_t src_offset,
+                               void *dest, size_t dest_offset, size_t length);
+void sxo_convert_tx_buffer_s16(const void *src, size_t src_offset,
+                               void *dest, size_t dest_offset, size_t length,
+                               float tx_threshold2);
+
 /* SoapySDR::ticksToTimeNs / timeNsToTicks as used at SoapySX.cpp:564,570.
  * SoapySDR is an external, unpinned dependency (SoapySX/CMakeLists.txt:45); this is a
  * restatement of its published algorithm (lib/TimeC.cpp).  Parity unpinned upstream. */

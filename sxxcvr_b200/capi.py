@@ -57,6 +57,8 @@ SIGNATURES = {
     "sxgpu_convert_tx_buffer": (C.c_int, [_P, _P, _S, _P, _S, _S, _F, _P]),
     "sxgpu_convert_rx_buffer_cs16": (C.c_int, [_P, _P, _S, _P, _S, _S, _P]),
     "sxgpu_convert_tx_buffer_cs16": (C.c_int, [_P, _P, _S, _P, _S, _S, _F, _P]),
+    "sxgpu_convert_rx_buffer_s16": (C.c_int, [_P, _P, _S, _P, _S, _S, _P]),
+    "sxgpu_convert_tx_buffer_s16": (C.c_int, [_P, _P, _S, _P, _S, _S, _F, _P]),
     "sxgpu_convert_rx_batch": (C.c_int, [_P, _P, C.c_uint32, C.c_int, _S, _P]),
     "sxgpu_convert_tx_batch": (C.c_int, [_P, _P, C.c_uint32, C.c_int, _S, _P]),
     "sxgpu_convert_loopback": (C.c_int, [_P, _P, _P, _P, _S, _F, _P]),
@@ -158,6 +160,14 @@ class Context:
     def convert_tx_buffer_cs16(self, d_src, src_offset, d_dest, dest_offset, length, tx_threshold2, stream=None):
         self.check(self.lib.sxgpu_convert_tx_buffer_cs16(self.handle, d_src, src_offset, d_dest, dest_offset, length,
                                                          tx_threshold2, stream), "sxgpu_convert_tx_buffer_cs16")
+
+    def convert_rx_buffer_s16(self, d_src, src_offset, d_dest, dest_offset, length, stream=None):
+        self.check(self.lib.sxgpu_convert_rx_buffer_s16(self.handle, d_src, src_offset, d_dest, dest_offset, length,
+                                                        stream), "sxgpu_convert_rx_buffer_s16")
+
+    def convert_tx_buffer_s16(self, d_src, src_offset, d_dest, dest_offset, length, tx_threshold2, stream=None):
+        self.check(self.lib.sxgpu_convert_tx_buffer_s16(self.handle, d_src, src_offset, d_dest, dest_offset, length,
+                                                        tx_threshold2, stream), "sxgpu_convert_tx_buffer_s16")
 
     def convert_batch(self, direction: str, blocks, on_device=False, max_length=0, stream=None, nblocks=None):
         fn = self.lib.sxgpu_convert_rx_batch if direction == "rx" else self.lib.sxgpu_convert_tx_batch

@@ -185,6 +185,42 @@ struct TxCs16 {
     }
 };
 
+// EXTENSION (no reference): 16-bit I2S slots, frame = [I:int16][Q:int16] in one word.
+// RX: f = s * 2^-15 (exact).
+struct RxS16Cf32 {
+    static constexpr int kSrcWords = 1, kDstWords = 2;
+    template <int FR>
+    __device__ __forceinline__ static void apply(const Pack<FR> &in, Pack<2 * FR> &out, float)
+    {
+#pragma unroll
+        for (int n = 0; n < FR; n++) {
+            uint32_t w = in.w[n];
+            out.w[2 * n] = __float_as_uint(__int2float_rn(int(short(w & 0xFFFFu))) * 3.0517578125e-05f);
+            out.w[2 * n + 1] = __float_as_uint(__int2float_rn(int(w) >> 16) * 3.0517578125e-05f);
+        }
+    }
+};
+
+// TX: v = trunc(2^15 * f) saturated to int16, low two bits cleared; flag bits as in TxCf32.
+struct TxCf32S16 {
+    static constexpr int kSrcWords = 2, kDstWords = 1;
+    __device__ __forceinline__ static uint32_t component(float f)
+    {
+        int v = __float2int_rz(f * 32768.0f); // saturates at the int32 rails, NaN -> 0
+        v = v > 32767 ? 32767 : (v < -32768 ? -32768 : v);
+        return uint32_t(v) & 0xFFFCu;
+    }
+    template <int FR>
+    __device__ __forceinline__ static void apply(const Pack<2 * FR> &in, Pack<FR> &out, float thr2)
+    {
+#pragma unroll
+        for (int n = 0; n < FR; n++) {
+            float fi = __uint_as_float(in.w[2 * n]), fq = __uint_as_float(in.w[2 * n + 1]);
+            out.w[n] = (component(fi) | tx_enable_bits(fi, fq, thr2)) | (component(fq) << 16);
+        }
+    }
+};
+
 // ---------------------------------------------------------------------------------------
 // vector128 / vector256: persistent grid-stride streaming kernel
 // ---------------------------------------------------------------------------------------

@@ -684,7 +684,8 @@ int sxgpu_init(int device, sxgpu_ctx **out)
         cudaHostAlloc(&ctx->h_stats, sizeof(StatsAcc), cudaHostAllocDefault) != cudaSuccess)
         return bail(SXGPU_ERR_NOMEM);
     if (prepare_bulk_kernels<RxCf32>(ctx) != SXGPU_OK || prepare_bulk_kernels<TxCf32>(ctx) != SXGPU_OK ||
-        prepare_bulk_kernels<RxCs16>(ctx) != SXGPU_OK || prepare_bulk_kernels<TxCs16>(ctx) != SXGPU_OK)
+        prepare_bulk_kernels<RxCs16>(ctx) != SXGPU_OK || prepare_bulk_kernels<TxCs16>(ctx) != SXGPU_OK ||
+        prepare_bulk_kernels<RxS16Cf32>(ctx) != SXGPU_OK || prepare_bulk_kernels<TxCf32S16>(ctx) != SXGPU_OK)
         return bail(SXGPU_ERR_CUDA);
     *out = ctx;
     return SXGPU_OK;
@@ -771,6 +772,27 @@ int sxgpu_convert_tx_buffer_cs16(sxgpu_ctx *ctx, const void *d_src, size_t src_o
 {
     int r = convert_entry<TxCs16>(ctx, d_src, src_offset, d_dest, dest_offset, length,
                                   tx_threshold2, ctx ? ctx->tx_variant : 0, stream);
+    if (r == SXGPU_OK)
+        ctx->frames_tx += length;
+    return r;
+}
+
+int sxgpu_convert_rx_buffer_s16(sxgpu_ctx *ctx, const void *d_src, size_t src_offset, void *d_dest,
+                                size_t dest_offset, size_t length, sxgpu_stream stream)
+{
+    int r = convert_entry<RxS16Cf32>(ctx, d_src, src_offset, d_dest, dest_offset, length, 0.0f,
+                                     ctx ? ctx->rx_variant : 0, stream);
+    if (r == SXGPU_OK)
+        ctx->frames_rx += length;
+    return r;
+}
+
+int sxgpu_convert_tx_buffer_s16(sxgpu_ctx *ctx, const void *d_src, size_t src_offset, void *d_dest,
+                                size_t dest_offset, size_t length, float tx_threshold2,
+                                sxgpu_stream stream)
+{
+    int r = convert_entry<TxCf32S16>(ctx, d_src, src_offset, d_dest, dest_offset, length,
+                                     tx_threshold2, ctx ? ctx->tx_variant : 0, stream);
     if (r == SXGPU_OK)
         ctx->frames_tx += length;
     return r;

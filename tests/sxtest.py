@@ -39,6 +39,10 @@ def load_oracle() -> C.CDLL:
     for f in ("sxo_convert_rx_buffer", "sxo_convert_tx_buffer", "sxo_convert_rx_buffer_cs16",
               "sxo_convert_tx_buffer_cs16"):
         getattr(lib, f).restype = None
+    lib.sxo_convert_rx_buffer_s16.argtypes = [P, S, P, S, S]
+    lib.sxo_convert_rx_buffer_s16.restype = None
+    lib.sxo_convert_tx_buffer_s16.argtypes = [P, S, P, S, S, C.c_float]
+    lib.sxo_convert_tx_buffer_s16.restype = None
     lib.sxo_ticks_to_time_ns.argtypes = [C.c_longlong, C.c_double]
     lib.sxo_ticks_to_time_ns.restype = C.c_longlong
     lib.sxo_time_ns_to_ticks.argtypes = [C.c_longlong, C.c_double]
@@ -99,6 +103,20 @@ def oracle_tx_cs16(lib, shorts: np.ndarray, thr2: float) -> np.ndarray:
     shorts = np.ascontiguousarray(shorts, dtype=np.int16)
     out = np.empty(shorts.size, np.int32)
     lib.sxo_convert_tx_buffer_cs16(shorts.ctypes.data, 0, out.ctypes.data, 0, shorts.size // 2, thr2)
+    return out
+
+
+def oracle_rx_s16(lib, shorts: np.ndarray) -> np.ndarray:
+    shorts = np.ascontiguousarray(shorts, dtype=np.int16)
+    out = np.empty(shorts.size, np.float32)
+    lib.sxo_convert_rx_buffer_s16(shorts.ctypes.data, 0, out.ctypes.data, 0, shorts.size // 2)
+    return out
+
+
+def oracle_tx_s16(lib, floats: np.ndarray, thr2: float) -> np.ndarray:
+    floats = np.ascontiguousarray(floats, dtype=np.float32)
+    out = np.empty(floats.size, np.int16)
+    lib.sxo_convert_tx_buffer_s16(floats.ctypes.data, 0, out.ctypes.data, 0, floats.size // 2, thr2)
     return out
 
 

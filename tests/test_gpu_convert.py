@@ -276,6 +276,30 @@ def test_cs16_extensions_match_their_specification(ctx, oracle):
             assert np.array_equal(host(idst), sxtest.oracle_tx_cs16(oracle, s, sxtest.THR2_DEFAULT)), (n, variant)
 
 
+def test_s16_frame_extension_matches_its_specification(ctx, oracle):
+    """EXTENSION: 16-bit I2S slots; no reference implementation (SoapySX.cpp:200-207, :474)."""
+    for n in (1, 2, 3, 4, 7, 4096, 100003, (1 << 21) + 2):
+        for variant in (1, 2, 3):
+            ctx.set_option("rx_variant", variant)
+            ctx.set_option("tx_variant", variant)
+            rng = np.random.default_rng(n)
+            s = rng.integers(-32768, 32768, size=2 * n, dtype=np.int64).astype(np.int16)
+            src = dev(s)
+            dst = torch.zeros(2 * n, dtype=torch.float32, device="cuda")
+            ctx.convert_rx_buffer_s16(src.data_ptr(), 0, dst.data_ptr(), 0, n)
+            ctx.stream_sync()
+            assert np.array_equal(bits(host(dst)), bits(sxtest.oracle_rx_s16(oracle, s))), (n, variant)
+            f = np.concatenate([sxtest.tx_gaussian_defined(n, seed=n), sxtest.tx_specials()])[: 2 * n]
+            if f.size < 2 * n:
+                f = np.resize(f, 2 * n)
+            fsrc = dev(f)
+            out = torch.zeros(2 * n, dtype=torch.int16, device="cuda")
+            for thr2 in (sxtest.THR2_DEFAULT, 0.0):
+                ctx.convert_tx_buffer_s16(fsrc.data_ptr(), 0, out.data_ptr(), 0, n, thr2)
+                ctx.stream_sync()
+                assert np.array_equal(host(out), sxtest.oracle_tx_s16(oracle, f, thr2)), (n, variant, thr2)
+
+
 @pytest.mark.parametrize("pinned", [True, False])
 @pytest.mark.parametrize("nframes", [255, 4096, (1 << 21) + 5])
 def test_cs16_extension_host_entry_points(ctx, oracle, pinned, nframes):

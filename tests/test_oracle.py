@@ -176,6 +176,16 @@ def test_cs16_extension_specification(oracle):
     assert [int(x) for x in out] == [0, 0, 0x00010000, 0xFFFF0000, 0x7FFF0003, 0x80000000, 0x00210003, 0]
 
 
+def test_s16_frame_extension_specification(oracle):
+    s = np.array([0, 1, -1, 32767, -32768, 16384, -16384, 3], np.int16)
+    f = sxtest.oracle_rx_s16(oracle, s)
+    assert f.tolist() == [0.0, 2.0**-15, -(2.0**-15), 32767 / 32768, -1.0, 0.5, -0.5, 3 * 2.0**-15]
+    x = np.array([1.0, -1.0, 0.5, -0.5, 2.0, np.nan, 1e-3, 0.0, 0.99997, -3e-5, np.inf, -np.inf], np.float32)
+    out = sxtest.oracle_tx_s16(oracle, x, sxtest.THR2_DEFAULT).view(np.uint16)
+    assert [int(v) for v in out] == [0x7FFF, 0x8000, 0x4003, 0xC000, 0x7FFC, 0x0000, 0x0023, 0x0000,
+                                    0x7FFF, 0x0000, 0x7FFF, 0x8000]
+
+
 def test_stats_definition(oracle):
     w = np.array([3, 0, 0x7FFFFFFC, 0x80000000, 2, 2, 0xFFFFFFFF, 1], dtype=np.uint32)
     s = sxtest.oracle_stats(oracle, w, 10)
