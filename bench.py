@@ -5,9 +5,9 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One "step" = one RX block (S32_LE I2S frames -> CF32) and one TX block (CF32 -> I2S frames
-with clamp/truncate/flag bits) of 2^27 frames each per GPU: 1 GiB in and 1 GiB out per
-conversion, the 1 GiB point of BASELINE config 5's sweep and ~8x the L2, so every byte
-comes from and goes to HBM.  Blocks are independent, so ranks shard them with no collective
+with clamp/truncate/flag bits) of 2^29 frames each per GPU: 4 GiB in and 4 GiB out per
+conversion, the largest point of BASELINE config 5's sweep (1 MB - 4 GB per block) and ~32x
+the L2, so every byte comes from and goes to HBM.  Blocks are independent, so ranks shard them with no collective
 on the data path ("weak" scaling); NCCL only gathers the output checksums afterwards.
 
 The JSON line carries
@@ -144,10 +144,10 @@ def run_reference_arm(args, rank: int):
 def workload_config(args, per_gpu_frames):
     return {
         "workload": "SoapySX RX convert (S32_LE I2S -> CF32) + TX convert (CF32 -> S32_LE I2S, clamp/trunc/flag bits), "
-                    "one block each per step per GPU (BASELINE config 5, 1 GiB point)",
+                    f"one block each per step per GPU (BASELINE config 5, {8 * per_gpu_frames / 2**30:g} GiB-per-block point)",
         "frames_per_block": per_gpu_frames, "blocks_per_step_per_gpu": 2,
         "bytes_per_frame": BYTES_PER_FRAME, "tx_threshold2": THR2,
-        "cache": "each buffer is 8*frames bytes (1 GiB at 2^27), >> 126 MB L2; no flush needed",
+        "cache": f"each buffer is {8 * per_gpu_frames / 2**20:g} MiB, inputs >> 126 MB L2, so no flush is needed",
         "parallelism": f"independent blocks sharded over {args.gpus} GPU(s), no data-path collective",
     }
 
@@ -347,11 +347,14 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
     roof_rx = roof(rx_ms, "bulk_convert_kernel<RxCf32>")
     roof_tx = roof(tx_ms, "bulk_convert_kernel<TxCf32>")
     dominant = roof_tx if sum(tx_ms) >= sum(rx_ms) else roof_rx
-    traffic_file = ROOT / "profiles" / "r01_traffic.json"   # dram bytes per launch from the ncu --set full capture
+    # DRAM bytes per launch from the committed `ncu --set full` capture -- only valid for the
+    # launch size it was captured at.
+    traffic_file = ROOT / "profiles" / "r01_traffic.json"
     if traffic_file.exists():
         try:
             t = json.loads(traffic_file.read_text())
-            roof_rx["traffic"], roof_tx["traffic"] = t.get("rx_bytes_per_launch"), t.get("tx_bytes_per_launch")
+            if t.get("frames_per_launch") == frames:
+                roof_rx["traffic"], roof_tx["traffic"] = t.get("rx_bytes_per_launch"), t.get("tx_bytes_per_launch")
         except ValueError:
             pass
 
@@ -446,7 +449,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--log2-frames", type=int, default=27, help="frames per block per GPU (2^27 = 1 GiB in)")
+    ap.add_argument("--log2-frames", type=int, default=29, help="frames per block per GPU (2^29 = 4 GiB in)")
     ap.add_argument("--e2e-log2-frames", type=int, default=26)
     ap.add_argument("--cpu-log2-frames", type=int, default=26)
     ap.add_argument("--no-cpu-baseline", action="store_true")
