@@ -30,6 +30,7 @@ struct Fault {
 
 const snd_pcm_uframes_t kBoundary = snd_pcm_uframes_t(1) << 62;
 const snd_pcm_uframes_t kMaxBuffer = 65536; // observed Pi limit, reference :464
+const unsigned kWaitWatchdog = 1000;
 
 } // namespace
 
@@ -63,6 +64,7 @@ struct _snd_pcm {
     int64_t hw_ptr = 0;   // frames the "hardware" has captured / played
 
     bool free_run = true;
+    unsigned fruitless_waits = 0; // consecutive snd_pcm_wait calls that timed out (watchdog, see snd_pcm_wait)
     snd_pcm_uframes_t max_transfer = 0;
     uint64_t transferred = 0;
 
@@ -280,6 +282,12 @@ int snd_pcm_link(snd_pcm_t *a, snd_pcm_t *b)
 }
 
 // Waits until avail >= avail_min.  In free-run mode the wait is the clock advancing.
+//
+// Watchdog: when the clock cannot move (free-run off, or the stream is not running) the wait
+// times out, and a driver that forwards-and-waits in a loop (reference SoapySX.cpp:1045-1073)
+// would spin for ever -- on real hardware it would sit in 10 s waits instead.  After
+// kWaitWatchdog fruitless waits in a row the next snd_pcm_forwardable reports -EIO, so the loop
+// ends with a stream error and no test can hang.
 int snd_pcm_wait(snd_pcm_t *pcm, int)
 {
     Guard lock(g_mutex);
@@ -287,12 +295,15 @@ int snd_pcm_wait(snd_pcm_t *pcm, int)
         return -EPIPE;
     int64_t need = int64_t(pcm->sw.avail_min) - pcm->avail();
     if (need > 0) {
-        if (!pcm->free_run || pcm->state != SND_PCM_STATE_RUNNING)
+        if (!pcm->free_run || pcm->state != SND_PCM_STATE_RUNNING) {
+            pcm->fruitless_waits++;
             return 0; // timed out
+        }
         advanceGroup(pcm, need);
         if (pcm->state == SND_PCM_STATE_XRUN)
             return -EPIPE;
     }
+    pcm->fruitless_waits = 0;
     return 1;
 }
 
@@ -317,6 +328,10 @@ snd_pcm_sframes_t snd_pcm_forwardable(snd_pcm_t *pcm)
     int err;
     if (takeFault(pcm, SX_ALSA_OP_FORWARDABLE, &err))
         return err;
+    if (pcm->fruitless_waits >= kWaitWatchdog) {
+        pcm->fruitless_waits = 0;
+        return -EIO;
+    }
     if (pcm->state == SND_PCM_STATE_XRUN)
         return -EPIPE;
     return snd_pcm_sframes_t(std::max<int64_t>(pcm->avail(), 0));
