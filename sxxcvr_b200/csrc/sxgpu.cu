@@ -13,8 +13,10 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
+#include <tuple>
 
 using namespace sx;
 
@@ -46,7 +48,7 @@ struct sxgpu_ctx {
 
     // options
     int64_t rx_variant = 0, tx_variant = 0; // 0 auto, 1 vec128, 2 vec256, 3 bulk
-    int64_t unroll = 0;                     // 0 auto, else 1/2/4/8
+    int64_t unroll = 0;                     // 0 auto (4), else 2/4/8
     int64_t block = 0;                      // 0 auto, threads per CTA
     int64_t ctas_per_sm = 0;                // 0 auto
     int64_t bulk_tile = 0, bulk_stages = 0; // 0 auto
@@ -70,6 +72,11 @@ struct sxgpu_ctx {
 
     std::mutex err_mutex;
     std::string last_error;
+
+    // occupancy of each (kernel, block, smem) seen so far: the query costs about a microsecond,
+    // which matters when the whole call is a 2 KiB block
+    std::mutex occupancy_mutex;
+    std::map<std::tuple<const void *, int, size_t>, int> occupancy;
 
     int fail(cudaError_t e, const char *what)
     {
@@ -166,11 +173,19 @@ int persistent_grid(sxgpu_ctx *ctx, K kernel, int block, size_t smem, uint64_t w
 {
     int per_sm = int(ctx->ctas_per_sm);
     if (per_sm <= 0) {
-        int occ = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, block, smem) != cudaSuccess ||
-            occ <= 0)
-            occ = 1;
-        per_sm = occ;
+        std::lock_guard<std::mutex> lock(ctx->occupancy_mutex);
+        auto key = std::make_tuple(reinterpret_cast<const void *>(kernel), block, smem);
+        auto it = ctx->occupancy.find(key);
+        if (it == ctx->occupancy.end()) {
+            int occ = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, block, smem) != cudaSuccess ||
+                occ <= 0) {
+                cudaGetLastError();
+                occ = 1;
+            }
+            it = ctx->occupancy.emplace(key, occ).first;
+        }
+        per_sm = it->second;
     }
     uint64_t grid = uint64_t(ctx->prop.multiProcessorCount) * uint64_t(per_sm);
     grid = std::min<uint64_t>(grid, std::max<uint64_t>(work_items, 1));
@@ -277,7 +292,7 @@ int launch_convert(sxgpu_ctx *ctx, const void *src_v, void *dst_v, uint64_t tota
         return ctx->invalid("sample buffers must be at least 4-byte aligned");
 
     if (variant == 0)
-        variant = 3; // measured default (profiles/r01_sweep.md): bulk-async staging wins
+        variant = 3; // measured default (profiles/r01_summary.md section 4): bulk-async staging wins
     if (variant == 3) {
         bool handled = false;
         SX_TRY(launch_bulk<Op>(ctx, src, dst, total, thr2, st, &handled));
