@@ -402,6 +402,17 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
         for _ in range(reps):
             ctx.convert_rx_buffer_host(h_i2s.data_ptr(), 0, h_cf_out.data_ptr(), 0, nf)
         small[f"rx_host_{nf}_frames_us_per_call"] = (time.perf_counter() - t0) / reps * 1e6
+    # the same period-sized call through the opt-in resident converter (doorbell in pinned memory)
+    ctx.set_option("resident_max_frames", 4096)
+    for nf in (256, 4096):
+        for _ in range(5):
+            ctx.convert_rx_buffer_host(h_i2s.data_ptr(), 0, h_cf_out.data_ptr(), 0, nf)
+        reps = 500
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            ctx.convert_rx_buffer_host(h_i2s.data_ptr(), 0, h_cf_out.data_ptr(), 0, nf)
+        small[f"rx_host_{nf}_frames_us_per_call_resident"] = (time.perf_counter() - t0) / reps * 1e6
+    ctx.set_option("resident_max_frames", 0)
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ---------------------------------------------
     cpu = None

@@ -246,11 +246,16 @@ int sxgpu_stream_sync(sxgpu_ctx *ctx, sxgpu_stream stream); /* NULL = context st
  *   "ctas_per_sm"               persistent grid = sm_count * ctas_per_sm (0 = auto)
  *   "host_chunk_frames"         chunk size of the *_host pipeline
  *   "host_mode"                 0 = auto, 1 = copy-engine pipeline, 2 = zero-copy kernel
+ *   "resident_max_frames"       0 = off (default).  N > 0: synchronous CF32 calls of up to N
+ *                               frames on host buffers are served by a resident single-CTA
+ *                               kernel through a doorbell in pinned memory instead of a kernel
+ *                               launch + stream sync each (period-sized blocks, SoapySX.cpp:451);
+ *                               the kernel leaves by itself after 2 ms without work
  */
 int sxgpu_set_option(sxgpu_ctx *ctx, const char *key, int64_t value);
 int sxgpu_get_option(sxgpu_ctx *ctx, const char *key, int64_t *value);
 /* Counters: "launches" (kernels launched by this context), "frames_rx", "frames_tx",
- * "h2d_bytes", "d2h_bytes". */
+ * "h2d_bytes", "d2h_bytes", "resident_launches", "resident_calls". */
 int sxgpu_get_counter(sxgpu_ctx *ctx, const char *key, uint64_t *value);
 
 #ifdef __cplusplus

@@ -183,6 +183,10 @@ SoapySXB200::SoapySXB200(const SoapySDR::Kwargs &args)
     // detection is inconclusive: 38.4 MHz (SoapySX.cpp:656-659).  clock=32e6 selects the
     // other board variant.  The initial rate is masterClock/256 (:662).
     cs16_enabled_ = kwarg(args, "cs16", "0") == "1";
+    // lowlatency=1: period-sized blocks (up to 4096 frames) are converted by a resident kernel
+    // that is rung through a doorbell in pinned memory -- no launch, no stream sync per call.
+    if (kwarg(args, "lowlatency", "0") == "1")
+        sxgpu_set_option(gpu_, "resident_max_frames", 4096);
     master_clock_ = std::stod(kwarg(args, "clock", "38.4e6"));
     sample_rate_ = master_clock_ / 256.0;
     antenna_[SOAPY_SDR_RX] = "RX";

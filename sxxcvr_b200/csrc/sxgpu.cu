@@ -8,9 +8,11 @@
 
 #include "sx_kernels.cuh"
 #include "sx_bank.cuh"
+#include "sx_resident.cuh"
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -56,6 +58,13 @@ struct sxgpu_ctx {
     int64_t host_chunk_frames = 0;          // 0 auto (see pick_chunk_frames)
     int64_t host_mode = 0;                  // 0 auto, 1 copy engines, 2 zero-copy
     int64_t zero_copy_max_frames = 1 << 18; // measured crossover, profiles/r01_sweep_host_path.json
+    int64_t resident_max_frames = 0;        // > 0: blocks up to this size go to the resident converter
+
+    // resident converter (sx_resident.cuh); guarded by host_mutex
+    Mailbox *mailbox = nullptr;
+    cudaStream_t s_resident = nullptr;
+    unsigned long long resident_seq = 0;
+    std::atomic<uint64_t> resident_launches{0}, resident_calls{0};
 
     // host pipeline
     std::mutex host_mutex;
@@ -433,6 +442,86 @@ int ensure_ring(sxgpu_ctx *ctx, size_t frames, bool bounce_in, bool bounce_out)
     return SXGPU_OK;
 }
 
+// Hand one small block to the resident converter and wait for it.  `src` and `dst` are
+// device-visible addresses of distinct buffers.  Every wait is bounded.
+int resident_convert_call(sxgpu_ctx *ctx, int op, const void *src, void *dst, size_t length, float thr2)
+{
+    using clock = std::chrono::steady_clock;
+    if (!ctx->mailbox) {
+        SX_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(&ctx->mailbox), sizeof(Mailbox),
+                                   cudaHostAllocMapped | cudaHostAllocPortable));
+        std::memset(ctx->mailbox, 0, sizeof(Mailbox));
+        SX_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_resident, cudaStreamNonBlocking));
+    }
+    volatile Mailbox *box = ctx->mailbox;
+
+    auto ensure_listening = [&]() -> int {
+        if (box->alive)
+            return SXGPU_OK;
+        // No kernel is listening (never started, or it left after its idle timeout).  Wait for
+        // the old one to be completely gone, then start a new one and wait until it says so.
+        SX_CUDA(ctx, cudaStreamSynchronize(ctx->s_resident));
+        resident_kernel<<<1, 256, 0, ctx->s_resident>>>(ctx->mailbox, ctx->resident_seq);
+        SX_CUDA(ctx, cudaGetLastError());
+        ctx->launches++;
+        ctx->resident_launches++;
+        auto t0 = clock::now();
+        while (!box->alive) {
+            if (clock::now() - t0 > std::chrono::seconds(2))
+                return ctx->invalid("resident converter did not start");
+        }
+        return SXGPU_OK;
+    };
+    SX_TRY(ensure_listening());
+
+    const unsigned long long seq = ++ctx->resident_seq;
+    unsigned thr2_bits;
+    std::memcpy(&thr2_bits, &thr2, sizeof thr2_bits);
+    box->src = static_cast<const char *>(src);
+    box->dst = static_cast<char *>(dst);
+    box->nframes = unsigned(length) | (unsigned(op) << 31);
+    box->thr2_bits_op = thr2_bits;
+    std::atomic_thread_fence(std::memory_order_release);
+    box->request = seq;
+
+    auto t0 = clock::now();
+    unsigned spins = 0;
+    while (box->done != seq) {
+        if ((++spins & 0xFF) != 0)
+            continue;
+        if (!box->alive) {
+            // The kernel left.  Once it is really gone either it served this request in its last
+            // look (done == seq) or it never saw it: then a fresh kernel, started with
+            // last_seen = seq - 1, picks it up from the mailbox.
+            SX_CUDA(ctx, cudaStreamSynchronize(ctx->s_resident));
+            if (box->done == seq)
+                break;
+            ctx->resident_seq = seq - 1;
+            SX_TRY(ensure_listening());
+            ctx->resident_seq = seq;
+            t0 = clock::now();
+        }
+        if (clock::now() - t0 > std::chrono::seconds(2))
+            return ctx->invalid("resident converter did not answer");
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    ctx->resident_calls++;
+    return SXGPU_OK;
+}
+
+template <class Op> constexpr int resident_op()
+{
+    return -1;
+}
+template <> constexpr int resident_op<RxCf32>()
+{
+    return 0;
+}
+template <> constexpr int resident_op<TxCf32>()
+{
+    return 1;
+}
+
 template <class Op>
 int convert_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset, void *h_dest,
                  size_t dest_offset, size_t length, float thr2, int64_t variant)
@@ -475,9 +564,17 @@ int convert_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset, void *h_d
         }
         if (bounce_out)
             kernel_out = ctx->ring.h_out[0];
-        SX_TRY(launch_convert<Op>(ctx, kernel_in, kernel_out, length, thr2, both_on_device ? variant : 1,
-                                  ctx->s_comp));
-        SX_CUDA(ctx, cudaStreamSynchronize(ctx->s_comp));
+        const bool frame_aligned = reinterpret_cast<uintptr_t>(kernel_in) % 8 == 0 &&
+                                   reinterpret_cast<uintptr_t>(kernel_out) % 8 == 0;
+        if (resident_op<Op>() >= 0 && !both_on_device && length <= size_t(ctx->resident_max_frames) &&
+            length < (size_t(1) << 31) &&
+            frame_aligned && kernel_in != kernel_out) {
+            SX_TRY(resident_convert_call(ctx, resident_op<Op>(), kernel_in, kernel_out, length, thr2));
+        } else {
+            SX_TRY(launch_convert<Op>(ctx, kernel_in, kernel_out, length, thr2, both_on_device ? variant : 1,
+                                      ctx->s_comp));
+            SX_CUDA(ctx, cudaStreamSynchronize(ctx->s_comp));
+        }
         if (bounce_out)
             std::memcpy(dst, ctx->ring.h_out[0], length * DFB);
         ctx->h2d_bytes += in_bytes;
@@ -622,6 +719,7 @@ int64_t *option_slot(sxgpu_ctx *ctx, const char *key)
         {"host_chunk_frames", &ctx->host_chunk_frames},
         {"host_mode", &ctx->host_mode},
         {"zero_copy_max_frames", &ctx->zero_copy_max_frames},
+        {"resident_max_frames", &ctx->resident_max_frames},
     };
     for (auto &e : table)
         if (std::strcmp(e.name, key) == 0)
@@ -727,6 +825,8 @@ int sxgpu_destroy(sxgpu_ctx *ctx)
     if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
     if (ctx->s_comp) cudaStreamDestroy(ctx->s_comp);
     if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
+    if (ctx->s_resident) cudaStreamDestroy(ctx->s_resident); // the resident kernel has left: device was synchronised
+    if (ctx->mailbox) cudaFreeHost(ctx->mailbox);
     if (ctx->d_stats) cudaFree(ctx->d_stats);
     if (ctx->h_stats) cudaFreeHost(ctx->h_stats);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1347,6 +1447,8 @@ int sxgpu_get_counter(sxgpu_ctx *ctx, const char *key, uint64_t *value)
     else if (!std::strcmp(key, "frames_tx")) *value = ctx->frames_tx;
     else if (!std::strcmp(key, "h2d_bytes")) *value = ctx->h2d_bytes;
     else if (!std::strcmp(key, "d2h_bytes")) *value = ctx->d2h_bytes;
+    else if (!std::strcmp(key, "resident_launches")) *value = ctx->resident_launches;
+    else if (!std::strcmp(key, "resident_calls")) *value = ctx->resident_calls;
     else return ctx->invalid("unknown counter");
     return SXGPU_OK;
 }

@@ -386,6 +386,70 @@ def test_host_entry_points_accept_device_memory_on_either_side(ctx, oracle, nfra
     assert np.array_equal(out_i.numpy(), sxtest.oracle_tx(oracle, f, sxtest.THR2_DEFAULT))
 
 
+def test_resident_converter_for_period_sized_blocks(ctx, oracle):
+    """Opt-in low-latency path: a resident kernel rung through a doorbell in pinned memory.  Same
+    bits as every other path; survives its own idle timeout (it leaves after 2 ms and is relaunched);
+    large blocks still take the normal route."""
+    import time
+    ctx.set_option("resident_max_frames", 4096)
+    try:
+        calls0, launches0 = ctx.counter("resident_calls"), ctx.counter("resident_launches")
+        for pinned in (True, False):
+            for n in (1, 2, 255, 256, 1000, 4096):
+                words = sxtest.rx_uniform(n, seed=n)
+                f = sxtest.tx_gaussian_defined(n, seed=n + 1)
+                hw, hf = torch.from_numpy(words), torch.from_numpy(f)
+                ho, hi = torch.zeros(2 * n, dtype=torch.float32), torch.zeros(2 * n, dtype=torch.int32)
+                if pinned:
+                    hw, hf, ho, hi = hw.pin_memory(), hf.pin_memory(), ho.pin_memory(), hi.pin_memory()
+                for rep in range(3):
+                    ho.zero_()
+                    ctx.convert_rx_buffer_host(hw.data_ptr(), 0, ho.data_ptr(), 0, n)
+                    assert np.array_equal(bits(ho.numpy()), bits(sxtest.oracle_rx(oracle, words))), (pinned, n, rep)
+                    ctx.convert_tx_buffer_host(hf.data_ptr(), 0, hi.data_ptr(), 0, n, sxtest.THR2_DEFAULT)
+                    assert np.array_equal(hi.numpy(), sxtest.oracle_tx(oracle, f, sxtest.THR2_DEFAULT)), (pinned, n, rep)
+        assert ctx.counter("resident_calls") - calls0 == 2 * 6 * 3 * 2
+        # the same staging buffer reused with new contents every call: no stale cache lines
+        n = 256
+        hw = torch.zeros(2 * n, dtype=torch.int32).pin_memory()
+        ho = torch.zeros(2 * n, dtype=torch.float32).pin_memory()
+        for k in range(500):
+            words = sxtest.rx_uniform(n, seed=5000 + k)
+            hw.copy_(torch.from_numpy(words))
+            ctx.convert_rx_buffer_host(hw.data_ptr(), 0, ho.data_ptr(), 0, n)
+            assert np.array_equal(bits(ho.numpy()), bits(sxtest.oracle_rx(oracle, words))), k
+        # idle longer than the kernel's timeout: it leaves, the next call starts a new one
+        before = ctx.counter("resident_launches")
+        for _ in range(3):
+            time.sleep(0.02)
+            ctx.convert_rx_buffer_host(hw.data_ptr(), 0, ho.data_ptr(), 0, n)
+            assert np.array_equal(bits(ho.numpy()), bits(sxtest.oracle_rx(oracle, words)))
+        assert ctx.counter("resident_launches") - before >= 2
+        # bigger than the limit: the usual path, interleaved with resident calls
+        big = sxtest.rx_uniform(100000, seed=1)
+        hb = torch.from_numpy(big).pin_memory()
+        hob = torch.zeros(200000, dtype=torch.float32).pin_memory()
+        c = ctx.counter("resident_calls")
+        ctx.convert_rx_buffer_host(hb.data_ptr(), 0, hob.data_ptr(), 0, 100000)
+        ctx.convert_rx_buffer_host(hw.data_ptr(), 0, ho.data_ptr(), 0, n)
+        assert ctx.counter("resident_calls") - c == 1
+        assert np.array_equal(bits(hob.numpy()), bits(sxtest.oracle_rx(oracle, big)))
+        # latency, for the record (asserted loosely: it must not be slower than the launch path)
+        t0 = time.perf_counter()
+        for _ in range(2000):
+            ctx.convert_rx_buffer_host(hw.data_ptr(), 0, ho.data_ptr(), 0, n)
+        resident_us = (time.perf_counter() - t0) / 2000 * 1e6
+        ctx.set_option("resident_max_frames", 0)
+        t0 = time.perf_counter()
+        for _ in range(2000):
+            ctx.convert_rx_buffer_host(hw.data_ptr(), 0, ho.data_ptr(), 0, n)
+        launch_us = (time.perf_counter() - t0) / 2000 * 1e6
+        print(f"256-frame RX call: resident {resident_us:.2f} us, launch+sync {launch_us:.2f} us")
+        assert resident_us < launch_us * 1.2
+    finally:
+        ctx.set_option("resident_max_frames", 0)
+
+
 def test_full_size_block_by_properties(ctx, oracle):
     """BASELINE config 5 size (2^27 frames = 1 GiB in): too big for the scalar oracle in a test,
     so check size-independent properties: the checksum of the output equals the checksum of

@@ -179,3 +179,17 @@ def test_cpp_repeater_example(args):
     exe = _build.build_examples()
     p = subprocess.run([str(exe)] + args, capture_output=True, text=True, timeout=120)
     assert p.returncode == 0 and p.stdout.startswith("OK"), (p.stdout, p.stderr[-500:])
+
+
+def test_lowlatency_device_argument_matches_golden_traces(product):
+    """lowlatency=1 routes period-sized blocks through the resident converter; observable
+    behaviour must not change."""
+    for name in ("repeater", "timed_bursts", "nonblocking"):
+        class Low:
+            lib = product.lib
+
+            @staticmethod
+            def device(args="driver=sx"):
+                return product.device(args + ", lowlatency=1")
+        got = sxstream.normalise(sxstream.SCENARIOS[name](Low))
+        assert got == GOLDEN[name], name
