@@ -9,12 +9,15 @@
 //     clock        frames the (virtual) SX1255 has produced/consumed since the streams started
 //     rx_position  the RX frame counter (AlsaPcm::position of the capture side, :378)
 //     tx_position  the TX frame counter (playback side)
-// plus a playback ring of `ring` frames and a capture staging slot of one period, and runs
-//     bank_rx_plan_kernel     what readStream decides for every stream    (one thread / stream)
-//     bank_capture_kernel     stand-in for the I2S DMA: writes the planned frames into HBM
-//     batch_warp_kernel<RxCf32>  the conversion                           (one warp / stream)
-//     bank_tx_plan_kernel     what writeStream decides for every stream   (one thread / stream)
-//     bank_tx_convert_kernel  silence for forwarded-over gaps + the conversion into the ring
+// plus a playback ring of `ring` frames and a capture staging slot of one period, and runs,
+// with one warp per stream (up to 8192 streams lane 0 decides and the warp moves the data;
+// beyond that the decisions are taken first by thread-per-stream plan kernels, so that no lane
+// idles through the timestamp arithmetic):
+//     bank_capture_kernel     what readStream decides (bank_plan_read) + stand-in for the I2S
+//                             DMA: writes the planned frames into HBM
+//     batch_warp_kernel<RxCf32>  the conversion, from the capture slot to the caller's CF32
+//     bank_tx_kernel          what writeStream decides (bank_plan_write) + silence for
+//                             forwarded-over gaps + the conversion into the playback ring
 // The virtual clock follows the same rule as the host-side ALSA stand-in: it moves when a
 // blocking transfer must wait (by exactly the deficit) or when the owner advances it.
 #pragma once
@@ -57,11 +60,9 @@ struct BankState {
 constexpr int SX_HAS_TIME = 1 << 2; // SOAPY_SDR_HAS_TIME
 
 // readStream(stream, buf, period, timeoutUs > 0) for stream s: SoapySX.cpp:897-959.
-__global__ void bank_rx_plan_kernel(BankState b, char *cf32_out)
+// Run by one lane of the warp that owns the stream.
+__device__ __forceinline__ void bank_plan_read(const BankState &b, uint64_t s, char *cf32_out)
 {
-    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= b.nstreams)
-        return;
     const sxplan::Geometry geo = {b.period, b.ring};
     long long clock = b.clock[s], pos = b.rx_position[s];
     long pending = long(clock - pos);
@@ -92,13 +93,32 @@ __global__ void bank_rx_plan_kernel(BankState b, char *cf32_out)
     b.rx_blocks[s] = d;
 }
 
-// Stand-in for the I2S DMA: frame k of stream s is sx_synth_frame(seed + s, k).
-__global__ void bank_capture_kernel(BankState b)
+// One warp per stream: lane 0 makes readStream's decisions, then the warp plays the I2S DMA --
+// frame k of stream s is sx_synth_frame(seed + s, k) -- and writes the planned frames into the
+// stream's capture slot.  The conversion itself is a separate launch (batch_warp_kernel<RxCf32>
+// over the descriptors written here): it reads the frames back from HBM as it would after a
+// real DMA.
+// `fused`: lane 0 plans here (few streams: saves a launch).  Otherwise bank_plan_read_kernel
+// has already planned every stream with one thread each (many streams: keeps all lanes busy).
+__global__ void bank_plan_read_kernel(BankState b, char *cf32_out)
+{
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < b.nstreams)
+        bank_plan_read(b, s, cf32_out);
+}
+
+__global__ void bank_capture_kernel(BankState b, char *cf32_out, bool fused)
 {
     const uint32_t lane = threadIdx.x & 31, warps_per_cta = blockDim.x >> 5;
     const uint64_t nwarps = uint64_t(gridDim.x) * warps_per_cta;
     for (uint64_t s = uint64_t(blockIdx.x) * warps_per_cta + (threadIdx.x >> 5); s < b.nstreams; s += nwarps) {
-        const uint64_t first = uint64_t(b.rx_first_frame[s]);
+        long long first_ll = 0;
+        if (lane == 0) {
+            if (fused)
+                bank_plan_read(b, s, cf32_out);
+            first_ll = b.rx_first_frame[s];
+        }
+        const uint64_t first = uint64_t(__shfl_sync(0xffffffffu, first_ll, 0));
         char *out = b.capture_stage + s * b.period * 8;
         for (uint32_t i = lane; i < b.period; i += 32) {
             uint64_t z = sx_synth_frame(b.seed + s, first + i);
@@ -112,13 +132,10 @@ __global__ void bank_capture_kernel(BankState b)
 
 // writeStream(stream, buf, period, flags, timeNs, timeoutUs > 0) for stream s: :989-1097.
 // time_ns == nullptr means "the timestamp of this stream's last read plus rx_time_offset_ns",
-// the repeater pattern (example/linear_repeater.py:64-69).
-__global__ void bank_tx_plan_kernel(BankState b, int flags, const long long *time_ns,
-                                    long long rx_time_offset_ns)
+// the repeater pattern (example/linear_repeater.py:64-69).  Run by one lane of the stream's warp.
+__device__ __forceinline__ void bank_plan_write(const BankState &b, uint64_t s, int flags,
+                                                const long long *time_ns, long long rx_time_offset_ns)
 {
-    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= b.nstreams)
-        return;
     long long clock = b.clock[s], pos = b.tx_position[s];
     const long long ring = (long long)b.ring, period = (long long)b.period;
     const long queued = long(pos - clock); // ALSA delay: written but not yet played
@@ -171,21 +188,39 @@ __global__ void bank_tx_plan_kernel(BankState b, int flags, const long long *tim
     b.clock[s] = clock;
 }
 
-// Silence for the forwarded-over region, then the block itself, into the stream's ring.
-__global__ void bank_tx_convert_kernel(BankState b, const char *cf32_in)
+// One warp per stream: lane 0 makes writeStream's decisions, then the warp writes silence for
+// the forwarded-over region and converts the block into the stream's playback ring.
+__global__ void bank_plan_write_kernel(BankState b, int flags, const long long *time_ns,
+                                       long long rx_time_offset_ns)
+{
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < b.nstreams)
+        bank_plan_write(b, s, flags, time_ns, rx_time_offset_ns);
+}
+
+__global__ void bank_tx_kernel(BankState b, const char *cf32_in, int flags, const long long *time_ns,
+                               long long rx_time_offset_ns, bool fused)
 {
     const uint32_t lane = threadIdx.x & 31, warps_per_cta = blockDim.x >> 5;
     const uint64_t nwarps = uint64_t(gridDim.x) * warps_per_cta;
     for (uint64_t s = uint64_t(blockIdx.x) * warps_per_cta + (threadIdx.x >> 5); s < b.nstreams; s += nwarps) {
-        const long long at = b.tx_write_position[s];
+        long long at = 0, gap = 0, start = 0;
+        if (lane == 0) {
+            if (fused)
+                bank_plan_write(b, s, flags, time_ns, rx_time_offset_ns);
+            at = b.tx_write_position[s];
+            gap = b.tx_gap_length[s];
+            start = b.tx_gap_start[s];
+        }
+        at = __shfl_sync(0xffffffffu, at, 0);
+        gap = __shfl_sync(0xffffffffu, gap, 0);
+        start = __shfl_sync(0xffffffffu, start, 0);
         if (at < 0)
             continue; // discarded
         char *ring = b.playback_ring + s * b.ring * 8;
 
         // ALSA plays zeros for regions the application skipped (silence_size = boundary, :493-496).
-        long long gap = b.tx_gap_length[s];
         if (gap > 0) {
-            long long start = b.tx_gap_start[s];
             if (gap > (long long)b.ring) { // older than one lap: only the last lap is still in the ring
                 start += gap - (long long)b.ring;
                 gap = (long long)b.ring;

@@ -971,6 +971,11 @@ template <class T> T *carve(char *&cursor, size_t count)
     return reinterpret_cast<T *>(p);
 }
 
+// Measured (profiles/r01_summary.md section 6): up to a few thousand streams an iteration is
+// launch-bound and planning inside the data kernels saves two launches; at 65536 streams the
+// separate thread-per-stream plan kernels are 20 % faster.
+constexpr uint32_t kBankFusedPlanStreams = 8192;
+
 cudaStream_t bank_stream(sxgpu_bank *bank, sxgpu_stream stream)
 {
     return stream ? static_cast<cudaStream_t>(stream) : bank->ctx->stream;
@@ -1107,11 +1112,13 @@ int sxgpu_bank_read(sxgpu_bank *bank, void *d_cf32, sxgpu_stream stream)
     SX_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = bank_stream(bank, stream);
     const BankState &b = bank->st;
-    bank_rx_plan_kernel<<<per_stream_grid(b.nstreams, 256), 256, 0, st>>>(b, static_cast<char *>(d_cf32));
-    bank_capture_kernel<<<per_warp_grid(ctx, b.nstreams, 256), 256, 0, st>>>(b);
+    const bool fused = b.nstreams <= kBankFusedPlanStreams;
+    if (!fused)
+        bank_plan_read_kernel<<<per_stream_grid(b.nstreams, 256), 256, 0, st>>>(b, static_cast<char *>(d_cf32));
+    bank_capture_kernel<<<per_warp_grid(ctx, b.nstreams, 256), 256, 0, st>>>(b, static_cast<char *>(d_cf32), fused);
     batch_warp_kernel<RxCf32><<<per_warp_grid(ctx, b.nstreams, 256), 256, 0, st>>>(b.rx_blocks, b.nstreams);
     SX_CUDA(ctx, cudaGetLastError());
-    ctx->launches += 3;
+    ctx->launches += fused ? 2 : 3;
     ctx->frames_rx += uint64_t(b.nstreams) * b.period;
     return SXGPU_OK;
 }
@@ -1127,12 +1134,14 @@ int sxgpu_bank_write(sxgpu_bank *bank, const void *d_cf32, int flags, const long
     SX_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = bank_stream(bank, stream);
     const BankState &b = bank->st;
-    bank_tx_plan_kernel<<<per_stream_grid(b.nstreams, 256), 256, 0, st>>>(b, flags, d_time_ns,
-                                                                       rx_time_offset_ns);
-    bank_tx_convert_kernel<<<per_warp_grid(ctx, b.nstreams, 256), 256, 0, st>>>(
-        b, static_cast<const char *>(d_cf32));
+    const bool fused = b.nstreams <= kBankFusedPlanStreams;
+    if (!fused)
+        bank_plan_write_kernel<<<per_stream_grid(b.nstreams, 256), 256, 0, st>>>(b, flags, d_time_ns,
+                                                                             rx_time_offset_ns);
+    bank_tx_kernel<<<per_warp_grid(ctx, b.nstreams, 256), 256, 0, st>>>(
+        b, static_cast<const char *>(d_cf32), flags, d_time_ns, rx_time_offset_ns, fused);
     SX_CUDA(ctx, cudaGetLastError());
-    ctx->launches += 2;
+    ctx->launches += fused ? 1 : 2;
     ctx->frames_tx += uint64_t(b.nstreams) * b.period;
     return SXGPU_OK;
 }

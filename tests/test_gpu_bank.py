@@ -133,16 +133,17 @@ def test_bank_constant_latency_at_every_rate(ctx):
                 assert (rxp == 256 * (k + 1)).all() and (txp == 256 * k + 768 + 256).all(), (rate, k)
 
 
-def test_bank_large_and_values_against_oracle(ctx, oracle):
+@pytest.mark.parametrize("S", [4096, 16384])       # planned inside the data kernels / by plan kernels
+def test_bank_large_and_values_against_oracle(ctx, oracle, S):
     from sxxcvr_b200 import Bank
-    S, P = 4096, 256
+    P = 256
     with Bank(ctx, S, P, 75000.0, 0.0, 77) as bank:
         cf = torch.empty(S * P * 2, dtype=torch.float32, device="cuda")
         for _ in range(3):
             bank.read(cf.data_ptr())
             bank.write(cf.data_ptr(), HAS_TIME, None, 10_240_000)
         got = cf.cpu().numpy().reshape(S, 2 * P)
-        for s in (0, 1, 2047, 4095):
+        for s in (0, 1, 2047, S - 1):
             frames = sxtest.synth_frames(oracle, 2 * P, P, seed=77 + s)
             want_cf = sxtest.oracle_rx(oracle, frames)
             assert np.array_equal(got[s].view(np.uint32), want_cf.view(np.uint32))
