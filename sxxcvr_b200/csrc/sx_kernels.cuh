@@ -398,6 +398,7 @@ struct BulkArgs {
     float thr2;
     int load_policy;  // see bulk::make_policy
     int store_policy;
+    int contiguous;   // 0: tile t belongs to CTA t mod grid (round robin); 1: each CTA owns one contiguous range
 };
 
 // Persistent CTAs; tile t of TILE frames belongs to CTA (t mod gridDim.x).  Per CTA a ring
@@ -417,10 +418,20 @@ __global__ void bulk_convert_kernel(const BulkArgs a)
     uint64_t *full = reinterpret_cast<uint64_t *>(out_buf + size_t(STAGES) * TILE * DFB);
 
     const uint64_t ntiles = (a.nframes + TILE - 1) / TILE;
-    const uint64_t first = blockIdx.x, stride = gridDim.x;
-    if (first >= ntiles)
+    // Tile i of this CTA is global tile first + i * stride.
+    uint64_t first, stride, mine;
+    if (a.contiguous) {
+        const uint64_t per = (ntiles + gridDim.x - 1) / gridDim.x;
+        first = uint64_t(blockIdx.x) * per;
+        stride = 1;
+        mine = first >= ntiles ? 0 : (ntiles - first < per ? ntiles - first : per);
+    } else {
+        first = blockIdx.x;
+        stride = gridDim.x;
+        mine = first >= ntiles ? 0 : (ntiles - first + stride - 1) / stride;
+    }
+    if (mine == 0)
         return;
-    const uint64_t mine = (ntiles - first + stride - 1) / stride; // tiles this CTA owns
     const uint64_t pol = bulk::make_policy(a.load_policy), pol_store = bulk::make_policy(a.store_policy);
 
     auto tile_frames = [&](uint64_t i) -> uint32_t {

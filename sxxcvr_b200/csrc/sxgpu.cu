@@ -55,6 +55,7 @@ struct sxgpu_ctx {
     int64_t ctas_per_sm = 0;                // 0 auto
     int64_t bulk_tile = 0, bulk_stages = 0; // 0 auto
     int64_t bulk_load_policy = 0, bulk_store_policy = 0; // L2 eviction: 0 first, 1 normal, 2 last, 3 unchanged
+    int64_t bulk_contiguous = 0;            // 0 round-robin tiles, 1 one contiguous range per CTA
     int64_t host_chunk_frames = 0;          // 0 auto (see pick_chunk_frames)
     int64_t host_mode = 0;                  // 0 auto, 1 copy engines, 2 zero-copy
     int64_t zero_copy_max_frames = 1 << 18; // measured crossover, profiles/r01_sweep_host_path.json
@@ -264,7 +265,7 @@ int launch_bulk(sxgpu_ctx *ctx, const char *src, const char *dst_c, uint64_t tot
 
     uint64_t mid = (total - head) / G * G;
     BulkArgs a = {src + head * SFB, dst + head * DFB, mid, thr2, int(ctx->bulk_load_policy),
-                  int(ctx->bulk_store_policy)};
+                  int(ctx->bulk_store_policy), int(ctx->bulk_contiguous)};
     uint64_t ntiles = (mid + shape.tile - 1) / shape.tile;
     int grid = persistent_grid(ctx, k, block, smem, ntiles);
     k<<<grid, block, smem, st>>>(a);
@@ -716,6 +717,7 @@ int64_t *option_slot(sxgpu_ctx *ctx, const char *key)
         {"bulk_stages", &ctx->bulk_stages},
         {"bulk_load_policy", &ctx->bulk_load_policy},
         {"bulk_store_policy", &ctx->bulk_store_policy},
+        {"bulk_contiguous", &ctx->bulk_contiguous},
         {"host_chunk_frames", &ctx->host_chunk_frames},
         {"host_mode", &ctx->host_mode},
         {"zero_copy_max_frames", &ctx->zero_copy_max_frames},
