@@ -60,6 +60,7 @@ struct sxgpu_ctx {
     int64_t host_mode = 0;                  // 0 auto, 1 copy engines, 2 zero-copy
     int64_t zero_copy_max_frames = 1 << 18; // measured crossover, profiles/r01_sweep_host_path.json
     int64_t resident_max_frames = 0;        // > 0: blocks up to this size go to the resident converter
+    int64_t zero_copy_variant = 1;          // schedule of the zero-copy kernel (1 vec128, 2 vec256, 3 bulk)
 
     // resident converter (sx_resident.cuh); guarded by host_mutex
     Mailbox *mailbox = nullptr;
@@ -572,8 +573,8 @@ int convert_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset, void *h_d
             frame_aligned && kernel_in != kernel_out) {
             SX_TRY(resident_convert_call(ctx, resident_op<Op>(), kernel_in, kernel_out, length, thr2));
         } else {
-            SX_TRY(launch_convert<Op>(ctx, kernel_in, kernel_out, length, thr2, both_on_device ? variant : 1,
-                                      ctx->s_comp));
+            SX_TRY(launch_convert<Op>(ctx, kernel_in, kernel_out, length, thr2,
+                                      both_on_device ? variant : ctx->zero_copy_variant, ctx->s_comp));
             SX_CUDA(ctx, cudaStreamSynchronize(ctx->s_comp));
         }
         if (bounce_out)
@@ -722,6 +723,7 @@ int64_t *option_slot(sxgpu_ctx *ctx, const char *key)
         {"host_mode", &ctx->host_mode},
         {"zero_copy_max_frames", &ctx->zero_copy_max_frames},
         {"resident_max_frames", &ctx->resident_max_frames},
+        {"zero_copy_variant", &ctx->zero_copy_variant},
     };
     for (auto &e : table)
         if (std::strcmp(e.name, key) == 0)
