@@ -16,10 +16,11 @@
  *  - `d_` pointers are device memory on the context's GPU, `h_` pointers host memory;
  *    the caller owns every buffer; src and dest must not overlap unless identical
  *    (in-place is allowed for the equal-width CF32 paths);
- *  - functions taking an `sxgpu_stream` are asynchronous with respect to it (NULL = the
- *    context's own stream) and may be called concurrently from several host threads as
- *    long as each thread uses its own stream; the *_host functions are synchronous and
- *    serialise on an internal lock;
+ *  - functions taking an `sxgpu_stream` are asynchronous with respect to it and may be
+ *    called concurrently from several host threads as long as each thread uses its own
+ *    stream; NULL selects the context's own stream, an ordinary (blocking) stream that
+ *    orders with the legacy default stream like any cudaStreamCreate() stream; the *_host
+ *    functions are synchronous and serialise on an internal lock;
  *  - there is no CPU fallback: without a usable sm_100 device sxgpu_init() fails.
  */
 #ifndef SXGPU_H

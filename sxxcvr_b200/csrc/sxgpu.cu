@@ -408,9 +408,11 @@ int ensure_ring(sxgpu_ctx *ctx, size_t frames, bool bounce_in, bool bounce_out)
 {
     HostRing &r = ctx->ring;
     if (!ctx->s_h2d) {
-        SX_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
-        SX_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking));
-        SX_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+        // Ordinary streams as well (they still run concurrently with each other): a device buffer
+        // the caller produced on the default stream is safe to hand to the synchronous calls.
+        SX_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamDefault));
+        SX_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamDefault));
+        SX_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamDefault));
     }
     if (!r.events) {
         for (int i = 0; i < kRingSlots; i++) {
@@ -795,7 +797,10 @@ int sxgpu_init(int device, sxgpu_ctx **out)
         return bail(SXGPU_ERR_NO_DEVICE);
     if (cudaSetDevice(device) != cudaSuccess)
         return bail(SXGPU_ERR_CUDA);
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess)
+    // An ordinary (blocking) stream: it orders with the legacy default stream exactly like any
+    // cudaStreamCreate() stream, so a caller that fills a buffer on the default stream and then
+    // converts it on "the context's stream" (or reads the result back) needs no extra sync.
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamDefault) != cudaSuccess)
         return bail(SXGPU_ERR_CUDA);
     if (cudaMalloc(&ctx->d_stats, sizeof(StatsAcc)) != cudaSuccess ||
         cudaHostAlloc(&ctx->h_stats, sizeof(StatsAcc), cudaHostAllocDefault) != cudaSuccess)
