@@ -9,6 +9,7 @@
 
 #include "sxgpu.h"
 
+#include <algorithm>
 #include <cerrno>
 #include <climits>
 #include <cmath>
@@ -213,6 +214,8 @@ SoapySXB200::SoapySXB200(const SoapySDR::Kwargs &args)
 SoapySXB200::~SoapySXB200()
 {
     SoapySDR_logf(SOAPY_SDR_INFO, "Uninitializing SoapySX (B200 stream path)");
+    unpin_all(rx_);
+    unpin_all(tx_);
     delete stage_rx_;
     delete stage_tx_;
     sxgpu_destroy(gpu_);
@@ -279,6 +282,7 @@ SoapySDR::Stream *SoapySXB200::setupStream(const int direction, const std::strin
     }
 
     ep.cs16 = want_cs16;
+    ep.pin_caller_buffers = kwarg(args, "pin", "0") == "1";
     ep.mode = (kwarg(args, "link", "") == "1") ? Endpoint::Mode::Linked : Endpoint::Mode::Normal;
     ep.configure(args.count("period") ? std::stoul(args.at("period")) : 0);
     ep.configured = true;
@@ -298,6 +302,46 @@ void SoapySXB200::closeStream(SoapySDR::Stream *stream)
     Endpoint *ep = endpoint_of(stream);
     std::scoped_lock lock(ep->mutex);
     ep->configured = false;
+    unpin_all(*ep);
+}
+
+// Stream argument pin=1 (ours; the reference has nothing like it).  SDR applications reuse one
+// or two sample buffers for the life of a stream, and those are pageable memory (a numpy array,
+// a std::vector), which the GPU can only reach through a CPU bounce copy.  With pin=1 the
+// driver page-locks each distinct (buffer, size) it is handed, once, so that later calls move
+// it by DMA.  The caller must keep such a buffer alive until closeStream: page-locking follows
+// the virtual address, and freed-then-reused memory would still look pinned.  Off by default.
+void SoapySXB200::pin_if_asked(Endpoint &ep, const void *buffer, size_t bytes)
+{
+    if (!ep.pin_caller_buffers || bytes == 0)
+        return;
+    for (const auto &known : ep.pinned)
+        if (known.first == buffer && known.second >= bytes)
+            return;
+    for (auto &known : ep.pinned) {
+        if (known.first == buffer) { // same buffer, now used with a larger size: pin again, larger
+            sxgpu_host_unregister(gpu_, const_cast<void *>(buffer));
+            known.second = 0;
+        }
+    }
+    if (sxgpu_host_register(gpu_, const_cast<void *>(buffer), bytes) == SXGPU_OK) {
+        ep.pinned.erase(std::remove_if(ep.pinned.begin(), ep.pinned.end(),
+                                       [&](const std::pair<const void *, size_t> &k) { return k.first == buffer; }),
+                        ep.pinned.end());
+        ep.pinned.emplace_back(buffer, bytes);
+    } else {
+        // Already pinned by the caller, overlapping another registration, or not pinnable: the
+        // conversion still works (in place if it is pinned, through the bounce copy if not).
+        SoapySDR_logf(SOAPY_SDR_DEBUG, "pin=1: buffer %p not registered (%s)", buffer, sxgpu_last_error(gpu_));
+    }
+}
+
+void SoapySXB200::unpin_all(Endpoint &ep)
+{
+    for (const auto &known : ep.pinned)
+        if (known.second)
+            sxgpu_host_unregister(gpu_, const_cast<void *>(known.first));
+    ep.pinned.clear();
 }
 
 size_t SoapySXB200::getStreamMTU(SoapySDR::Stream *stream) const
@@ -390,6 +434,7 @@ int SoapySXB200::readStream(SoapySDR::Stream *stream, void *const *buffs, const 
     ep.position += got;
 
     // I2S words -> CF32 on the GPU, straight out of pinned staging into the caller's buffer.
+    pin_if_asked(ep, buffs[0], numElems * (ep.cs16 ? 4 : 8));
     int rc = ep.cs16
                  ? sxgpu_convert_rx_buffer_cs16_host(gpu_, stage_rx_->data(), 0, buffs[0], 0, size_t(got))
                  : sxgpu_convert_rx_buffer_host(gpu_, stage_rx_->data(), 0, buffs[0], 0, size_t(got));
@@ -470,6 +515,7 @@ int SoapySXB200::writeStream(SoapySDR::Stream *stream, const void *const *buffs,
         return 0;
 
     // CF32 -> I2S words on the GPU, from the caller's buffer into pinned staging.
+    pin_if_asked(ep, buffs[0], numElems * (ep.cs16 ? 4 : 8));
     stage_tx_->reserve(length);
     int rc = ep.cs16 ? sxgpu_convert_tx_buffer_cs16_host(gpu_, buffs[0], 0, stage_tx_->data(), 0, length,
                                                          tx_threshold2_)

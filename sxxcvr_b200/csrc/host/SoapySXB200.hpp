@@ -23,6 +23,7 @@
 #include <cstdint>
 #include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "stream_plan.hpp"
@@ -42,6 +43,8 @@ struct Endpoint {
     mutable std::mutex mutex;
     Mode mode = Mode::Normal;
     bool cs16 = false; // EXTENSION: stream format CS16 instead of CF32 (device argument cs16=1)
+    bool pin_caller_buffers = false; // stream argument pin=1, see SoapySXB200::pin_if_asked
+    std::vector<std::pair<const void *, size_t>> pinned; // caller buffers this stream page-locked
     bool configured = false;
     bool active = false;
     int64_t position = 0; // frames read / written / skipped since the last reset
@@ -134,6 +137,8 @@ private:
     {
         return reinterpret_cast<Endpoint *>(stream);
     }
+    void pin_if_asked(Endpoint &ep, const void *buffer, size_t bytes);
+    void unpin_all(Endpoint &ep);
 
     sxgpu_ctx *gpu_ = nullptr;
     int gpu_ordinal_ = 0;
