@@ -139,7 +139,7 @@ def run_reference_arm(args, rank: int):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
 
 
 def workload_config(args, per_gpu_frames):
@@ -448,11 +448,44 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
                           "gathered_with": "nccl all_gather" if world > 1 else "local"},
             "device": info.name.decode(), "sm_count": info.sm_count,
         }
-        print(json.dumps(line), flush=True)
+        emit(json.dumps(line))
 
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+class QuietStdout:
+    """stdout must carry exactly one JSON line.  Native libraries write banners to file descriptor 1
+    (NCCL prints its version there when NCCL_DEBUG is set), so for the duration of the run fd 1
+    points at stderr; emit() restores it for the one line that matters."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, line: str):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        print(line, flush=True)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
+OUT = None
+
+
+def emit(line: str):
+    if OUT is not None:
+        OUT.emit(line)
+    else:
+        print(line, flush=True)
 
 
 def main():
@@ -475,10 +508,12 @@ def main():
                "--master-addr", "127.0.0.1", "--master-port", str(port), __file__] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd))
 
-    if args.impl == "reference":
-        run_reference_arm(args, rank)
-    else:
-        run_gpu_arm(args, rank, local_rank, world)
+    global OUT
+    with QuietStdout() as OUT:
+        if args.impl == "reference":
+            run_reference_arm(args, rank)
+        else:
+            run_gpu_arm(args, rank, local_rank, world)
 
 
 if __name__ == "__main__":
