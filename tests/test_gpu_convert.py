@@ -483,3 +483,33 @@ def test_full_size_block_by_properties(ctx, oracle):
     assert int(diff.max()) <= 260
     del diff
     assert ctx.stats_words(out.data_ptr(), 2 * n, 0)[4] == 0      # thr2 = 2.0 > max |z|^2: PA never enabled
+
+
+def test_maximum_block_of_the_sweep_4gib(ctx, oracle):
+    """BASELINE config 5's largest block: 2^29 frames = 4 GiB on the input side, 2^30 words, byte
+    offsets beyond 32 bits.  Sampled chunks (start, the 4 GiB-byte boundary, an odd place, the very
+    end) against the oracle in both directions, and shard-wise checksums that must add up."""
+    n = 1 << 29
+    i2s = torch.empty(2 * n, dtype=torch.int32, device="cuda")
+    cf = torch.empty(2 * n, dtype=torch.float32, device="cuda")
+    ctx.synth_frames(i2s.data_ptr(), 0, n, 99)
+    ctx.convert_rx_buffer(i2s.data_ptr(), 0, cf.data_ptr(), 0, n)
+    ctx.stream_sync()
+    spots = (0, (1 << 28) - 2048, (1 << 28), 333333333, n - 4096)
+    for first in spots:
+        frames = sxtest.synth_frames(oracle, first, 4096, seed=99)
+        assert np.array_equal(host(i2s[2 * first: 2 * (first + 4096)]), frames), first
+        want = sxtest.oracle_rx(oracle, frames)
+        assert np.array_equal(bits(host(cf[2 * first: 2 * (first + 4096)])), bits(want)), first
+    out = i2s          # reuse the input buffer for the TX result
+    ctx.convert_tx_buffer(cf.data_ptr(), 0, out.data_ptr(), 0, n, sxtest.THR2_DEFAULT)
+    ctx.stream_sync()
+    for first in spots:
+        want_cf = sxtest.oracle_rx(oracle, sxtest.synth_frames(oracle, first, 4096, seed=99))
+        assert np.array_equal(host(out[2 * first: 2 * (first + 4096)]), sxtest.oracle_tx(oracle, want_cf, sxtest.THR2_DEFAULT)), first
+    whole = ctx.stats_words(out.data_ptr(), 2 * n, 0)
+    cut = (1 << 29) + 6        # words; an unaligned cut
+    a = ctx.stats_words(out.data_ptr(), cut, 0)
+    b = ctx.stats_words(out.data_ptr() + 4 * cut, 2 * n - cut, cut)
+    from sxxcvr_b200 import sharding
+    assert whole == sharding.combine_stats([a, b]) and whole[3] == 2 * n
