@@ -495,7 +495,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log2-frames", type=int, default=27, help="frames per block per GPU (2^27 = 1 GiB in)")
-    ap.add_argument("--e2e-log2-frames", type=int, default=26)
+    ap.add_argument("--e2e-log2-frames", type=int, default=27, help="frames per block of the host-buffer leg (same as --log2-frames by default)")
     ap.add_argument("--cpu-log2-frames", type=int, default=26)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
