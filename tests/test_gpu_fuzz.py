@@ -33,7 +33,8 @@ def test_random_shapes_offsets_and_schedules(ctx, oracle):
     d_words = torch.from_numpy(words).cuda()
     d_floats = torch.from_numpy(floats).cuda()
     try:
-        for case in range(300):
+        import os
+        for case in range(int(os.environ.get("SX_FUZZ_CASES", "300"))):
             opts = {k: int(rng.choice(v)) for k, v in OPTIONS.items()}
             if opts["bulk_tile"] == 512:
                 opts["bulk_stages"] = 4
