@@ -392,7 +392,7 @@ __device__ __forceinline__ void fence_async_smem()
 } // namespace bulk
 
 struct BulkArgs {
-    const char *src;  // 16-byte aligned, start of the aligned middle
+    const char *src;  // 16-byte aligned, start of the aligned middle (SKEW: 8 bytes before it)
     char *dst;        // 16-byte aligned
     uint64_t nframes; // frames in the middle; nframes * frame bytes is a multiple of 16 on both sides
     float thr2;
@@ -407,14 +407,24 @@ struct BulkArgs {
 // 128-bit shared accesses; thread 0 then bulk-stores the output buffer and refills the
 // input buffer with the tile STAGES ahead.  An output buffer is rewritten only after the
 // bulk store that last read it has drained (wait_group.read).
-// Dynamic shared memory: STAGES * TILE * (src + dst frame bytes) + STAGES * 8.
-template <class Op, int TILE, int STAGES>
+// Dynamic shared memory: STAGES * (TILE * (src + dst frame bytes) + skew pad) + STAGES * 8.
+//
+// SKEW (8-byte frames on both sides only): the source is one frame out of step with the
+// destination -- 8 modulo 16 where the destination is 16-byte aligned -- which bulk copies
+// cannot express.  Then a.src is the source address rounded DOWN to 16 bytes, every tile
+// loads 16 bytes more than it needs (8 before, 8 after), and the conversion reads shared
+// memory 8 bytes in.  The host sizes head and tail so that this superset never leaves the
+// caller's range (launch_bulk).
+template <class Op, int TILE, int STAGES, bool SKEW = false>
 __global__ void bulk_convert_kernel(const BulkArgs a)
 {
     constexpr int SFB = Op::kSrcWords * 4, DFB = Op::kDstWords * 4; // frame bytes
+    static_assert(!SKEW || (SFB == 8 && DFB == 8), "the skewed variant is for 8-byte frames on both sides");
+    constexpr int PAD = SKEW ? 16 : 0;                 // extra bytes loaded per tile
+    constexpr size_t IN_STAGE = size_t(TILE) * SFB + PAD;
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char *in_buf = smem;
-    unsigned char *out_buf = smem + size_t(STAGES) * TILE * SFB;
+    unsigned char *out_buf = smem + size_t(STAGES) * IN_STAGE;
     uint64_t *full = reinterpret_cast<uint64_t *>(out_buf + size_t(STAGES) * TILE * DFB);
 
     const uint64_t ntiles = (a.nframes + TILE - 1) / TILE;
@@ -450,9 +460,9 @@ __global__ void bulk_convert_kernel(const BulkArgs a)
     if (threadIdx.x == 0) {
         for (uint64_t i = 0; i < uint64_t(STAGES) && i < mine; i++) {
             uint32_t nf = tile_frames(i);
-            bulk::mbar_expect_tx(&full[i], nf * SFB);
-            bulk::load_g2s(in_buf + i * TILE * SFB, a.src + (first + i * stride) * TILE * SFB,
-                           nf * SFB, &full[i], pol);
+            bulk::mbar_expect_tx(&full[i], nf * SFB + PAD);
+            bulk::load_g2s(in_buf + i * IN_STAGE, a.src + (first + i * stride) * TILE * SFB,
+                           nf * SFB + PAD, &full[i], pol);
         }
     }
 
@@ -470,17 +480,26 @@ __global__ void bulk_convert_kernel(const BulkArgs a)
 
         // 2 frames per access on the 8-byte/frame side; nf is even for every tile because
         // TILE is even and the middle is a whole number of 16-byte units.
-        const unsigned char *ib = in_buf + size_t(s) * TILE * SFB;
+        const unsigned char *ib = in_buf + size_t(s) * IN_STAGE + (SKEW ? 8 : 0);
         unsigned char *ob = out_buf + size_t(s) * TILE * DFB;
         constexpr int FR = (Op::kSrcWords == 1 || Op::kDstWords == 1) ? 4 : 2;
         for (uint32_t v = threadIdx.x; v * FR < nf; v += blockDim.x) {
             Pack<Op::kSrcWords * FR> in;
             Pack<Op::kDstWords * FR> out;
-            const uint4 *ip = reinterpret_cast<const uint4 *>(ib + size_t(v) * FR * SFB);
+            if constexpr (SKEW) { // 8 bytes off a 16-byte boundary: frame-wide shared loads
+                const uint2 *ip = reinterpret_cast<const uint2 *>(ib + size_t(v) * FR * SFB);
 #pragma unroll
-            for (int q = 0; q < Op::kSrcWords * FR / 4; q++) {
-                uint4 t = ip[q];
-                in.w[4 * q] = t.x, in.w[4 * q + 1] = t.y, in.w[4 * q + 2] = t.z, in.w[4 * q + 3] = t.w;
+                for (int q = 0; q < FR; q++) {
+                    uint2 t = ip[q];
+                    in.w[2 * q] = t.x, in.w[2 * q + 1] = t.y;
+                }
+            } else {
+                const uint4 *ip = reinterpret_cast<const uint4 *>(ib + size_t(v) * FR * SFB);
+#pragma unroll
+                for (int q = 0; q < Op::kSrcWords * FR / 4; q++) {
+                    uint4 t = ip[q];
+                    in.w[4 * q] = t.x, in.w[4 * q + 1] = t.y, in.w[4 * q + 2] = t.z, in.w[4 * q + 3] = t.w;
+                }
             }
             Op::template apply<FR>(in, out, a.thr2);
             uint4 *op = reinterpret_cast<uint4 *>(ob + size_t(v) * FR * DFB);
@@ -497,9 +516,9 @@ __global__ void bulk_convert_kernel(const BulkArgs a)
             uint64_t nxt = i + STAGES;
             if (nxt < mine) {
                 uint32_t nnf = tile_frames(nxt);
-                bulk::mbar_expect_tx(&full[s], nnf * SFB);
-                bulk::load_g2s(in_buf + size_t(s) * TILE * SFB,
-                               a.src + (first + nxt * stride) * TILE * SFB, nnf * SFB, &full[s], pol);
+                bulk::mbar_expect_tx(&full[s], nnf * SFB + PAD);
+                bulk::load_g2s(in_buf + size_t(s) * IN_STAGE,
+                               a.src + (first + nxt * stride) * TILE * SFB, nnf * SFB + PAD, &full[s], pol);
             }
         }
     }

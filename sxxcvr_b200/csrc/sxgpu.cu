@@ -167,9 +167,20 @@ template <class Op> BulkKernel bulk_kernel(BulkShape s)
     return nullptr;
 }
 
-template <class Op> size_t bulk_smem_bytes(BulkShape s)
+template <class Op> size_t bulk_smem_bytes(BulkShape s, bool skew = false)
 {
-    return size_t(s.stages) * s.tile * (Op::kSrcWords + Op::kDstWords) * 4 + size_t(s.stages) * 8;
+    return size_t(s.stages) * (size_t(s.tile) * (Op::kSrcWords + Op::kDstWords) * 4 + (skew ? 16 : 0)) +
+           size_t(s.stages) * 8;
+}
+
+// The one-frame-out-of-step variant exists for the two default shapes of the CF32 conversions.
+template <class Op> BulkKernel bulk_skew_kernel(BulkShape s)
+{
+    if constexpr (Op::kSrcWords == 2 && Op::kDstWords == 2) {
+        if (s.tile == 2048 && s.stages == 4) return bulk_convert_kernel<Op, 2048, 4, true>;
+        if (s.tile == 1024 && s.stages == 4) return bulk_convert_kernel<Op, 1024, 4, true>;
+    }
+    return nullptr;
 }
 
 int normalise_unroll(int64_t u)
@@ -251,21 +262,40 @@ int launch_bulk(sxgpu_ctx *ctx, const char *src, const char *dst_c, uint64_t tot
             break;
         }
     }
-    if (!found || total < head + G)
-        return SXGPU_OK; // caller falls back to the vector kernel
 
     // Measured (profiles/r01_summary.md): 2048-frame tiles x 4 stages for large blocks; below
     // 2^24 frames the 1024-frame tile spreads the fewer tiles over more SMs.
     BulkShape shape = {int(ctx->bulk_tile ? ctx->bulk_tile : (total >= (uint64_t(1) << 24) ? 2048 : 1024)),
                        int(ctx->bulk_stages ? ctx->bulk_stages : 4)};
-    BulkKernel k = bulk_kernel<Op>(shape);
-    if (!k)
-        return ctx->invalid("unsupported bulk_tile/bulk_stages combination");
-    size_t smem = bulk_smem_bytes<Op>(shape);
+    BulkKernel k = nullptr;
+    bool skew = false;
+    uint64_t mid = 0;
+    if (found) {
+        if (total < head + G)
+            return SXGPU_OK; // too short: the caller falls back to the vector kernel
+        mid = (total - head) / G * G;
+        k = bulk_kernel<Op>(shape);
+        if (!k)
+            return ctx->invalid("unsupported bulk_tile/bulk_stages combination");
+    } else {
+        // No head aligns both sides.  With 8-byte frames on both sides that means they are one
+        // frame out of step.  Pick the head (1 or 2 frames) that aligns the DESTINATION and is
+        // at least one frame, so that the 8 bytes the skewed loads take in front of the middle
+        // are the caller's own frame head-1; and keep at least one frame behind the middle, so
+        // that the 8 bytes taken after it are the caller's own too.
+        k = bulk_skew_kernel<Op>(shape);
+        if (!k || reinterpret_cast<uintptr_t>(src) % 8 || reinterpret_cast<uintptr_t>(dst) % 8)
+            return SXGPU_OK;
+        head = (reinterpret_cast<uintptr_t>(dst) % 16) ? 1 : 2;
+        if (total < head + 3)
+            return SXGPU_OK;
+        mid = (total - head - 1) / 2 * 2;
+        skew = true;
+    }
+    size_t smem = bulk_smem_bytes<Op>(shape, skew);
     int block = int(ctx->block ? ctx->block : 256);
 
-    uint64_t mid = (total - head) / G * G;
-    BulkArgs a = {src + head * SFB, dst + head * DFB, mid, thr2, int(ctx->bulk_load_policy),
+    BulkArgs a = {src + head * SFB - (skew ? 8 : 0), dst + head * DFB, mid, thr2, int(ctx->bulk_load_policy),
                   int(ctx->bulk_store_policy), int(ctx->bulk_contiguous)};
     uint64_t ntiles = (mid + shape.tile - 1) / shape.tile;
     int grid = persistent_grid(ctx, k, block, smem, ntiles);
@@ -274,6 +304,7 @@ int launch_bulk(sxgpu_ctx *ctx, const char *src, const char *dst_c, uint64_t tot
     ctx->launches++;
 
     // Up to G-1 frames on either side of the 16-byte-aligned middle.
+    // (Skewed: 1-2 frames in front and 1-2 behind.)
     uint64_t tail = total - head - mid;
     if (head) {
         StreamArgs e = {src, dst, head, head, 0, thr2};
@@ -737,10 +768,14 @@ template <class Op> int prepare_bulk_kernels(sxgpu_ctx *ctx)
 {
     const BulkShape shapes[] = {{4096, 3}, {3072, 4}, {2048, 6}, {2048, 5}, {2048, 4},
                                 {2048, 3}, {1024, 6}, {1024, 4}, {512, 4}};
-    for (BulkShape s : shapes)
+    for (BulkShape s : shapes) {
         SX_CUDA(ctx, cudaFuncSetAttribute(bulk_kernel<Op>(s),
                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           int(bulk_smem_bytes<Op>(s))));
+        if (BulkKernel skewed = bulk_skew_kernel<Op>(s))
+            SX_CUDA(ctx, cudaFuncSetAttribute(skewed, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              int(bulk_smem_bytes<Op>(s, true))));
+    }
     return SXGPU_OK;
 }
 
