@@ -21,6 +21,10 @@
  *    stream; NULL selects the context's own stream, an ordinary (blocking) stream that
  *    orders with the legacy default stream like any cudaStreamCreate() stream; the *_host
  *    functions are synchronous and serialise on an internal lock;
+ *  - the asynchronous functions only enqueue kernels (and, for host-resident batch
+ *    descriptors, stream-ordered allocations and copies) on the given stream, so after one
+ *    warm-up call they can be recorded with CUDA stream capture and replayed as a graph --
+ *    the way to run a launch-bound inner loop such as one bank iteration;
  *  - there is no CPU fallback: without a usable sm_100 device sxgpu_init() fails.
  */
 #ifndef SXGPU_H
