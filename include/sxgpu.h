@@ -159,7 +159,7 @@ typedef struct {
     uint64_t seed;
 } sxgpu_bank_config;
 int sxgpu_bank_create(sxgpu_ctx *ctx, const sxgpu_bank_config *config, sxgpu_bank **out);
-int sxgpu_bank_destroy(sxgpu_bank *bank);
+int sxgpu_bank_destroy(sxgpu_bank *bank); /* before sxgpu_destroy of its context, which refuses otherwise */
 /* Let `frames` sample periods pass on every stream. */
 int sxgpu_bank_advance(sxgpu_bank *bank, int64_t frames, sxgpu_stream stream);
 /* d_cf32: [nstreams][period] CF32 samples on the device. */

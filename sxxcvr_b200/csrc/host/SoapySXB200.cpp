@@ -195,8 +195,8 @@ SoapySXB200::SoapySXB200(const SoapySDR::Kwargs &args)
     setFrequency(SOAPY_SDR_RX, 0, 433.92e6, SoapySDR::Kwargs());
     setFrequency(SOAPY_SDR_TX, 0, 433.92e6, SoapySDR::Kwargs());
 
-    stage_rx_ = new PinnedFrames(gpu_);
-    stage_tx_ = new PinnedFrames(gpu_);
+    stage_rx_ = std::make_unique<PinnedFrames>(gpu_);
+    stage_tx_ = std::make_unique<PinnedFrames>(gpu_);
     try {
         // Same initial staging size as the reference (:704-707).
         stage_rx_->reserve(8192);
@@ -204,8 +204,8 @@ SoapySXB200::SoapySXB200(const SoapySDR::Kwargs &args)
         rx_.open();
         tx_.open();
     } catch (...) {
-        delete stage_rx_;
-        delete stage_tx_;
+        stage_rx_.reset(); // pinned memory goes back before the context that owns it
+        stage_tx_.reset();
         sxgpu_destroy(gpu_);
         throw;
     }
@@ -216,8 +216,8 @@ SoapySXB200::~SoapySXB200()
     SoapySDR_logf(SOAPY_SDR_INFO, "Uninitializing SoapySX (B200 stream path)");
     unpin_all(rx_);
     unpin_all(tx_);
-    delete stage_rx_;
-    delete stage_tx_;
+    stage_rx_.reset(); // pinned memory goes back before the context that owns it
+    stage_tx_.reset();
     sxgpu_destroy(gpu_);
 }
 

@@ -21,6 +21,7 @@
 #include <alsa/asoundlib.h>
 
 #include <cstdint>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <utility>
@@ -157,8 +158,8 @@ private:
     float tx_threshold2_ = 0.0f;
     bool linked_ = false;
 
-    PinnedFrames *stage_rx_ = nullptr;
-    PinnedFrames *stage_tx_ = nullptr;
+    std::unique_ptr<PinnedFrames> stage_rx_;
+    std::unique_ptr<PinnedFrames> stage_tx_;
 };
 
 } // namespace sxhost

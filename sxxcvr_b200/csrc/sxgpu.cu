@@ -67,6 +67,7 @@ struct sxgpu_ctx {
     cudaStream_t s_resident = nullptr;
     unsigned long long resident_seq = 0;
     std::atomic<uint64_t> resident_launches{0}, resident_calls{0};
+    std::atomic<int> live_banks{0}; // banks keep a pointer to their context
 
     // host pipeline
     std::mutex host_mutex;
@@ -852,6 +853,8 @@ int sxgpu_destroy(sxgpu_ctx *ctx)
 {
     if (!ctx)
         return SXGPU_ERR_INVALID;
+    if (ctx->live_banks.load() != 0)
+        return ctx->invalid("destroy the context's stream banks first");
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     HostRing &r = ctx->ring;
@@ -1108,6 +1111,7 @@ int sxgpu_bank_create(sxgpu_ctx *ctx, const sxgpu_bank_config *config, sxgpu_ban
     b.rx_blocks = carve<BlockDesc>(cur, n);
     b.capture_stage = carve<char>(cur, n * geo.period * 8);
     b.playback_ring = carve<char>(cur, n * geo.buffer * 8);
+    ctx->live_banks++;
     *out = bank;
     return SXGPU_OK;
 }
@@ -1119,6 +1123,7 @@ int sxgpu_bank_destroy(sxgpu_bank *bank)
     cudaSetDevice(bank->ctx->device);
     cudaDeviceSynchronize();
     cudaFree(bank->arena);
+    bank->ctx->live_banks--;
     delete bank;
     return SXGPU_OK;
 }

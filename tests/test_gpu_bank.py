@@ -194,3 +194,13 @@ def test_asynchronous_entry_points_can_be_captured_into_a_cuda_graph(ctx, oracle
         for s_ in (0, 63):
             want = sxtest.oracle_rx(oracle, sxtest.synth_frames(oracle, 4 * P, P, seed=5 + s_))
             assert np.array_equal(got[s_].view(np.uint32), want.view(np.uint32))
+
+
+def test_context_refuses_to_die_before_its_banks():
+    from sxxcvr_b200 import Bank, Context
+    c = Context(0)
+    bank = Bank(c, 4, 256, 75000.0, 0.0, 1)
+    assert c.lib.sxgpu_destroy(c.handle) == -1          # SXGPU_ERR_INVALID, context still alive
+    assert b"banks first" in c.lib.sxgpu_last_error(c.handle)
+    bank.close()
+    c.close()
