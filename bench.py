@@ -455,6 +455,94 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
         dist.destroy_process_group()
 
 
+def run_bank_arm(args, rank: int, local_rank: int, world: int):
+    """--workload bank: BASELINE config 4.  S HBM-resident stream pairs per GPU (streams sharded
+    over the ranks in contiguous ranges), one step = readStream(256) on every stream followed by
+    writeStream(256, HAS_TIME, rx time + 768 frames) on every stream.  Same JSON contract; there is
+    no host-buffer leg because the bank exists to keep the samples off PCIe."""
+    import torch
+    import torch.distributed as dist
+    from sxxcvr_b200 import Bank, Context, sharding
+
+    torch.cuda.set_device(local_rank)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ctx = Context(local_rank)
+    S, P, rate = args.streams, 256, 75000.0
+    lat_ns = int(round(768 * 1e9 / rate))
+    side = torch.cuda.Stream()
+    torch.cuda.set_stream(side)
+    st = side.cuda_stream
+    bank = Bank(ctx, S, P, rate, 0.0, SEED + rank * S)          # this rank's streams: ids rank*S .. rank*S+S-1
+    cf = torch.empty(S * P * 2, dtype=torch.float32, device="cuda")
+
+    def step():
+        bank.read(cf.data_ptr(), st)
+        bank.write(cf.data_ptr(), 4, None, lat_ns, st)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    run = step
+    if args.graph:
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            step()
+        run = g.replay
+        run()
+    barrier()
+    launches0 = ctx.counter("launches")
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    a.record(side)
+    for _ in range(args.steps):
+        run()
+    b.record(side)
+    barrier()
+    ms = a.elapsed_time(b) / args.steps
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    launches = ctx.counter("launches") - launches0
+    _, rxp, txp = bank.positions(st)
+    ok = bool(((txp - rxp) == 768).all())
+    ring = bank.playback(0, int(txp[0]) - P, P, st)
+    stats = ctx.stats_words(cf.data_ptr(), 2 * S * P, 0, st)
+    checks = [list(c) for c in sharding.gather_stats(stats, device="cuda")]
+    peak, peak_src = measured_peak()
+    value = world * 2 * S * P / (ms * 1e-3) / 1e6
+    if rank == 0:
+        emit(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "s32<->f32", "data": "synthetic",
+            "config": {"workload": "BASELINE config 4: bank of HBM-resident stream pairs, per step readStream(256) + "
+                                   "writeStream(256, HAS_TIME, rx time + 768 frames) on every stream",
+                       "streams_per_gpu": S, "frames_per_block": P, "sample_rate": rate,
+                       "cuda_graph_replay": bool(args.graph),
+                       "parallelism": f"streams sharded over {world} GPU(s) in contiguous ranges, no data-path collective"},
+            "roofline": {"kernel": "bank iteration (stand-in DMA 8 W + RX 8 R + 8 W + TX 8 R + 8 W per frame)",
+                         "bound": "hbm", "achieved": 40 * S * P / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": 40 * S * P / (ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src},
+            "e2e": None, "gpu_launches": launches if not args.graph else None, "cpu_baseline": None,
+            "constant_latency_holds": ok, "last_block_nonzero": bool(ring.any()),
+            "checksums": {"fields": list(sharding.STATS_FIELDS), "per_rank": checks,
+                          "combined": list(sharding.combine_stats(checks))},
+        }))
+    bank.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 class QuietStdout:
     """stdout must carry exactly one JSON line.  Native libraries write banners to file descriptor 1
     (NCCL prints its version there when NCCL_DEBUG is set), so for the duration of the run fd 1
@@ -498,6 +586,10 @@ def main():
     ap.add_argument("--e2e-log2-frames", type=int, default=27, help="frames per block of the host-buffer leg (same as --log2-frames by default)")
     ap.add_argument("--cpu-log2-frames", type=int, default=26)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="blocks", choices=["blocks", "bank"],
+                    help="blocks: the judged RX+TX block workload (default); bank: BASELINE config 4")
+    ap.add_argument("--streams", type=int, default=65536, help="--workload bank: stream pairs per GPU")
+    ap.add_argument("--graph", action="store_true", help="--workload bank: replay the step from a CUDA graph")
     args = ap.parse_args()
 
     rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
@@ -512,6 +604,8 @@ def main():
     with QuietStdout() as OUT:
         if args.impl == "reference":
             run_reference_arm(args, rank)
+        elif args.workload == "bank":
+            run_bank_arm(args, rank, local_rank, world)
         else:
             run_gpu_arm(args, rank, local_rank, world)
 
