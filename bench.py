@@ -365,7 +365,7 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
     checks = [list(c) for c in sharding.gather_stats(stats, device="cuda")]
 
     # ---- end to end: host buffers through the C ABI, PCIe copies inside the timed region -------
-    e2e_frames = 1 << args.e2e_log2_frames
+    e2e_frames = min(1 << args.e2e_log2_frames, frames)   # its inputs are a prefix of the device-resident ones
     h_i2s = torch.empty(2 * e2e_frames, dtype=torch.int32).pin_memory()
     h_cf_out = torch.empty(2 * e2e_frames, dtype=torch.float32).pin_memory()
     h_cf_in = torch.empty(2 * e2e_frames, dtype=torch.float32).pin_memory()
