@@ -13,6 +13,8 @@ against this repo's SoapySDR/ALSA stand-ins) and writes
   tests/golden/stream_traces.json  what an application observes when the scenarios in
                                    tests/sxstream.py drive the reference's readStream/writeStream
                                    (SoapySX.cpp:868-1105) over the deterministic ALSA stub
+  tests/golden/stream_fuzz_traces.json  the same for the 40 default seeds of the random-script
+                                   fuzzer in tests/test_gpu_stream_fuzz.py
 
 The reference itself ships no golden vectors (SoapySX/test/README.md:1-4); these files are the
 pin.  TX vectors are restricted to the domain where the reference is defined C++ (no NaN, both
@@ -75,6 +77,11 @@ def main():
     h = sxstream.Harness(sxstream.REF_LIB)
     traces = {name: sxstream.normalise(fn(h)) for name, fn in sxstream.SCENARIOS.items()}
     (HERE / "stream_traces.json").write_text(json.dumps(traces, indent=0, separators=(",", ":")) + "\n")
+    # the default seeds of the stream-level differential fuzzer (tests/test_gpu_stream_fuzz.py)
+    import test_gpu_stream_fuzz as fuzz
+    fuzz_traces = {str(seed): fuzz.run_script(h, fuzz.make_script(seed)) for seed in range(1000, 1040)}
+    (HERE / "stream_fuzz_traces.json").write_text(json.dumps(fuzz_traces, separators=(",", ":")) + "\n")
+    print("wrote", HERE / "stream_fuzz_traces.json", (HERE / "stream_fuzz_traces.json").stat().st_size, "bytes")
     print("wrote", HERE / "convert_kat.json", (HERE / "convert_kat.json").stat().st_size, "bytes")
     print("wrote", HERE / "stream_traces.json", (HERE / "stream_traces.json").stat().st_size, "bytes")
 

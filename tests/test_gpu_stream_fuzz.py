@@ -100,13 +100,21 @@ def run_script(h, sc):
     return sxstream.normalise(tr)
 
 
+GOLDEN_FUZZ = sxstream.ROOT / "tests" / "golden" / "stream_fuzz_traces.json"
+
+
 @pytest.fixture(scope="module")
 def harnesses():
     from sxxcvr_b200 import _build
     _build.build_soapy_module()
-    if not sxstream.REF_LIB.exists():
-        pytest.skip("oracle/_ref/libsx_ref.so not present: nothing to differ against")
-    return sxstream.Harness(sxstream.PRODUCT_LIB), sxstream.Harness(sxstream.REF_LIB)
+    ref = sxstream.Harness(sxstream.REF_LIB) if sxstream.REF_LIB.exists() else None
+    return sxstream.Harness(sxstream.PRODUCT_LIB), ref
+
+
+@pytest.fixture(scope="module")
+def golden_fuzz():
+    import json
+    return json.loads(GOLDEN_FUZZ.read_text())
 
 
 import os
@@ -115,11 +123,20 @@ NSEEDS = int(os.environ.get("SX_FUZZ_SEEDS", "40"))      # a soak run raises thi
 
 
 @pytest.mark.parametrize("seed", range(NSEEDS))
-def test_random_script_matches_reference(harnesses, seed):
+def test_random_script_matches_reference(harnesses, golden_fuzz, seed):
+    """Against the live reference driver when oracle/_ref is present, and against the committed
+    traces it generated (tests/golden/stream_fuzz_traces.json) for the default seeds."""
     product, ref = harnesses
     sc = make_script(1000 + seed)
-    want = run_script(ref, sc)
     got = run_script(product, sc)
+    golden = golden_fuzz.get(str(sc["seed"]))
+    if golden is not None:
+        assert got == golden, f"seed {sc['seed']}: product differs from the committed reference trace"
+    if ref is None:
+        if golden is None:
+            pytest.skip("no live reference and no committed trace for this seed")
+        return
+    want = run_script(ref, sc)
     for i, (g, w) in enumerate(zip(got, want)):
         assert g == w, f"seed {sc['seed']} step {i}: product {g} != reference {w}"
     assert len(got) == len(want)

@@ -32,3 +32,12 @@ def test_golden_repeater_has_constant_latency():
     assert all(b[1] == 256 and b[2] == 4 and b[5] == 256 for b in blocks)       # ret, HAS_TIME, written
     timeline = [t for t in tr if t[0] == "timeline"][0][1]
     assert timeline["written"] == [[768, 256 * len(blocks)]]                  # TX lands 768 frames after RX
+
+
+def test_reference_reproduces_golden_fuzz_traces(ref_harness):
+    """The 40 default random scripts of tests/test_gpu_stream_fuzz.py, reference side only."""
+    import test_gpu_stream_fuzz as fuzz
+    golden = json.loads(fuzz.GOLDEN_FUZZ.read_text())
+    assert sorted(golden) == [str(s) for s in range(1000, 1040)]
+    for seed, want in golden.items():
+        assert fuzz.run_script(ref_harness, fuzz.make_script(int(seed))) == want, seed
