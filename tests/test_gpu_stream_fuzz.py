@@ -27,7 +27,7 @@ def make_script(seed):
     ops = []
     for _ in range(int(rng.integers(40, 90))):
         r = rng.random()
-        n = int(rng.choice([1, 7, 100, 256, 257, 1000, 4096, 20000]))
+        n = int(rng.choice([0, 1, 7, 100, 256, 257, 1000, 4096, 20000]))
         timeout = int(rng.choice([100000, 100000, 100000, 0, -1]))
         if r < 0.35:
             ops.append(("read", n, timeout))
