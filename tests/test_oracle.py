@@ -117,6 +117,37 @@ def test_tx_properties(oracle, vals, thr2):
     assert ((exact - top >= 0) & (exact - top < 4) | (exact < 0) & (top - exact <= 0) & (exact - top < 4)).all()
 
 
+def numpy_tx(f: np.ndarray, thr2: float) -> np.ndarray:
+    """A second, independent restatement of SoapySX.cpp:116-137 (ARM semantics where C++ is
+    undefined), in numpy float32 arithmetic: every operation is a single IEEE single-precision
+    operation, so nothing can be fused."""
+    f = np.ascontiguousarray(f, np.float32)
+    one, two31 = np.float32(1.0), np.float32(2147483648.0)
+    with np.errstate(invalid="ignore", over="ignore"):
+        c = np.where(one < f, one, f)                       # std::min(f, 1.0f): NaN stays
+        c = np.where(c < -one, -one, c).astype(np.float32)  # std::max(., -1.0f)
+        p = (c * two31).astype(np.float32)
+        t = np.trunc(p.astype(np.float64))
+        v = np.where(np.isnan(p), 0.0, np.clip(t, -2.0**31, 2.0**31 - 1)).astype(np.int64)
+        v = (v & 0xFFFFFFFC).astype(np.uint32)
+        pairs = f.reshape(-1, 2)
+        mag2 = ((pairs[:, 0] * pairs[:, 0]).astype(np.float32) + (pairs[:, 1] * pairs[:, 1]).astype(np.float32)).astype(np.float32)
+        on = mag2 >= np.float32(thr2)
+    out = v.reshape(-1, 2).copy()
+    out[on, 0] |= 3
+    return out.ravel()
+
+
+@pytest.mark.parametrize("thr2", [sxtest.THR2_DEFAULT, 0.0, 0.25, 2.0, float("nan")])
+def test_oracle_agrees_with_an_independent_numpy_restatement(oracle, thr2):
+    sets = [sxtest.tx_uniform(1 << 16), sxtest.tx_gaussian_defined(1 << 16), sxtest.tx_specials(),
+            sxtest.tx_threshold_circle(1 << 16, sxtest.THR2_DEFAULT), sxtest.tx_threshold_circle(1 << 14, 0.25)]
+    rng = np.random.default_rng(3)
+    sets.append(rng.integers(0, 2**32, size=1 << 17, dtype=np.uint64).astype(np.uint32).view(np.float32))  # any bit pattern
+    for f in sets:
+        assert np.array_equal(bits(sxtest.oracle_tx(oracle, f, thr2)), numpy_tx(f, thr2))
+
+
 def test_rx_then_tx_is_not_identity_but_close(oracle):
     w = sxtest.rx_uniform(1 << 16)
     back = sxtest.oracle_tx(oracle, sxtest.oracle_rx(oracle, w), 3.0)
