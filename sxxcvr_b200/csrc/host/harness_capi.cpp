@@ -282,6 +282,114 @@ int sxh_set_gain(sxh_device *h, int direction, double gain)
     });
 }
 
+// name == NULL or "" selects the overall gain.
+int sxh_set_gain_element(sxh_device *h, int direction, const char *name, double gain)
+{
+    return guarded([&] {
+        if (name && *name)
+            h->dev->setGain(direction, 0, name, gain);
+        else
+            h->dev->setGain(direction, 0, gain);
+        return 0;
+    });
+}
+
+int sxh_get_gain(sxh_device *h, int direction, const char *name, double *gain)
+{
+    return guarded([&] {
+        *gain = (name && *name) ? h->dev->getGain(direction, 0, name) : h->dev->getGain(direction, 0);
+        return 0;
+    });
+}
+
+// out[0..2] = minimum, maximum, step
+int sxh_gain_range(sxh_device *h, int direction, const char *name, double *out)
+{
+    return guarded([&] {
+        SoapySDR::Range r = (name && *name) ? h->dev->getGainRange(direction, 0, name)
+                                            : h->dev->getGainRange(direction, 0);
+        out[0] = r.minimum(), out[1] = r.maximum(), out[2] = r.step();
+        return 0;
+    });
+}
+
+static const char *joined(const std::vector<std::string> &items)
+{
+    t_text.clear();
+    for (const auto &i : items) {
+        if (!t_text.empty())
+            t_text += ",";
+        t_text += i;
+    }
+    return t_text.c_str();
+}
+
+const char *sxh_list_gains(sxh_device *h, int direction)
+{
+    t_text.clear();
+    guarded([&] {
+        joined(h->dev->listGains(direction, 0));
+        return 0;
+    });
+    return t_text.c_str();
+}
+
+const char *sxh_list_antennas(sxh_device *h, int direction)
+{
+    t_text.clear();
+    guarded([&] {
+        joined(h->dev->listAntennas(direction, 0));
+        return 0;
+    });
+    return t_text.c_str();
+}
+
+int sxh_set_antenna(sxh_device *h, int direction, const char *name)
+{
+    return guarded([&] {
+        h->dev->setAntenna(direction, 0, name);
+        return 0;
+    });
+}
+
+const char *sxh_get_antenna(sxh_device *h, int direction)
+{
+    t_text.clear();
+    guarded([&] {
+        t_text = h->dev->getAntenna(direction, 0);
+        return 0;
+    });
+    return t_text.c_str();
+}
+
+int sxh_read_registers(sxh_device *h, const char *name, unsigned addr, size_t length, unsigned *out)
+{
+    return guarded([&] {
+        std::vector<unsigned> v = h->dev->readRegisters(name ? name : "", addr, length);
+        for (size_t i = 0; i < v.size() && i < length; i++)
+            out[i] = v[i];
+        return int(v.size());
+    });
+}
+
+int sxh_write_registers(sxh_device *h, const char *name, unsigned addr, const unsigned *values, size_t length)
+{
+    return guarded([&] {
+        h->dev->writeRegisters(name ? name : "", addr, std::vector<unsigned>(values, values + length));
+        return 0;
+    });
+}
+
+const char *sxh_read_setting(sxh_device *h, const char *key)
+{
+    t_text.clear();
+    guarded([&] {
+        t_text = h->dev->readSetting(key);
+        return 0;
+    });
+    return t_text.c_str();
+}
+
 int sxh_write_setting(sxh_device *h, const char *key, const char *value)
 {
     return guarded([&] {

@@ -231,9 +231,27 @@ std::vector<std::string> Device::listGains(const int, const size_t) const
 }
 void Device::setGain(const int, const size_t, const double) {}
 void Device::setGain(const int, const size_t, const std::string &, const double) {}
-double Device::getGain(const int, const size_t) const { return 0.0; }
+// Overall gain, as upstream's default does it: the elements' gains above their minima, summed,
+// on top of the overall minimum.  (The SoapySX driver only implements the named elements,
+// reference SoapySX.cpp:1279-1394, and relies on these defaults for the overall figures.)
+double Device::getGain(const int direction, const size_t channel) const
+{
+    double gain = 0.0;
+    for (const auto &name : listGains(direction, channel))
+        gain += getGain(direction, channel, name) - getGainRange(direction, channel, name).minimum();
+    return gain + getGainRange(direction, channel).minimum();
+}
 double Device::getGain(const int, const size_t, const std::string &) const { return 0.0; }
-Range Device::getGainRange(const int, const size_t) const { return Range(0.0, 0.0); }
+Range Device::getGainRange(const int direction, const size_t channel) const
+{
+    double lowest = 0.0, span = 0.0;
+    for (const auto &name : listGains(direction, channel)) {
+        const Range r = getGainRange(direction, channel, name);
+        lowest += r.minimum();
+        span += r.maximum() - r.minimum();
+    }
+    return Range(lowest, lowest + span);
+}
 Range Device::getGainRange(const int, const size_t, const std::string &) const
 {
     return Range(0.0, 0.0);
