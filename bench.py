@@ -288,6 +288,14 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def all_ranks(x: float):
+        if world == 1:
+            return [x]
+        mine = torch.tensor([x], dtype=torch.float64, device="cuda")
+        every = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        return [float(t.item()) for t in every]
+
     ctx = Context(local_rank)
     frames = 1 << args.log2_frames
     side = torch.cuda.Stream()  # a real stream handle: 0 would mean "the context's own stream"
@@ -366,10 +374,21 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
 
     # ---- end to end: host buffers through the C ABI, PCIe copies inside the timed region -------
     e2e_frames = min(1 << args.e2e_log2_frames, frames)   # its inputs are a prefix of the device-resident ones
-    h_i2s = torch.empty(2 * e2e_frames, dtype=torch.int32).pin_memory()
-    h_cf_out = torch.empty(2 * e2e_frames, dtype=torch.float32).pin_memory()
-    h_cf_in = torch.empty(2 * e2e_frames, dtype=torch.float32).pin_memory()
-    h_i2s_out = torch.empty(2 * e2e_frames, dtype=torch.int32).pin_memory()
+    # Pinned host buffers from the library's own allocator: it places them on the GPU's NUMA
+    # node (option numa_local_alloc), which is what lets N ranks use N PCIe links at once.
+    ctx.set_option("numa_local_alloc", args.numa_local)
+    pinned = []
+
+    def pinned_words(nwords, dtype):
+        import ctypes
+        addr = ctx.malloc_host(4 * nwords)
+        pinned.append(addr)
+        return torch.frombuffer((ctypes.c_char * (4 * nwords)).from_address(addr), dtype=dtype)
+
+    h_i2s = pinned_words(2 * e2e_frames, torch.int32)
+    h_cf_out = pinned_words(2 * e2e_frames, torch.float32)
+    h_cf_in = pinned_words(2 * e2e_frames, torch.float32)
+    h_i2s_out = pinned_words(2 * e2e_frames, torch.int32)
     h_i2s.copy_(i2s_in[: 2 * e2e_frames].cpu())
     h_cf_in.copy_(cf[: 2 * e2e_frames].cpu())
 
@@ -389,6 +408,8 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
     e2e_sec = (time.perf_counter() - t0) / args.steps
     barrier()
     e2e_launches = ctx.counter("launches") - l0
+    e2e_per_rank = [2 * e2e_frames / t / 1e6 for t in all_ranks(e2e_sec)]
+    numa_nodes = [int(v) for v in all_ranks(float(ctx.get_option("numa_node")))]
     e2e_sec = max_over_ranks(e2e_sec)
     e2e_value = world * 2 * e2e_frames / e2e_sec / 1e6
 
@@ -441,7 +462,10 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
                     "d2h_bytes_per_step": 2 * 8 * e2e_frames, "frames_per_block": e2e_frames,
                     "ms_per_step": e2e_sec * 1e3, "gpu_launches": e2e_launches,
                     "api": "sxgpu_convert_rx_buffer_host + sxgpu_convert_tx_buffer_host, pinned host buffers",
-                    "bound": "PCIe: 16 B/frame cross the link each way"},
+                    "bound": "PCIe: 16 B/frame cross the link each way",
+                    "per_rank": [round(v, 1) for v in e2e_per_rank],
+                    "host_numa": {"gpu_numa_node_per_rank": numa_nodes,
+                                  "pinned_memory_on_gpu_node": bool(args.numa_local)}},
             "gpu_launches": launches, "clocks": clocks, "cpu_baseline": cpu, "small_blocks": small,
             "checksums": {"fields": list(sharding.STATS_FIELDS), "per_rank": checks,
                           "combined": list(sharding.combine_stats(checks)),
@@ -450,6 +474,9 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
         }
         emit(json.dumps(line))
 
+    del h_i2s, h_cf_out, h_cf_in, h_i2s_out
+    for addr in pinned:
+        ctx.free_host(addr)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -586,6 +613,8 @@ def main():
     ap.add_argument("--e2e-log2-frames", type=int, default=27, help="frames per block of the host-buffer leg (same as --log2-frames by default)")
     ap.add_argument("--cpu-log2-frames", type=int, default=26)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--numa-local", type=int, default=1, choices=[0, 1],
+                    help="place the host-buffer leg's pinned memory on the GPU's NUMA node (default 1)")
     ap.add_argument("--workload", default="blocks", choices=["blocks", "bank"],
                     help="blocks: the judged RX+TX block workload (default); bank: BASELINE config 4")
     ap.add_argument("--streams", type=int, default=65536, help="--workload bank: stream pairs per GPU")

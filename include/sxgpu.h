@@ -231,7 +231,7 @@ int sxgpu_synth_frames(sxgpu_ctx *ctx, void *d_i2s, uint64_t first_frame, size_t
 
 int sxgpu_malloc(sxgpu_ctx *ctx, void **d_ptr, size_t bytes);
 int sxgpu_free(sxgpu_ctx *ctx, void *d_ptr);
-int sxgpu_malloc_host(sxgpu_ctx *ctx, void **h_ptr, size_t bytes); /* pinned */
+int sxgpu_malloc_host(sxgpu_ctx *ctx, void **h_ptr, size_t bytes); /* pinned, on the GPU's NUMA node */
 int sxgpu_free_host(sxgpu_ctx *ctx, void *h_ptr);
 int sxgpu_host_register(sxgpu_ctx *ctx, void *h_ptr, size_t bytes); /* pin caller memory */
 int sxgpu_host_unregister(sxgpu_ctx *ctx, void *h_ptr);
@@ -256,6 +256,12 @@ int sxgpu_stream_sync(sxgpu_ctx *ctx, sxgpu_stream stream); /* NULL = context st
  *                               kernel through a doorbell in pinned memory instead of a kernel
  *                               launch + stream sync each (period-sized blocks, SoapySX.cpp:451);
  *                               the kernel leaves by itself after 2 ms without work
+ *   "numa_local_alloc"          1 (default): pinned host memory this library allocates
+ *                               (sxgpu_malloc_host, the bounce buffers of the *_host pipeline) is
+ *                               faulted in while the calling thread is confined to the CPUs next to
+ *                               the GPU, so it lands on the GPU's NUMA node; the thread's affinity
+ *                               is restored before the call returns.  0 = leave placement alone
+ *   "numa_node"                 read-only: the GPU's NUMA node, -1 if the system reports none
  */
 int sxgpu_set_option(sxgpu_ctx *ctx, const char *key, int64_t value);
 int sxgpu_get_option(sxgpu_ctx *ctx, const char *key, int64_t *value);

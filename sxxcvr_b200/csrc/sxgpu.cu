@@ -20,6 +20,8 @@
 #include <string>
 #include <tuple>
 
+#include <sched.h>
+
 using namespace sx;
 
 // ---------------------------------------------------------------------------------------
@@ -61,6 +63,12 @@ struct sxgpu_ctx {
     int64_t zero_copy_max_frames = 1 << 18; // measured crossover, profiles/r01_sweep_host_path.json
     int64_t resident_max_frames = 0;        // > 0: blocks up to this size go to the resident converter
     int64_t zero_copy_variant = 1;          // schedule of the zero-copy kernel (1 vec128, 2 vec256, 3 bulk)
+    int64_t numa_local_alloc = 1;           // place pinned host memory on the GPU's NUMA node
+    int64_t numa_node = -1;                 // read-only: the GPU's NUMA node, -1 unknown / no NUMA
+
+    // CPUs local to the GPU (sysfs local_cpulist of its PCI function); empty set = unknown
+    cpu_set_t local_cpus;
+    bool have_local_cpus = false;
 
     // resident converter (sx_resident.cuh); guarded by host_mutex
     Mailbox *mailbox = nullptr;
@@ -104,6 +112,84 @@ struct sxgpu_ctx {
         return SXGPU_ERR_INVALID;
     }
 };
+
+namespace {
+
+// Which CPUs sit next to this GPU?  Linux publishes it per PCI function; a VM without NUMA
+// topology lists every CPU and node -1, and then there is nothing to choose.
+void read_gpu_locality(sxgpu_ctx *ctx)
+{
+    CPU_ZERO(&ctx->local_cpus);
+    char bdf[32] = {0};
+    if (cudaDeviceGetPCIBusId(bdf, sizeof bdf, ctx->device) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    for (char *c = bdf; *c; c++)
+        if (*c >= 'A' && *c <= 'F')
+            *c = char(*c - 'A' + 'a'); // sysfs spells the address in lower case
+    const std::string base = std::string("/sys/bus/pci/devices/") + bdf + "/";
+    if (FILE *f = std::fopen((base + "numa_node").c_str(), "r")) {
+        long node = -1;
+        if (std::fscanf(f, "%ld", &node) == 1)
+            ctx->numa_node = node;
+        std::fclose(f);
+    }
+    if (FILE *f = std::fopen((base + "local_cpulist").c_str(), "r")) {
+        // "0-15,64-79": comma-separated CPU numbers and inclusive ranges
+        int lo = 0, hi = 0, count = 0;
+        for (;;) {
+            if (std::fscanf(f, "%d", &lo) != 1)
+                break;
+            hi = lo;
+            int c = std::fgetc(f);
+            if (c == '-') {
+                if (std::fscanf(f, "%d", &hi) != 1)
+                    break;
+                c = std::fgetc(f);
+            }
+            for (int cpu = lo; cpu <= hi && cpu < CPU_SETSIZE; cpu++, count++)
+                CPU_SET(cpu, &ctx->local_cpus);
+            if (c != ',')
+                break;
+        }
+        std::fclose(f);
+        ctx->have_local_cpus = count > 0;
+    }
+}
+
+// While one of these lives, the calling thread runs only on CPUs next to the GPU, so that
+// pages the thread faults in (cudaHostAlloc pins fresh pages in the caller's context) come
+// from the GPU's NUMA node and its DMA does not cross the socket interconnect.  The previous
+// affinity comes back on destruction; the memory stays where it was placed.
+class NearGpu {
+public:
+    explicit NearGpu(sxgpu_ctx *ctx)
+    {
+        if (!ctx->numa_local_alloc || !ctx->have_local_cpus)
+            return;
+        if (sched_getaffinity(0, sizeof saved_, &saved_) != 0)
+            return;
+        cpu_set_t want;
+        CPU_AND(&want, &saved_, &ctx->local_cpus); // never widen what the caller was given
+        if (CPU_COUNT(&want) == 0 || CPU_EQUAL(&want, &saved_))
+            return;
+        bound_ = sched_setaffinity(0, sizeof want, &want) == 0;
+    }
+    ~NearGpu()
+    {
+        if (bound_)
+            sched_setaffinity(0, sizeof saved_, &saved_);
+    }
+    NearGpu(const NearGpu &) = delete;
+    NearGpu &operator=(const NearGpu &) = delete;
+
+private:
+    cpu_set_t saved_;
+    bool bound_ = false;
+};
+
+} // namespace
 
 #define SX_CUDA(ctx, call)                                                                     \
     do {                                                                                       \
@@ -469,6 +555,7 @@ int ensure_ring(sxgpu_ctx *ctx, size_t frames, bool bounce_in, bool bounce_out)
         }
         r.chunk_frames = frames;
     }
+    NearGpu near(ctx);
     for (int i = 0; i < kRingSlots; i++) {
         if (bounce_in && !r.h_in[i])
             SX_CUDA(ctx, cudaHostAlloc(&r.h_in[i], r.chunk_frames * 8, cudaHostAllocDefault));
@@ -758,6 +845,8 @@ int64_t *option_slot(sxgpu_ctx *ctx, const char *key)
         {"zero_copy_max_frames", &ctx->zero_copy_max_frames},
         {"resident_max_frames", &ctx->resident_max_frames},
         {"zero_copy_variant", &ctx->zero_copy_variant},
+        {"numa_local_alloc", &ctx->numa_local_alloc},
+        {"numa_node", &ctx->numa_node},
     };
     for (auto &e : table)
         if (std::strcmp(e.name, key) == 0)
@@ -838,6 +927,7 @@ int sxgpu_init(int device, sxgpu_ctx **out)
     // converts it on "the context's stream" (or reads the result back) needs no extra sync.
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamDefault) != cudaSuccess)
         return bail(SXGPU_ERR_CUDA);
+    read_gpu_locality(ctx);
     if (cudaMalloc(&ctx->d_stats, sizeof(StatsAcc)) != cudaSuccess ||
         cudaHostAlloc(&ctx->h_stats, sizeof(StatsAcc), cudaHostAllocDefault) != cudaSuccess)
         return bail(SXGPU_ERR_NOMEM);
@@ -1398,6 +1488,7 @@ int sxgpu_malloc_host(sxgpu_ctx *ctx, void **h_ptr, size_t bytes)
     if (!ctx || !h_ptr)
         return SXGPU_ERR_INVALID;
     SX_CUDA(ctx, cudaSetDevice(ctx->device));
+    NearGpu near(ctx);
     SX_CUDA(ctx, cudaHostAlloc(h_ptr, bytes, cudaHostAllocPortable | cudaHostAllocMapped));
     return SXGPU_OK;
 }
@@ -1480,6 +1571,8 @@ int sxgpu_set_option(sxgpu_ctx *ctx, const char *key, int64_t value)
         return ctx->invalid("unknown option");
     if (value < 0)
         return ctx->invalid("option values are non-negative");
+    if (slot == &ctx->numa_node)
+        return ctx->invalid("numa_node is read-only");
     std::lock_guard<std::mutex> lock(ctx->host_mutex);
     *slot = value;
     return SXGPU_OK;
