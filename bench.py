@@ -507,12 +507,19 @@ def run_bank_arm(args, rank: int, local_rank: int, world: int):
     side = torch.cuda.Stream()
     torch.cuda.set_stream(side)
     st = side.cuda_stream
+    if args.repeat_variant is not None:
+        ctx.set_option("bank_repeat_variant", args.repeat_variant)
+    if args.ctas_per_sm is not None:
+        ctx.set_option("ctas_per_sm", args.ctas_per_sm)
     bank = Bank(ctx, S, P, rate, 0.0, SEED + rank * S)          # this rank's streams: ids rank*S .. rank*S+S-1
     cf = torch.empty(S * P * 2, dtype=torch.float32, device="cuda")
 
     def step():
-        bank.read(cf.data_ptr(), st)
-        bank.write(cf.data_ptr(), 4, None, lat_ns, st)
+        if args.fused:
+            bank.repeat(cf.data_ptr(), lat_ns, st)      # the same iteration as one launch
+        else:
+            bank.read(cf.data_ptr(), st)
+            bank.write(cf.data_ptr(), 4, None, lat_ns, st)
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -555,8 +562,14 @@ def run_bank_arm(args, rank: int, local_rank: int, world: int):
                                    "writeStream(256, HAS_TIME, rx time + 768 frames) on every stream",
                        "streams_per_gpu": S, "frames_per_block": P, "sample_rate": rate,
                        "cuda_graph_replay": bool(args.graph),
+                       "bank_repeat_variant": ctx.get_option("bank_repeat_variant") if args.fused else None,
+                       "ctas_per_sm": ctx.get_option("ctas_per_sm"),
+                       "calls_per_step": "sxgpu_bank_repeat (one launch)" if args.fused
+                                         else "sxgpu_bank_read + sxgpu_bank_write",
                        "parallelism": f"streams sharded over {world} GPU(s) in contiguous ranges, no data-path collective"},
-            "roofline": {"kernel": "bank iteration (stand-in DMA 8 W + RX 8 R + 8 W + TX 8 R + 8 W per frame)",
+            "roofline": {"kernel": "bank iteration (stand-in DMA 8 W + RX 8 R + 8 W + TX 8 R + 8 W per frame"
+                                   + ("; fused: the two reads are served from L2, 24 B/frame reach HBM)" if args.fused else ")"),
+                         "hbm_bytes_per_frame": 24 if args.fused else 40,
                          "bound": "hbm", "achieved": 40 * S * P / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": 40 * S * P / (ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src},
             "e2e": None, "gpu_launches": launches if not args.graph else None, "cpu_baseline": None,
@@ -619,6 +632,10 @@ def main():
                     help="blocks: the judged RX+TX block workload (default); bank: BASELINE config 4")
     ap.add_argument("--streams", type=int, default=65536, help="--workload bank: stream pairs per GPU")
     ap.add_argument("--graph", action="store_true", help="--workload bank: replay the step from a CUDA graph")
+    ap.add_argument("--repeat-variant", type=int, default=None, help="--fused: option bank_repeat_variant")
+    ap.add_argument("--ctas-per-sm", type=int, default=None, help="option ctas_per_sm (persistent grids)")
+    ap.add_argument("--fused", action="store_true",
+                    help="--workload bank: the iteration as one sxgpu_bank_repeat launch instead of read + write")
     args = ap.parse_args()
 
     rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)

@@ -168,6 +168,12 @@ int sxgpu_bank_read(sxgpu_bank *bank, void *d_cf32, sxgpu_stream stream);
  * when d_time_ns is NULL, at the timestamp its last read returned plus rx_time_offset_ns. */
 int sxgpu_bank_write(sxgpu_bank *bank, const void *d_cf32, int flags, const long long *d_time_ns,
                      long long rx_time_offset_ns, sxgpu_stream stream);
+/* The repeater iteration (example/linear_repeater.py:50-71 without its filters) in one launch:
+ * sxgpu_bank_read(bank, d_cf32) followed by sxgpu_bank_write(bank, d_cf32, SOAPY_SDR_HAS_TIME,
+ * NULL, rx_time_offset_ns).  Same state, results, CF32 block and playback ring as the two calls;
+ * each stream's three stages run back to back on one warp, so the intermediate reads are served
+ * from L2 and only the writes reach HBM. */
+int sxgpu_bank_repeat(sxgpu_bank *bank, void *d_cf32, long long rx_time_offset_ns, sxgpu_stream stream);
 /* Per-stream results of the last read / write and the counters, copied to host arrays of
  * nstreams elements (any pointer may be NULL).  These synchronise with `stream`. */
 int sxgpu_bank_last_read(sxgpu_bank *bank, int32_t *h_ret, int32_t *h_flags, int64_t *h_time_ns,

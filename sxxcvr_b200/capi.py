@@ -68,6 +68,7 @@ SIGNATURES = {
     "sxgpu_bank_advance": (C.c_int, [_P, C.c_int64, _P]),
     "sxgpu_bank_read": (C.c_int, [_P, _P, _P]),
     "sxgpu_bank_write": (C.c_int, [_P, _P, C.c_int, _P, C.c_longlong, _P]),
+    "sxgpu_bank_repeat": (C.c_int, [_P, _P, C.c_longlong, _P]),
     "sxgpu_bank_last_read": (C.c_int, [_P, _P, _P, _P, _P]),
     "sxgpu_bank_last_write": (C.c_int, [_P, _P, _P]),
     "sxgpu_bank_positions": (C.c_int, [_P, _P, _P, _P, _P]),
@@ -295,6 +296,10 @@ class Bank:
     def write(self, d_cf32, flags=4, d_time_ns=None, rx_time_offset_ns=0, stream=None):
         self.ctx.check(self.lib.sxgpu_bank_write(self.handle, d_cf32, flags, d_time_ns, rx_time_offset_ns, stream),
                        "sxgpu_bank_write")
+
+    def repeat(self, d_cf32, rx_time_offset_ns=0, stream=None):
+        """read(d_cf32) then write(d_cf32, HAS_TIME, rx time + offset) in one launch."""
+        self.ctx.check(self.lib.sxgpu_bank_repeat(self.handle, d_cf32, rx_time_offset_ns, stream), "sxgpu_bank_repeat")
 
     def last_read(self, stream=None):
         np = self.np

@@ -188,8 +188,48 @@ __device__ __forceinline__ void bank_plan_write(const BankState &b, uint64_t s, 
     b.clock[s] = clock;
 }
 
-// One warp per stream: lane 0 makes writeStream's decisions, then the warp writes silence for
-// the forwarded-over region and converts the block into the stream's playback ring.
+// The data side of writeStream for stream s, done by one warp: silence for the forwarded-over
+// region [start, start + gap), then the block converted into the playback ring at counter `at`
+// (at < 0: the block was discarded as late, nothing is written).
+__device__ __forceinline__ void bank_play_block(const BankState &b, uint64_t s, const char *cf32_in, long long at,
+                                                long long gap, long long start, uint32_t lane)
+{
+    if (at < 0)
+        return;
+    char *ring = b.playback_ring + s * b.ring * 8;
+
+    // ALSA plays zeros for regions the application skipped (silence_size = boundary, :493-496).
+    if (gap > 0) {
+        if (gap > (long long)b.ring) { // older than one lap: only the last lap is still in the ring
+            start += gap - (long long)b.ring;
+            gap = (long long)b.ring;
+        }
+        Pack<2> zero;
+        zero.w[0] = zero.w[1] = 0;
+        for (long long i = lane; i < gap; i += 32)
+            st_stream<8>(ring + size_t(uint64_t(start + i) % b.ring) * 8, zero);
+        // A gap of a whole lap or more silences the slots the block is about to take.
+        __syncwarp();
+    }
+
+    // The block may straddle the end of the ring: at most two contiguous spans.
+    const uint64_t offset = uint64_t(at) % b.ring;
+    const uint64_t first_span = (b.ring - offset < b.period) ? b.ring - offset : b.period;
+    BlockDesc d;
+    d.thr2 = b.thr2;
+    d.reserved = 0;
+    d.src = cf32_in + s * b.period * 8;
+    d.dst = ring + offset * 8;
+    d.length = first_span;
+    convert_span<TxCf32>(d, 0, first_span, lane, 32);
+    if (first_span < b.period) {
+        d.src = cf32_in + (s * b.period + first_span) * 8;
+        d.dst = ring;
+        d.length = b.period - first_span;
+        convert_span<TxCf32>(d, 0, d.length, lane, 32);
+    }
+}
+
 __global__ void bank_plan_write_kernel(BankState b, int flags, const long long *time_ns,
                                        long long rx_time_offset_ns)
 {
@@ -198,6 +238,8 @@ __global__ void bank_plan_write_kernel(BankState b, int flags, const long long *
         bank_plan_write(b, s, flags, time_ns, rx_time_offset_ns);
 }
 
+// One warp per stream: lane 0 makes writeStream's decisions, then the warp writes silence for
+// the forwarded-over region and converts the block into the stream's playback ring.
 __global__ void bank_tx_kernel(BankState b, const char *cf32_in, int flags, const long long *time_ns,
                                long long rx_time_offset_ns, bool fused)
 {
@@ -215,39 +257,117 @@ __global__ void bank_tx_kernel(BankState b, const char *cf32_in, int flags, cons
         at = __shfl_sync(0xffffffffu, at, 0);
         gap = __shfl_sync(0xffffffffu, gap, 0);
         start = __shfl_sync(0xffffffffu, start, 0);
-        if (at < 0)
-            continue; // discarded
-        char *ring = b.playback_ring + s * b.ring * 8;
+        bank_play_block(b, s, cf32_in, at, gap, start, lane);
+    }
+}
 
-        // ALSA plays zeros for regions the application skipped (silence_size = boundary, :493-496).
-        if (gap > 0) {
-            if (gap > (long long)b.ring) { // older than one lap: only the last lap is still in the ring
-                start += gap - (long long)b.ring;
-                gap = (long long)b.ring;
-            }
-            Pack<2> zero;
-            zero.w[0] = zero.w[1] = 0;
-            for (long long i = lane; i < gap; i += 32)
-                st_stream<8>(ring + size_t(uint64_t(start + i) % b.ring) * 8, zero);
-            // A gap of a whole lap or more silences the slots the block is about to take.
-            __syncwarp();
+// The repeater iteration in one launch: readStream(period) on every stream, then
+// writeStream(period, HAS_TIME, that read's timestamp + rx_time_offset_ns) of the block just
+// read (example/linear_repeater.py:50-71 without the filters).  State and results are exactly
+// those of bank_read followed by bank_write; what changes is the schedule.  A CTA takes 32
+// streams at a time: its first warp takes the 32 streams' decisions, one stream per lane, and
+// hands them over in shared memory; then each warp carries its streams through all three
+// stages -- stand-in DMA into the capture slot, RX conversion into the caller's CF32 block, TX
+// conversion into the playback ring -- so each stage reads what the previous one has just
+// written while it is still in L2, and only the three writes (24 B/frame) reach HBM instead of
+// 40 B/frame over five launches.
+constexpr int kRepeatGroup = 32;
+
+__global__ void __launch_bounds__(256) bank_repeat_kernel(BankState b, char *cf32, long long rx_time_offset_ns)
+{
+    __shared__ long long s_first[kRepeatGroup], s_at[kRepeatGroup], s_gap[kRepeatGroup], s_start[kRepeatGroup];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps_per_cta = blockDim.x >> 5;
+    const uint64_t ngroups = (uint64_t(b.nstreams) + kRepeatGroup - 1) / kRepeatGroup;
+    for (uint64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+        const uint64_t base = g * kRepeatGroup;
+        const uint32_t count = uint32_t(b.nstreams - base < kRepeatGroup ? b.nstreams - base : kRepeatGroup);
+        if (threadIdx.x < count) {
+            const uint64_t s = base + threadIdx.x;
+            bank_plan_read(b, s, cf32);
+            bank_plan_write(b, s, SX_HAS_TIME, nullptr, rx_time_offset_ns);
+            s_first[threadIdx.x] = b.rx_first_frame[s];
+            s_at[threadIdx.x] = b.tx_write_position[s];
+            s_gap[threadIdx.x] = b.tx_gap_length[s];
+            s_start[threadIdx.x] = b.tx_gap_start[s];
         }
+        __syncthreads();
+        for (uint32_t j = warp; j < count; j += warps_per_cta) {
+            const uint64_t s = base + j;
+            const uint64_t first = uint64_t(s_first[j]);
+            char *slot = b.capture_stage + s * b.period * 8;
+            for (uint32_t i = lane; i < b.period; i += 32) {
+                uint64_t z = sx_synth_frame(b.seed + s, first + i);
+                Pack<2> p;
+                p.w[0] = uint32_t(z);
+                p.w[1] = uint32_t(z >> 32);
+                st_stream<8>(slot + size_t(i) * 8, p);
+            }
+            __syncwarp(); // the slot is complete before any lane reads it back
+            BlockDesc d;
+            d.src = slot;
+            d.dst = cf32 + s * b.period * 8;
+            d.length = b.period;
+            d.thr2 = 0.0f;
+            d.reserved = 0;
+            convert_span<RxCf32>(d, 0, d.length, lane, 32);
+            __syncwarp(); // the CF32 block is complete before the TX stage reads it
+            bank_play_block(b, s, cf32, s_at[j], s_gap[j], s_start[j], lane);
+        }
+        __syncthreads(); // the next group's plans overwrite the shared arrays
+    }
+}
 
-        // The block may straddle the end of the ring: at most two contiguous spans.
-        const uint64_t offset = uint64_t(at) % b.ring;
-        const uint64_t first_span = (b.ring - offset < b.period) ? b.ring - offset : b.period;
-        BlockDesc d;
-        d.thr2 = b.thr2;
-        d.reserved = 0;
-        d.src = cf32_in + s * b.period * 8;
-        d.dst = ring + offset * 8;
-        d.length = first_span;
-        convert_span<TxCf32>(d, 0, first_span, lane, 32);
-        if (first_span < b.period) {
-            d.src = cf32_in + (s * b.period + first_span) * 8;
-            d.dst = ring;
-            d.length = b.period - first_span;
-            convert_span<TxCf32>(d, 0, d.length, lane, 32);
+// The same iteration with every warp on its own: a warp takes K consecutive streams at a time,
+// lanes 0..K-1 take their decisions, and the warp then carries them through the three stages.
+// No shared memory, no CTA barrier, and K sets the granularity: small K spreads S streams more
+// evenly over the resident warps, large K spends fewer issue slots on the (one-lane-per-stream)
+// decisions.
+template <int K>
+__global__ void __launch_bounds__(256) bank_repeat_warp_kernel(BankState b, char *cf32, long long rx_time_offset_ns)
+{
+    const uint32_t lane = threadIdx.x & 31, warps_per_cta = blockDim.x >> 5;
+    const uint64_t nwarps = uint64_t(gridDim.x) * warps_per_cta;
+    const uint64_t nchunks = (uint64_t(b.nstreams) + K - 1) / K;
+    for (uint64_t c = uint64_t(blockIdx.x) * warps_per_cta + (threadIdx.x >> 5); c < nchunks; c += nwarps) {
+        const uint64_t base = c * K;
+        const uint32_t count = uint32_t(b.nstreams - base < K ? b.nstreams - base : K);
+        long long my_first = 0, my_at = -1, my_gap = 0, my_start = 0;
+        if (lane < count) {
+            const uint64_t s = base + lane;
+            bank_plan_read(b, s, cf32);
+            bank_plan_write(b, s, SX_HAS_TIME, nullptr, rx_time_offset_ns);
+            my_first = b.rx_first_frame[s];
+            my_at = b.tx_write_position[s];
+            my_gap = b.tx_gap_length[s];
+            my_start = b.tx_gap_start[s];
+        }
+#pragma unroll
+        for (uint32_t j = 0; j < K; j++) {
+            const uint64_t first = uint64_t(__shfl_sync(0xffffffffu, my_first, j));
+            const long long at = __shfl_sync(0xffffffffu, my_at, j);
+            const long long gap = __shfl_sync(0xffffffffu, my_gap, j);
+            const long long start = __shfl_sync(0xffffffffu, my_start, j);
+            if (j >= count)
+                break;
+            const uint64_t s = base + j;
+            char *slot = b.capture_stage + s * b.period * 8;
+            for (uint32_t i = lane; i < b.period; i += 32) {
+                uint64_t z = sx_synth_frame(b.seed + s, first + i);
+                Pack<2> p;
+                p.w[0] = uint32_t(z);
+                p.w[1] = uint32_t(z >> 32);
+                st_stream<8>(slot + size_t(i) * 8, p);
+            }
+            __syncwarp();
+            BlockDesc d;
+            d.src = slot;
+            d.dst = cf32 + s * b.period * 8;
+            d.length = b.period;
+            d.thr2 = 0.0f;
+            d.reserved = 0;
+            convert_span<RxCf32>(d, 0, d.length, lane, 32);
+            __syncwarp();
+            bank_play_block(b, s, cf32, at, gap, start, lane);
         }
     }
 }

@@ -63,6 +63,7 @@ struct sxgpu_ctx {
     int64_t zero_copy_max_frames = 1 << 18; // measured crossover, profiles/r01_sweep_host_path.json
     int64_t resident_max_frames = 0;        // > 0: blocks up to this size go to the resident converter
     int64_t zero_copy_variant = 1;          // schedule of the zero-copy kernel (1 vec128, 2 vec256, 3 bulk)
+    int64_t bank_repeat_variant = 0;        // 0 = 32 streams per CTA round; 1, 2, 4 = K streams per warp round
     int64_t numa_local_alloc = 1;           // place pinned host memory on the GPU's NUMA node
     int64_t numa_node = -1;                 // read-only: the GPU's NUMA node, -1 unknown / no NUMA
 
@@ -845,6 +846,7 @@ int64_t *option_slot(sxgpu_ctx *ctx, const char *key)
         {"zero_copy_max_frames", &ctx->zero_copy_max_frames},
         {"resident_max_frames", &ctx->resident_max_frames},
         {"zero_copy_variant", &ctx->zero_copy_variant},
+        {"bank_repeat_variant", &ctx->bank_repeat_variant},
         {"numa_local_alloc", &ctx->numa_local_alloc},
         {"numa_node", &ctx->numa_node},
     };
@@ -1281,6 +1283,38 @@ int sxgpu_bank_write(sxgpu_bank *bank, const void *d_cf32, int flags, const long
         b, static_cast<const char *>(d_cf32), flags, d_time_ns, rx_time_offset_ns, fused);
     SX_CUDA(ctx, cudaGetLastError());
     ctx->launches += fused ? 1 : 2;
+    ctx->frames_tx += uint64_t(b.nstreams) * b.period;
+    return SXGPU_OK;
+}
+
+int sxgpu_bank_repeat(sxgpu_bank *bank, void *d_cf32, long long rx_time_offset_ns, sxgpu_stream stream)
+{
+    if (!bank)
+        return SXGPU_ERR_INVALID;
+    sxgpu_ctx *ctx = bank->ctx;
+    if (!d_cf32 || reinterpret_cast<uintptr_t>(d_cf32) % 8)
+        return ctx->invalid("CF32 buffer must be 8-byte aligned device memory");
+    SX_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = bank_stream(bank, stream);
+    const BankState &b = bank->st;
+    char *cf = static_cast<char *>(d_cf32);
+    auto warp_variant = [&](auto kernel, uint64_t k) {
+        const uint64_t chunks = (uint64_t(b.nstreams) + k - 1) / k;
+        kernel<<<persistent_grid(ctx, kernel, 256, 0, (chunks + 7) / 8), 256, 0, st>>>(b, cf, rx_time_offset_ns);
+    };
+    switch (ctx->bank_repeat_variant) {
+    case 1: warp_variant(bank_repeat_warp_kernel<1>, 1); break;
+    case 2: warp_variant(bank_repeat_warp_kernel<2>, 2); break;
+    case 4: warp_variant(bank_repeat_warp_kernel<4>, 4); break;
+    default: {
+        const uint64_t groups = (uint64_t(b.nstreams) + kRepeatGroup - 1) / kRepeatGroup;
+        bank_repeat_kernel<<<persistent_grid(ctx, bank_repeat_kernel, 256, 0, groups), 256, 0, st>>>(
+            b, cf, rx_time_offset_ns);
+    }
+    }
+    SX_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    ctx->frames_rx += uint64_t(b.nstreams) * b.period;
     ctx->frames_tx += uint64_t(b.nstreams) * b.period;
     return SXGPU_OK;
 }

@@ -204,3 +204,86 @@ def test_context_refuses_to_die_before_its_banks():
     assert b"banks first" in c.lib.sxgpu_last_error(c.handle)
     bank.close()
     c.close()
+
+
+def snapshot(bank, cf, nstreams):
+    """Everything an application could observe of a bank: results, counters, CF32 block, rings."""
+    ret, fl, t = bank.last_read()
+    clock, rxp, txp = bank.positions()
+    rings = []
+    for s in range(nstreams):
+        end = int(txp[s])
+        start = max(0, end - bank.ring)
+        rings.append((start, bank.playback(s, start, end - start)))
+    return {"read": (ret.copy(), fl.copy(), t.copy()), "write": bank.last_write().copy(),
+            "positions": (clock.copy(), rxp.copy(), txp.copy()), "cf": cf.cpu().numpy().view(np.uint32).copy(),
+            "rings": rings}
+
+
+def assert_same(a, b, where):
+    for key in ("read", "positions"):
+        for x, y in zip(a[key], b[key]):
+            assert np.array_equal(x, y), (where, key)
+    assert np.array_equal(a["write"], b["write"]), (where, "write")
+    assert np.array_equal(a["cf"], b["cf"]), (where, "cf")
+    for s, ((sa, ra), (sb, rb)) in enumerate(zip(a["rings"], b["rings"])):
+        assert sa == sb and np.array_equal(ra, rb), (where, "ring", s)
+
+
+@pytest.mark.parametrize("nstreams,period,rate,thr2", [
+    (3, 256, 75000.0, 0.0),
+    (37, 256, 75000.0, 1.0e-6),      # one whole group of 32 streams and a ragged one
+    (5, 1000, 300000.0, 1.0e-6),     # ring of 65000 frames: blocks straddle the wrap at odd offsets
+    (70, 3, 600000.0, 0.0),          # odd ring, tiny blocks: frame-wide accesses only
+    (2, 4096, 32.0e6 / 1536, 0.25),
+])
+@pytest.mark.parametrize("variant", [0, 1, 2, 4])
+def test_repeat_is_read_then_write(ctx, nstreams, period, rate, thr2, variant):
+    """sxgpu_bank_repeat against the two calls it fuses, through overruns, late (discarded)
+    bursts, far-ahead bursts (forward-and-wait with silence) and interleaved separate calls."""
+    from sxxcvr_b200 import Bank
+    lat = int(round(768 * 1e9 / rate))
+    steps = [(0, lat)] * 5 + [(70000, lat)] + [(0, lat)] * 3 + [(0, -1_000_000_000)] + [(0, lat)] * 2
+    steps += [(0, int(2.5e9)), (0, lat), (5, lat), (100000, lat), (0, lat)]
+    ctx.set_option("bank_repeat_variant", variant)
+    with Bank(ctx, nstreams, period, rate, thr2, sxtest.SEED) as two_calls, \
+            Bank(ctx, nstreams, period, rate, thr2, sxtest.SEED) as fused:
+        cf_a = torch.zeros(nstreams * period * 2, dtype=torch.float32, device="cuda")
+        cf_b = torch.zeros_like(cf_a)
+        for i, (adv, off) in enumerate(steps):
+            if adv:
+                two_calls.advance(adv)
+                fused.advance(adv)
+            two_calls.read(cf_a.data_ptr())
+            two_calls.write(cf_a.data_ptr(), HAS_TIME, None, off)
+            fused.repeat(cf_b.data_ptr(), off)
+            assert_same(snapshot(two_calls, cf_a, nstreams), snapshot(fused, cf_b, nstreams), i)
+            if i == 7:   # separate calls in between leave the fused path where it should be
+                for bank, cf in ((two_calls, cf_a), (fused, cf_b)):
+                    bank.read(cf.data_ptr())
+                    bank.write(cf.data_ptr(), 0, None, 0)
+        assert snapshot(fused, cf_b, nstreams)["rings"][0][1].any()
+    ctx.set_option("bank_repeat_variant", 0)
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 4])
+def test_repeat_large_bank_against_oracle(ctx, oracle, variant):
+    from sxxcvr_b200 import Bank
+    S, P = 16384 + 5, 256
+    ctx.set_option("bank_repeat_variant", variant)
+    with Bank(ctx, S, P, 75000.0, 0.0, 77) as bank:
+        cf = torch.empty(S * P * 2, dtype=torch.float32, device="cuda")
+        for _ in range(3):
+            bank.repeat(cf.data_ptr(), 10_240_000)
+        got = cf.cpu().numpy().reshape(S, 2 * P)
+        for s in (0, 31, 32, 2047, S - 6, S - 1):
+            frames = sxtest.synth_frames(oracle, 2 * P, P, seed=77 + s)
+            want_cf = sxtest.oracle_rx(oracle, frames)
+            assert np.array_equal(got[s].view(np.uint32), want_cf.view(np.uint32))
+            assert np.array_equal(bank.playback(s, 2 * P + 768, P), sxtest.oracle_tx(oracle, want_cf, 0.0))
+            assert not bank.playback(s, 0, 768).any()
+        ret, fl, t = bank.last_read()
+        assert (ret == P).all() and (fl == HAS_TIME).all() and (t == 6_826_667).all()
+        _, rxp, txp = bank.positions()
+        assert (rxp == 3 * P).all() and (txp == 2 * P + 768 + P).all()
+    ctx.set_option("bank_repeat_variant", 0)
