@@ -341,13 +341,13 @@ __global__ void __launch_bounds__(256) bank_repeat_warp_kernel(BankState b, char
             my_gap = b.tx_gap_length[s];
             my_start = b.tx_gap_start[s];
         }
-#pragma unroll
+#pragma unroll(K <= 4 ? K : 1)
         for (uint32_t j = 0; j < K; j++) {
             const uint64_t first = uint64_t(__shfl_sync(0xffffffffu, my_first, j));
             const long long at = __shfl_sync(0xffffffffu, my_at, j);
             const long long gap = __shfl_sync(0xffffffffu, my_gap, j);
             const long long start = __shfl_sync(0xffffffffu, my_start, j);
-            if (j >= count)
+            if (j >= count) // count is the same in every lane
                 break;
             const uint64_t s = base + j;
             char *slot = b.capture_stage + s * b.period * 8;

@@ -27,7 +27,7 @@ from sxxcvr_b200 import Bank, Context  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default="gpurun_out/sweep_bank_repeat.json")
-    ap.add_argument("--streams", type=int, nargs="*", default=[64, 4096, 16384, 65536])
+    ap.add_argument("--streams", type=int, nargs="*", default=[64, 1024, 4096, 8192, 16384, 65536])
     ap.add_argument("--iters", type=int, default=200)
     args = ap.parse_args()
 
@@ -63,8 +63,8 @@ def main():
     for S in args.streams:
         cf = torch.empty(S * P * 2, dtype=torch.float32, device="cuda")
         schedules = [("read+write", None, 0)]
-        for variant in (0, 1, 2, 4):
-            for ctas in (0, 2, 4):
+        for variant in (0, 1, 2, 4, 8, 16, 32, 100):
+            for ctas in (0, 4):
                 schedules.append(("repeat", variant, ctas))
         for name, variant, ctas in schedules:
             ctx.set_option("ctas_per_sm", ctas)
@@ -89,12 +89,14 @@ def main():
                    "us_per_iteration": ms * 1e3, "us_lone": lone * 1e3,
                    "graph_us_per_iteration": gms * 1e3, "graph_us_lone": glone * 1e3,
                    "msps_rx_plus_tx": 2 * S * P / ms / 1e3, "graph_msps_rx_plus_tx": 2 * S * P / gms / 1e3,
-                   "gbs_of_40B_per_frame": 40 * S * P / ms / 1e6, "constant_latency_holds": ok}
+                   "gbs_of_40B_per_frame": 40 * S * P / ms / 1e6,
+                   "hbm_gbs_written_24B_per_frame": (24 * S * P / ms / 1e6) if name == "repeat" else None, "constant_latency_holds": ok}
             out["points"].append(rec)
             print(f"S={S:6d} {name:10s} variant={variant} ctas/SM={ctas}: {ms*1e3:8.1f} us "
                   f"({rec['msps_rx_plus_tx']:9.0f} Msps)  graph {gms*1e3:8.1f} us  latency ok={ok}", flush=True)
         del cf
     ctx.set_option("ctas_per_sm", 0)
+    ctx.set_option("bank_repeat_variant", 0)
     ctx.close()
     Path(args.out).parent.mkdir(parents=True, exist_ok=True)
     Path(args.out).write_text(json.dumps(out, indent=1))
