@@ -263,7 +263,7 @@ int sxgpu_stream_sync(sxgpu_ctx *ctx, sxgpu_stream stream); /* NULL = context st
  *                               launch + stream sync each (period-sized blocks, SoapySX.cpp:451);
  *                               the kernel leaves by itself after 2 ms without work
  *   "bank_repeat_variant"       schedule of sxgpu_bank_repeat: 0 = auto (by stream count),
- *                               K in {1, 2, 4, 8, 16, 32} = a warp takes K streams per round,
+ *                               K in {1, 2, 4, 8} = a warp takes K streams per round,
  *                               100 = a CTA takes 32 streams per round
  *   "numa_local_alloc"          1 (default): pinned host memory this library allocates
  *                               (sxgpu_malloc_host, the bounce buffers of the *_host pipeline) is

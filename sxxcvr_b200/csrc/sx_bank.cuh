@@ -60,11 +60,19 @@ struct BankState {
 constexpr int SX_HAS_TIME = 1 << 2; // SOAPY_SDR_HAS_TIME
 
 // readStream(stream, buf, period, timeoutUs > 0) for stream s: SoapySX.cpp:897-959.
-// Run by one lane of the warp that owns the stream.
-__device__ __forceinline__ void bank_plan_read(const BankState &b, uint64_t s, char *cf32_out)
+// Run by one lane of the warp that owns the stream.  The counters come in as values and the
+// decisions go out as values (and to the state arrays), so that a caller which goes on to plan
+// the write of the same stream does not wait for its own stores to come back from memory.
+struct BankReadPlan {
+    long long first;   // counter value of the first frame of the block
+    long long time_ns; // its timestamp
+    long long clock;   // the stream's clock after the read
+};
+
+__device__ __forceinline__ BankReadPlan bank_plan_read_core(const BankState &b, uint64_t s, char *cf32_out,
+                                                            long long clock, long long pos)
 {
     const sxplan::Geometry geo = {b.period, b.ring};
-    long long clock = b.clock[s], pos = b.rx_position[s];
     long pending = long(clock - pos);
 
     unsigned long skip = sxplan::overrun_skip(pending, geo); // :910-915
@@ -77,7 +85,11 @@ __device__ __forceinline__ void bank_plan_read(const BankState &b, uint64_t s, c
     if (pending < length) // a blocking read waits for the I2S clock
         clock += length - pending;
 
-    b.rx_time_ns[s] = sx_ticks_to_time_ns(pos, b.sample_rate); // timestamp of the first frame (:950)
+    BankReadPlan plan;
+    plan.first = pos;
+    plan.time_ns = sx_ticks_to_time_ns(pos, b.sample_rate); // timestamp of the first frame (:950)
+    plan.clock = clock;
+    b.rx_time_ns[s] = plan.time_ns;
     b.rx_flags[s] = SX_HAS_TIME;
     b.rx_first_frame[s] = pos;
     b.rx_ret[s] = int(length);
@@ -91,6 +103,12 @@ __device__ __forceinline__ void bank_plan_read(const BankState &b, uint64_t s, c
     d.thr2 = 0.0f;
     d.reserved = 0;
     b.rx_blocks[s] = d;
+    return plan;
+}
+
+__device__ __forceinline__ BankReadPlan bank_plan_read(const BankState &b, uint64_t s, char *cf32_out)
+{
+    return bank_plan_read_core(b, s, cf32_out, b.clock[s], b.rx_position[s]);
 }
 
 // One warp per stream: lane 0 makes readStream's decisions, then the warp plays the I2S DMA --
@@ -114,9 +132,7 @@ __global__ void bank_capture_kernel(BankState b, char *cf32_out, bool fused)
     for (uint64_t s = uint64_t(blockIdx.x) * warps_per_cta + (threadIdx.x >> 5); s < b.nstreams; s += nwarps) {
         long long first_ll = 0;
         if (lane == 0) {
-            if (fused)
-                bank_plan_read(b, s, cf32_out);
-            first_ll = b.rx_first_frame[s];
+            first_ll = fused ? bank_plan_read(b, s, cf32_out).first : b.rx_first_frame[s];
         }
         const uint64_t first = uint64_t(__shfl_sync(0xffffffffu, first_ll, 0));
         char *out = b.capture_stage + s * b.period * 8;
@@ -131,35 +147,35 @@ __global__ void bank_capture_kernel(BankState b, char *cf32_out, bool fused)
 }
 
 // writeStream(stream, buf, period, flags, timeNs, timeoutUs > 0) for stream s: :989-1097.
-// time_ns == nullptr means "the timestamp of this stream's last read plus rx_time_offset_ns",
-// the repeater pattern (example/linear_repeater.py:64-69).  Run by one lane of the stream's warp.
-__device__ __forceinline__ void bank_plan_write(const BankState &b, uint64_t s, int flags,
-                                                const long long *time_ns, long long rx_time_offset_ns)
+// Run by one lane of the stream's warp; counters in and decisions out as values, as above.
+struct BankWritePlan {
+    long long at;    // counter value the block is written at, -1: discarded as late
+    long long gap;   // length of the forwarded-over region to be silenced
+    long long start; // where that region starts
+};
+
+__device__ __forceinline__ BankWritePlan bank_plan_write_core(const BankState &b, uint64_t s, bool timed,
+                                                              long long time_ns, long long clock, long long pos)
 {
-    long long clock = b.clock[s], pos = b.tx_position[s];
     const long long ring = (long long)b.ring, period = (long long)b.period;
     const long queued = long(pos - clock); // ALSA delay: written but not yet played
 
-    const bool timed = (flags & SX_HAS_TIME) != 0;
-    long long ticks = 0;
-    if (timed) {
-        long long t = time_ns ? time_ns[s] : b.rx_time_ns[s] + rx_time_offset_ns;
-        ticks = sx_time_ns_to_ticks(t, b.sample_rate);
-    }
+    const long long ticks = timed ? sx_time_ns_to_ticks(time_ns, b.sample_rate) : 0;
     sxplan::TxPlacement where = sxplan::place_tx_block(pos, queued, timed, ticks, b.period);
 
-    b.tx_gap_start[s] = pos;
-    b.tx_gap_length[s] = 0;
+    BankWritePlan plan = {-1, 0, pos};
     if (where.discard) { // :1017-1023: report written, write nothing
+        b.tx_gap_start[s] = pos;
+        b.tx_gap_length[s] = 0;
         b.tx_ret[s] = int(period);
         b.tx_write_position[s] = -1;
-        return;
+        return plan;
     }
 
     // :1043-1073: forward the write pointer to the block's position, waiting for ring space.
     long long gap = where.write_position - pos;
     if (gap > 0)
-        b.tx_gap_length[s] = gap;
+        plan.gap = gap;
     while (gap > 0) {
         long long fits = clock + ring - pos;
         if (fits < 0)
@@ -182,10 +198,38 @@ __device__ __forceinline__ void bank_plan_write(const BankState &b, uint64_t s, 
     if (room < period)
         clock += period - room;
 
+    plan.at = pos;
+    b.tx_gap_start[s] = plan.start;
+    b.tx_gap_length[s] = plan.gap;
     b.tx_write_position[s] = pos;
     b.tx_ret[s] = int(period);
     b.tx_position[s] = pos + period;
     b.clock[s] = clock;
+    return plan;
+}
+
+// time_ns == nullptr means "the timestamp of this stream's last read plus rx_time_offset_ns",
+// the repeater pattern (example/linear_repeater.py:64-69).
+__device__ __forceinline__ BankWritePlan bank_plan_write(const BankState &b, uint64_t s, int flags,
+                                                         const long long *time_ns, long long rx_time_offset_ns)
+{
+    const bool timed = (flags & SX_HAS_TIME) != 0;
+    long long t = 0;
+    if (timed)
+        t = time_ns ? time_ns[s] : b.rx_time_ns[s] + rx_time_offset_ns;
+    return bank_plan_write_core(b, s, timed, t, b.clock[s], b.tx_position[s]);
+}
+
+// readStream then writeStream(HAS_TIME, that read's timestamp + rx_time_offset_ns) of one stream:
+// the three counters are loaded side by side, and the write is planned from the read's results
+// without a trip through memory.  Same stores, in the same order, as the two separate plans.
+__device__ __forceinline__ void bank_plan_repeat(const BankState &b, uint64_t s, char *cf32, long long rx_time_offset_ns,
+                                                 long long &first, BankWritePlan &w)
+{
+    const long long clock = b.clock[s], rx_pos = b.rx_position[s], tx_pos = b.tx_position[s];
+    const BankReadPlan r = bank_plan_read_core(b, s, cf32, clock, rx_pos);
+    w = bank_plan_write_core(b, s, true, r.time_ns + rx_time_offset_ns, r.clock, tx_pos);
+    first = r.first;
 }
 
 // The data side of writeStream for stream s, done by one warp: silence for the forwarded-over
@@ -248,11 +292,16 @@ __global__ void bank_tx_kernel(BankState b, const char *cf32_in, int flags, cons
     for (uint64_t s = uint64_t(blockIdx.x) * warps_per_cta + (threadIdx.x >> 5); s < b.nstreams; s += nwarps) {
         long long at = 0, gap = 0, start = 0;
         if (lane == 0) {
-            if (fused)
-                bank_plan_write(b, s, flags, time_ns, rx_time_offset_ns);
-            at = b.tx_write_position[s];
-            gap = b.tx_gap_length[s];
-            start = b.tx_gap_start[s];
+            if (fused) { // decisions straight from the plan, not back through memory
+                const BankWritePlan w = bank_plan_write(b, s, flags, time_ns, rx_time_offset_ns);
+                at = w.at;
+                gap = w.gap;
+                start = w.start;
+            } else {
+                at = b.tx_write_position[s];
+                gap = b.tx_gap_length[s];
+                start = b.tx_gap_start[s];
+            }
         }
         at = __shfl_sync(0xffffffffu, at, 0);
         gap = __shfl_sync(0xffffffffu, gap, 0);
@@ -283,12 +332,13 @@ __global__ void __launch_bounds__(256) bank_repeat_kernel(BankState b, char *cf3
         const uint32_t count = uint32_t(b.nstreams - base < kRepeatGroup ? b.nstreams - base : kRepeatGroup);
         if (threadIdx.x < count) {
             const uint64_t s = base + threadIdx.x;
-            bank_plan_read(b, s, cf32);
-            bank_plan_write(b, s, SX_HAS_TIME, nullptr, rx_time_offset_ns);
-            s_first[threadIdx.x] = b.rx_first_frame[s];
-            s_at[threadIdx.x] = b.tx_write_position[s];
-            s_gap[threadIdx.x] = b.tx_gap_length[s];
-            s_start[threadIdx.x] = b.tx_gap_start[s];
+            long long first;
+            BankWritePlan w;
+            bank_plan_repeat(b, s, cf32, rx_time_offset_ns, first, w);
+            s_first[threadIdx.x] = first;
+            s_at[threadIdx.x] = w.at;
+            s_gap[threadIdx.x] = w.gap;
+            s_start[threadIdx.x] = w.start;
         }
         __syncthreads();
         for (uint32_t j = warp; j < count; j += warps_per_cta) {
@@ -334,14 +384,13 @@ __global__ void __launch_bounds__(256) bank_repeat_warp_kernel(BankState b, char
         long long my_first = 0, my_at = -1, my_gap = 0, my_start = 0;
         if (lane < count) {
             const uint64_t s = base + lane;
-            bank_plan_read(b, s, cf32);
-            bank_plan_write(b, s, SX_HAS_TIME, nullptr, rx_time_offset_ns);
-            my_first = b.rx_first_frame[s];
-            my_at = b.tx_write_position[s];
-            my_gap = b.tx_gap_length[s];
-            my_start = b.tx_gap_start[s];
+            BankWritePlan w;
+            bank_plan_repeat(b, s, cf32, rx_time_offset_ns, my_first, w);
+            my_at = w.at;
+            my_gap = w.gap;
+            my_start = w.start;
         }
-#pragma unroll(K <= 4 ? K : 1)
+#pragma unroll
         for (uint32_t j = 0; j < K; j++) {
             const uint64_t first = uint64_t(__shfl_sync(0xffffffffu, my_first, j));
             const long long at = __shfl_sync(0xffffffffu, my_at, j);

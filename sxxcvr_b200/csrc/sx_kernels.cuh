@@ -600,7 +600,23 @@ __device__ __forceinline__ void convert_span(const BlockDesc &b, uint64_t lo, ui
     uint64_t done = lo;
     if (vec_ok) {
         uint64_t nvec = (hi - lo) / FR;
-        for (uint64_t v = tid; v < nvec; v += nthreads) {
+        // Four loads in flight per thread before the first store: a 256-frame period is four
+        // vectors per lane of a warp, i.e. one round trip to L2/HBM instead of four in a row.
+        constexpr int U = 4;
+        uint64_t v = tid;
+        for (; v + uint64_t(U - 1) * nthreads < nvec; v += uint64_t(U) * nthreads) {
+            Pack<Op::kSrcWords * FR> in[U];
+#pragma unroll
+            for (int u = 0; u < U; u++)
+                in[u] = ld_stream<SFB * FR>(b.src + (lo + (v + uint64_t(u) * nthreads) * FR) * SFB);
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                Pack<Op::kDstWords * FR> out;
+                Op::template apply<FR>(in[u], out, b.thr2);
+                st_stream<DFB * FR>(b.dst + (lo + (v + uint64_t(u) * nthreads) * FR) * DFB, out);
+            }
+        }
+        for (; v < nvec; v += nthreads) {
             Pack<Op::kSrcWords * FR> in = ld_stream<SFB * FR>(b.src + (lo + v * FR) * SFB);
             Pack<Op::kDstWords * FR> out;
             Op::template apply<FR>(in, out, b.thr2);

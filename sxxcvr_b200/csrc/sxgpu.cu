@@ -63,7 +63,7 @@ struct sxgpu_ctx {
     int64_t zero_copy_max_frames = 1 << 18; // measured crossover, profiles/r01_sweep_host_path.json
     int64_t resident_max_frames = 0;        // > 0: blocks up to this size go to the resident converter
     int64_t zero_copy_variant = 1;          // schedule of the zero-copy kernel (1 vec128, 2 vec256, 3 bulk)
-    int64_t bank_repeat_variant = 0;        // 0 auto; 1..32 = K streams per warp round; 100 = 32 per CTA round
+    int64_t bank_repeat_variant = 0;        // 0 auto; 1, 2, 4, 8 = K streams per warp round; 100 = 32 per CTA round
     int64_t numa_local_alloc = 1;           // place pinned host memory on the GPU's NUMA node
     int64_t numa_node = -1;                 // read-only: the GPU's NUMA node, -1 unknown / no NUMA
 
@@ -1302,27 +1302,24 @@ int sxgpu_bank_repeat(sxgpu_bank *bank, void *d_cf32, long long rx_time_offset_n
         const uint64_t chunks = (uint64_t(b.nstreams) + k - 1) / k;
         kernel<<<persistent_grid(ctx, kernel, 256, 0, (chunks + 7) / 8), 256, 0, st>>>(b, cf, rx_time_offset_ns);
     };
+    auto group_variant = [&](auto kernel) { // a CTA takes 32 streams per round, its first warp decides for all of them
+        const uint64_t groups = (uint64_t(b.nstreams) + kRepeatGroup - 1) / kRepeatGroup;
+        kernel<<<persistent_grid(ctx, kernel, 256, 0, groups), 256, 0, st>>>(b, cf, rx_time_offset_ns);
+    };
     // Streams per warp round.  Lanes 0..K-1 take K streams' decisions side by side, so a larger K
     // spends fewer issue slots on the timestamp arithmetic; a smaller K spreads few streams over
-    // more warps.  Measured crossovers (profiles/r01_sweep_bank_repeat.json): K = 1 wins at 64
-    // streams (6.2 us against 9.5 and 14.4), K = 1 and 2 tie at 4096, K = 4 wins from 16384 up.
+    // more warps (a warp needs 1-2 us per stream: dependent round trips through L2).  Measured
+    // crossovers: profiles/r01_sweep_bank_repeat.json.
     int64_t k = ctx->bank_repeat_variant;
     if (k == 0)
-        k = b.nstreams <= 2048 ? 1 : b.nstreams <= 8192 ? 2 : 4;
+        k = b.nstreams <= 2048 ? 1 : b.nstreams <= 8192 ? 2 : b.nstreams <= 32768 ? 4 : 100;
     switch (k) {
     case 1: warp_variant(bank_repeat_warp_kernel<1>, 1); break;
     case 2: warp_variant(bank_repeat_warp_kernel<2>, 2); break;
     case 4: warp_variant(bank_repeat_warp_kernel<4>, 4); break;
     case 8: warp_variant(bank_repeat_warp_kernel<8>, 8); break;
-    case 16: warp_variant(bank_repeat_warp_kernel<16>, 16); break;
-    case 32: warp_variant(bank_repeat_warp_kernel<32>, 32); break;
-    case 100: { // a CTA takes 32 streams per round, its first warp decides for all of them
-        const uint64_t groups = (uint64_t(b.nstreams) + kRepeatGroup - 1) / kRepeatGroup;
-        bank_repeat_kernel<<<persistent_grid(ctx, bank_repeat_kernel, 256, 0, groups), 256, 0, st>>>(
-            b, cf, rx_time_offset_ns);
-        break;
-    }
-    default: return ctx->invalid("bank_repeat_variant must be 0 (auto), 1, 2, 4, 8, 16, 32 or 100");
+    case 100: group_variant(bank_repeat_kernel); break;
+    default: return ctx->invalid("bank_repeat_variant must be 0 (auto), 1, 2, 4, 8 or 100");
     }
     SX_CUDA(ctx, cudaGetLastError());
     ctx->launches += 1;

@@ -3,7 +3,7 @@
 
 For S streams x 256 frames, times one repeater iteration (read 256, timed write of the same
 block at +768 frames) for the two-call form and for every schedule of the one-launch form
-(option bank_repeat_variant x option ctas_per_sm), per launch and replayed from a CUDA graph,
+(option bank_repeat_variant), per launch and replayed from a CUDA graph,
 and checks after every point that the constant-latency property still holds.
 
     python tools/sweep_bank_repeat.py --out gpurun_out/sweep_bank_repeat.json
@@ -63,11 +63,9 @@ def main():
     for S in args.streams:
         cf = torch.empty(S * P * 2, dtype=torch.float32, device="cuda")
         schedules = [("read+write", None, 0)]
-        for variant in (0, 1, 2, 4, 8, 16, 32, 100):
-            for ctas in (0, 4):
-                schedules.append(("repeat", variant, ctas))
+        for variant in (0, 1, 2, 4, 8, 100):
+            schedules.append(("repeat", variant, 0))
         for name, variant, ctas in schedules:
-            ctx.set_option("ctas_per_sm", ctas)
             if variant is not None:
                 ctx.set_option("bank_repeat_variant", variant)
             with Bank(ctx, S, P, 75000.0, 0.0, 1) as bank:
@@ -92,10 +90,9 @@ def main():
                    "gbs_of_40B_per_frame": 40 * S * P / ms / 1e6,
                    "hbm_gbs_written_24B_per_frame": (24 * S * P / ms / 1e6) if name == "repeat" else None, "constant_latency_holds": ok}
             out["points"].append(rec)
-            print(f"S={S:6d} {name:10s} variant={variant} ctas/SM={ctas}: {ms*1e3:8.1f} us "
+            print(f"S={S:6d} {name:10s} variant={variant}: {ms*1e3:8.1f} us "
                   f"({rec['msps_rx_plus_tx']:9.0f} Msps)  graph {gms*1e3:8.1f} us  latency ok={ok}", flush=True)
         del cf
-    ctx.set_option("ctas_per_sm", 0)
     ctx.set_option("bank_repeat_variant", 0)
     ctx.close()
     Path(args.out).parent.mkdir(parents=True, exist_ok=True)
