@@ -18,6 +18,12 @@
 //     batch_warp_kernel<RxCf32>  the conversion, from the capture slot to the caller's CF32
 //     bank_tx_kernel          what writeStream decides (bank_plan_write) + silence for
 //                             forwarded-over gaps + the conversion into the playback ring
+// and, for the repeater pattern (read, then a timed write of the block just read), all of the
+// above in one launch:
+//     bank_repeat_warp_kernel<K> / bank_repeat_kernel   K lanes decide for K streams from
+//                             registers, then the warp takes each stream through the three
+//                             stages back to back, each stage reading from L2 what the previous
+//                             one has just written
 // The virtual clock follows the same rule as the host-side ALSA stand-in: it moves when a
 // blocking transfer must wait (by exactly the deficit) or when the owner advances it.
 #pragma once
@@ -310,6 +316,33 @@ __global__ void bank_tx_kernel(BankState b, const char *cf32_in, int flags, cons
     }
 }
 
+// One stream's share of the repeater iteration, done by one warp once the decisions are taken:
+// the stand-in DMA writes the planned frames into the capture slot, the RX conversion reads
+// them back (as it would after a real DMA) into the caller's CF32 block, and the TX conversion
+// reads that block into the playback ring.
+__device__ __forceinline__ void bank_repeat_stream(const BankState &b, uint64_t s, char *cf32, uint64_t first,
+                                                   long long at, long long gap, long long start, uint32_t lane)
+{
+    char *slot = b.capture_stage + s * b.period * 8;
+    for (uint32_t i = lane; i < b.period; i += 32) {
+        uint64_t z = sx_synth_frame(b.seed + s, first + i);
+        Pack<2> p;
+        p.w[0] = uint32_t(z);
+        p.w[1] = uint32_t(z >> 32);
+        st_stream<8>(slot + size_t(i) * 8, p);
+    }
+    __syncwarp(); // the slot is complete before any lane reads it back
+    BlockDesc d;
+    d.src = slot;
+    d.dst = cf32 + s * b.period * 8;
+    d.length = b.period;
+    d.thr2 = 0.0f;
+    d.reserved = 0;
+    convert_span<RxCf32>(d, 0, d.length, lane, 32);
+    __syncwarp(); // the CF32 block is complete before the TX stage reads it
+    bank_play_block(b, s, cf32, at, gap, start, lane);
+}
+
 // The repeater iteration in one launch: readStream(period) on every stream, then
 // writeStream(period, HAS_TIME, that read's timestamp + rx_time_offset_ns) of the block just
 // read (example/linear_repeater.py:50-71 without the filters).  State and results are exactly
@@ -343,25 +376,7 @@ __global__ void __launch_bounds__(256) bank_repeat_kernel(BankState b, char *cf3
         __syncthreads();
         for (uint32_t j = warp; j < count; j += warps_per_cta) {
             const uint64_t s = base + j;
-            const uint64_t first = uint64_t(s_first[j]);
-            char *slot = b.capture_stage + s * b.period * 8;
-            for (uint32_t i = lane; i < b.period; i += 32) {
-                uint64_t z = sx_synth_frame(b.seed + s, first + i);
-                Pack<2> p;
-                p.w[0] = uint32_t(z);
-                p.w[1] = uint32_t(z >> 32);
-                st_stream<8>(slot + size_t(i) * 8, p);
-            }
-            __syncwarp(); // the slot is complete before any lane reads it back
-            BlockDesc d;
-            d.src = slot;
-            d.dst = cf32 + s * b.period * 8;
-            d.length = b.period;
-            d.thr2 = 0.0f;
-            d.reserved = 0;
-            convert_span<RxCf32>(d, 0, d.length, lane, 32);
-            __syncwarp(); // the CF32 block is complete before the TX stage reads it
-            bank_play_block(b, s, cf32, s_at[j], s_gap[j], s_start[j], lane);
+            bank_repeat_stream(b, s, cf32, uint64_t(s_first[j]), s_at[j], s_gap[j], s_start[j], lane);
         }
         __syncthreads(); // the next group's plans overwrite the shared arrays
     }
@@ -398,25 +413,7 @@ __global__ void __launch_bounds__(256) bank_repeat_warp_kernel(BankState b, char
             const long long start = __shfl_sync(0xffffffffu, my_start, j);
             if (j >= count) // count is the same in every lane
                 break;
-            const uint64_t s = base + j;
-            char *slot = b.capture_stage + s * b.period * 8;
-            for (uint32_t i = lane; i < b.period; i += 32) {
-                uint64_t z = sx_synth_frame(b.seed + s, first + i);
-                Pack<2> p;
-                p.w[0] = uint32_t(z);
-                p.w[1] = uint32_t(z >> 32);
-                st_stream<8>(slot + size_t(i) * 8, p);
-            }
-            __syncwarp();
-            BlockDesc d;
-            d.src = slot;
-            d.dst = cf32 + s * b.period * 8;
-            d.length = b.period;
-            d.thr2 = 0.0f;
-            d.reserved = 0;
-            convert_span<RxCf32>(d, 0, d.length, lane, 32);
-            __syncwarp();
-            bank_play_block(b, s, cf32, at, gap, start, lane);
+            bank_repeat_stream(b, base + j, cf32, first, at, gap, start, lane);
         }
     }
 }
