@@ -265,6 +265,10 @@ int sxgpu_stream_sync(sxgpu_ctx *ctx, sxgpu_stream stream); /* NULL = context st
  *   "bank_repeat_variant"       schedule of sxgpu_bank_repeat: 0 = auto (by stream count),
  *                               K in {1, 2, 4, 8} = a warp takes K streams per round,
  *                               100 = a CTA takes 32 streams per round
+ *   "bounce_threads"            threads that share the copy of a pageable caller buffer to or
+ *                               from pinned staging in the *_host calls (copies of 2 MiB and more):
+ *                               0 = auto (a quarter of the hardware threads, at most 4),
+ *                               1 = the calling thread alone
  *   "numa_local_alloc"          1 (default): pinned host memory this library allocates
  *                               (sxgpu_malloc_host, the bounce buffers of the *_host pipeline) is
  *                               faulted in while the calling thread is confined to the CPUs next to

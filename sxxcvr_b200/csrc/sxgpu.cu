@@ -9,6 +9,7 @@
 #include "sx_kernels.cuh"
 #include "sx_bank.cuh"
 #include "sx_resident.cuh"
+#include "host/par_copy.hpp"
 
 #include <algorithm>
 #include <atomic>
@@ -16,6 +17,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <tuple>
@@ -64,6 +66,7 @@ struct sxgpu_ctx {
     int64_t resident_max_frames = 0;        // > 0: blocks up to this size go to the resident converter
     int64_t zero_copy_variant = 1;          // schedule of the zero-copy kernel (1 vec128, 2 vec256, 3 bulk)
     int64_t bank_repeat_variant = 0;        // 0 auto; 1, 2, 4, 8 = K streams per warp round; 100 = 32 per CTA round
+    int64_t bounce_threads = 0;             // threads copying a pageable caller's buffer: 0 auto, 1 = the caller alone
     int64_t numa_local_alloc = 1;           // place pinned host memory on the GPU's NUMA node
     int64_t numa_node = -1;                 // read-only: the GPU's NUMA node, -1 unknown / no NUMA
 
@@ -80,6 +83,7 @@ struct sxgpu_ctx {
 
     // host pipeline
     std::mutex host_mutex;
+    std::unique_ptr<sxhost::ParallelCopier> copier; // guarded by host_mutex
     cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
     HostRing ring;
 
@@ -646,6 +650,19 @@ template <> constexpr int resident_op<TxCf32>()
     return 1;
 }
 
+// Bounce copy between a pageable caller buffer and pinned staging (host_mutex held).  A quarter
+// of the host's hardware threads, at most four, share a large copy: one thread moves about
+// 10 GB/s, the link behind the staging buffer 47-55.
+void bounce_copy(sxgpu_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    unsigned threads = unsigned(std::min<int64_t>(ctx->bounce_threads, 64));
+    if (threads == 0)
+        threads = std::max(1u, std::min(4u, std::thread::hardware_concurrency() / 4));
+    if (!ctx->copier || ctx->copier->helpers() != threads - 1)
+        ctx->copier.reset(new sxhost::ParallelCopier(threads - 1));
+    ctx->copier->copy(dst, src, bytes);
+}
+
 template <class Op>
 int convert_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset, void *h_dest,
                  size_t dest_offset, size_t length, float thr2, int64_t variant)
@@ -683,7 +700,7 @@ int convert_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset, void *h_d
         const void *kernel_in = si.device_alias;
         void *kernel_out = di.device_alias;
         if (bounce_in) {
-            std::memcpy(ctx->ring.h_in[0], src, length * SFB);
+            bounce_copy(ctx, ctx->ring.h_in[0], src, length * SFB);
             kernel_in = ctx->ring.h_in[0]; // pinned memory is device-addressable at the same address (UVA)
         }
         if (bounce_out)
@@ -700,7 +717,7 @@ int convert_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset, void *h_d
             SX_CUDA(ctx, cudaStreamSynchronize(ctx->s_comp));
         }
         if (bounce_out)
-            std::memcpy(dst, ctx->ring.h_out[0], length * DFB);
+            bounce_copy(ctx, dst, ctx->ring.h_out[0], length * DFB);
         ctx->h2d_bytes += in_bytes;
         ctx->d2h_bytes += out_bytes;
         return SXGPU_OK;
@@ -719,7 +736,7 @@ int convert_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset, void *h_d
         int slot = int(i % kRingSlots);
         SX_CUDA(ctx, cudaEventSynchronize(r.done[slot]));
         if (!di.pinned && !di.on_device)
-            std::memcpy(dst + i * chunk * DFB, r.h_out[slot], chunk_len(i) * DFB);
+            bounce_copy(ctx, dst + i * chunk * DFB, r.h_out[slot], chunk_len(i) * DFB);
         return SXGPU_OK;
     };
 
@@ -735,7 +752,7 @@ int convert_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset, void *h_d
         } else {
             const void *from = src + i * chunk * SFB;
             if (!si.pinned) {
-                std::memcpy(r.h_in[slot], from, n * SFB);
+                bounce_copy(ctx, r.h_in[slot], from, n * SFB);
                 from = r.h_in[slot];
             }
             SX_CUDA(ctx, cudaMemcpyAsync(r.d_in[slot], from, n * SFB, cudaMemcpyHostToDevice, ctx->s_h2d));
@@ -847,6 +864,7 @@ int64_t *option_slot(sxgpu_ctx *ctx, const char *key)
         {"resident_max_frames", &ctx->resident_max_frames},
         {"zero_copy_variant", &ctx->zero_copy_variant},
         {"bank_repeat_variant", &ctx->bank_repeat_variant},
+        {"bounce_threads", &ctx->bounce_threads},
         {"numa_local_alloc", &ctx->numa_local_alloc},
         {"numa_node", &ctx->numa_node},
     };

@@ -358,6 +358,28 @@ def test_host_buffer_entry_points(ctx, oracle, pinned, mode, nframes):
         ctx.set_option("host_chunk_frames", 0)
 
 
+@pytest.mark.parametrize("threads", [1, 2, 7])
+def test_pageable_callers_with_shared_bounce_copies(ctx, oracle, threads):
+    """Pageable caller buffers (numpy arrays: what the reference's Python callers pass) are moved
+    through pinned staging by `bounce_threads` threads; the result does not depend on how many."""
+    nframes = (1 << 22) + 17
+    ctx.set_option("bounce_threads", threads)
+    ctx.set_option("host_chunk_frames", (1 << 20) + 5)      # chunks that do not split evenly
+    try:
+        words = sxtest.rx_uniform(nframes, seed=21)
+        f = sxtest.tx_uniform(nframes, seed=22)
+        out_f = np.full(2 * nframes + 8, np.float32(7.0))   # guard elements behind the block
+        out_i = np.full(2 * nframes + 8, 7, np.int32)
+        ctx.convert_rx_buffer_host(words.ctypes.data, 0, out_f.ctypes.data, 0, nframes)
+        assert np.array_equal(bits(out_f[:2 * nframes]), bits(sxtest.oracle_rx(oracle, words)))
+        ctx.convert_tx_buffer_host(f.ctypes.data, 0, out_i.ctypes.data, 0, nframes, sxtest.THR2_DEFAULT)
+        assert np.array_equal(out_i[:2 * nframes], sxtest.oracle_tx(oracle, f, sxtest.THR2_DEFAULT))
+        assert (out_f[2 * nframes:] == 7.0).all() and (out_i[2 * nframes:] == 7).all()
+    finally:
+        ctx.set_option("bounce_threads", 0)
+        ctx.set_option("host_chunk_frames", 0)
+
+
 @pytest.mark.parametrize("nframes", [256, (1 << 19) + 3, (1 << 22) + 1])
 def test_host_entry_points_accept_device_memory_on_either_side(ctx, oracle, nframes):
     """A torch/cupy buffer handed to readStream/writeStream: that side's PCIe copy is skipped."""

@@ -78,3 +78,26 @@ def test_device_construction_fails_loudly_without_a_gpu():
     with pytest.raises(sxstream.Threw) as e:
         h.device()
     assert "no CPU fallback" in str(e.value)
+
+
+@pytest.mark.parametrize("helpers", [0, 1, 3, 7])
+def test_parallel_bounce_copier(tmp_path, helpers):
+    """csrc/host/par_copy.hpp (the bounce copies of pageable callers in the *_host entry points):
+    every size class, odd sizes and offsets, guard bytes around the destination, many copies
+    through one pool -- under ThreadSanitizer when the toolchain links it."""
+    import os
+    import subprocess
+    from sxxcvr_b200 import _build
+    src = _build.ROOT / "tests" / "native" / "par_copy_test.cpp"
+    exe = tmp_path / "par_copy_test"
+    base = [os.environ.get("CXX", "g++"), "-std=c++17", "-g", "-Wall", "-Wextra", "-pthread",
+            "-I", str(_build.CSRC), str(src), "-o", str(exe)]
+    tsan = subprocess.run(base + ["-O1", "-fsanitize=thread"], capture_output=True, text=True)
+    rounds = "1"
+    if tsan.returncode != 0:        # no libtsan here: plain build, more rounds
+        subprocess.run(base + ["-O2"], check=True, capture_output=True, text=True)
+        rounds = "3"
+    run = subprocess.run([str(exe), str(helpers), rounds], capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0, run.stdout + run.stderr
+    assert "ThreadSanitizer" not in run.stderr
+    assert f"{helpers} helpers" in run.stdout
