@@ -267,7 +267,8 @@ int sxgpu_stream_sync(sxgpu_ctx *ctx, sxgpu_stream stream); /* NULL = context st
  *                               100 = a CTA takes 32 streams per round
  *   "bounce_threads"            threads that share the copy of a pageable caller buffer to or
  *                               from pinned staging in the *_host calls (copies of 2 MiB and more):
- *                               0 = auto (a quarter of the hardware threads, at most 4),
+ *                               0 = auto (half of the hardware threads, shared between the
+ *                               LOCAL_WORLD_SIZE ranks of a torchrun job, at most 8),
  *                               1 = the calling thread alone
  *   "numa_local_alloc"          1 (default): pinned host memory this library allocates
  *                               (sxgpu_malloc_host, the bounce buffers of the *_host pipeline) is

@@ -15,6 +15,7 @@
 #include <atomic>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -650,14 +651,19 @@ template <> constexpr int resident_op<TxCf32>()
     return 1;
 }
 
-// Bounce copy between a pageable caller buffer and pinned staging (host_mutex held).  A quarter
-// of the host's hardware threads, at most four, share a large copy: one thread moves about
-// 10 GB/s, the link behind the staging buffer 47-55.
+// Bounce copy between a pageable caller buffer and pinned staging (host_mutex held).  Half of
+// this process's share of the hardware threads, at most eight, take a large copy together: one
+// thread moves 5-7 GB/s each way through the pipeline, eight 16-23, the link behind the staging
+// buffer 46 (profiles/r01_bench_pageable.json).  Under torchrun the share is 1 / LOCAL_WORLD_SIZE.
 void bounce_copy(sxgpu_ctx *ctx, void *dst, const void *src, size_t bytes)
 {
     unsigned threads = unsigned(std::min<int64_t>(ctx->bounce_threads, 64));
-    if (threads == 0)
-        threads = std::max(1u, std::min(4u, std::thread::hardware_concurrency() / 4));
+    if (threads == 0) {
+        unsigned ranks = 1;
+        if (const char *env = std::getenv("LOCAL_WORLD_SIZE"))
+            ranks = unsigned(std::max(1, std::atoi(env)));
+        threads = std::max(1u, std::min(8u, std::thread::hardware_concurrency() / (2 * ranks)));
+    }
     if (!ctx->copier || ctx->copier->helpers() != threads - 1)
         ctx->copier.reset(new sxhost::ParallelCopier(threads - 1));
     ctx->copier->copy(dst, src, bytes);
