@@ -10,6 +10,7 @@
 
 #include <alsa/asoundlib.h>
 
+#include <chrono>
 #include <cstring>
 #include <exception>
 #include <string>
@@ -394,6 +395,85 @@ int sxh_write_setting(sxh_device *h, const char *key, const char *value)
 {
     return guarded([&] {
         h->dev->writeSetting(key, value);
+        return 0;
+    });
+}
+
+// ---- timing loops ------------------------------------------------------------------------------
+// The same loops, compiled into both libraries, so that the product and the unmodified reference
+// are timed by identical code with no interpreter between the calls.  Each returns 0 and the
+// elapsed seconds of `iters` iterations (steady clock), or the first unexpected return value.
+// per_iter_us (may be NULL) receives every iteration's duration in microseconds.
+
+// readStream(n) then writeStream(n, HAS_TIME, that block's time + latency_ns): the repeater
+// iteration of example/linear_repeater.py:50-71 with an identity process().
+int sxh_bench_pairs(sxh_device *h, void *rx, void *tx, void *buf, size_t n, int iters,
+                    long long latency_ns, double *seconds, float *per_iter_us)
+{
+    return guarded([&] {
+        using clock = std::chrono::steady_clock;
+        void *rbuffs[1] = {buf};
+        const void *wbuffs[1] = {buf};
+        auto *rs = static_cast<SoapySDR::Stream *>(rx);
+        auto *ts = static_cast<SoapySDR::Stream *>(tx);
+        const auto t0 = clock::now();
+        auto last = t0;
+        for (int i = 0; i < iters; i++) {
+            int flags = 0;
+            long long t = 0;
+            int r = h->dev->readStream(rs, rbuffs, n, flags, t, 1000000);
+            if (r != int(n))
+                return r < 0 ? r : -2000;
+            int wflags = SOAPY_SDR_HAS_TIME;
+            int w = h->dev->writeStream(ts, wbuffs, n, wflags, t + latency_ns, 1000000);
+            if (w != int(n))
+                return w < 0 ? w : -2001;
+            if (per_iter_us) {
+                const auto now = clock::now();
+                per_iter_us[i] = std::chrono::duration<float, std::micro>(now - last).count();
+                last = now;
+            }
+        }
+        *seconds = std::chrono::duration<double>(clock::now() - t0).count();
+        return 0;
+    });
+}
+
+// readStream(n) only.
+int sxh_bench_reads(sxh_device *h, void *rx, void *buf, size_t n, int iters, double *seconds)
+{
+    return guarded([&] {
+        using clock = std::chrono::steady_clock;
+        void *rbuffs[1] = {buf};
+        auto *rs = static_cast<SoapySDR::Stream *>(rx);
+        const auto t0 = clock::now();
+        for (int i = 0; i < iters; i++) {
+            int flags = 0;
+            long long t = 0;
+            int r = h->dev->readStream(rs, rbuffs, n, flags, t, 1000000);
+            if (r != int(n))
+                return r < 0 ? r : -2000;
+        }
+        *seconds = std::chrono::duration<double>(clock::now() - t0).count();
+        return 0;
+    });
+}
+
+// Untimed blocking writeStream(n) only (example/tx_test.py:47-53).
+int sxh_bench_writes(sxh_device *h, void *tx, const void *buf, size_t n, int iters, double *seconds)
+{
+    return guarded([&] {
+        using clock = std::chrono::steady_clock;
+        const void *wbuffs[1] = {buf};
+        auto *ts = static_cast<SoapySDR::Stream *>(tx);
+        const auto t0 = clock::now();
+        for (int i = 0; i < iters; i++) {
+            int flags = 0;
+            int w = h->dev->writeStream(ts, wbuffs, n, flags, 0, 1000000);
+            if (w != int(n))
+                return w < 0 ? w : -2001;
+        }
+        *seconds = std::chrono::duration<double>(clock::now() - t0).count();
         return 0;
     });
 }

@@ -118,3 +118,145 @@ private:
 };
 
 } // namespace sxhost
+
+#include <atomic>
+#include <functional>
+
+namespace sxhost {
+
+// One parked thread that runs one job at a time beside its owner: the *_host pipeline hands it
+// "wait for each chunk's device-to-host copy, then bounce the chunk out to the caller's pageable
+// buffer", so that those copies overlap the inbound bounce copies and the CUDA calls the owner
+// is making for later chunks.  start() returns at once; finish() returns when the job has.
+class Sidekick {
+public:
+    Sidekick() = default;
+    ~Sidekick()
+    {
+        {
+            std::lock_guard<std::mutex> lock(mutex_);
+            quit_ = true;
+        }
+        wake_.notify_all();
+        if (thread_.joinable())
+            thread_.join();
+    }
+    Sidekick(const Sidekick &) = delete;
+    Sidekick &operator=(const Sidekick &) = delete;
+
+    void start(std::function<void()> job)
+    {
+        std::lock_guard<std::mutex> lock(mutex_);
+        if (!thread_.joinable())
+            thread_ = std::thread([this] { main(); });
+        job_ = std::move(job);
+        busy_ = true;
+        wake_.notify_all();
+    }
+
+    void finish()
+    {
+        std::unique_lock<std::mutex> lock(mutex_);
+        done_.wait(lock, [this] { return !busy_; });
+    }
+
+private:
+    void main()
+    {
+        std::unique_lock<std::mutex> lock(mutex_);
+        for (;;) {
+            wake_.wait(lock, [this] { return quit_ || busy_; });
+            if (quit_)
+                return;
+            std::function<void()> job = std::move(job_);
+            lock.unlock();
+            job();
+            lock.lock();
+            busy_ = false;
+            done_.notify_all();
+        }
+    }
+
+    std::thread thread_;
+    std::mutex mutex_;
+    std::condition_variable wake_, done_;
+    std::function<void()> job_;
+    bool busy_ = false, quit_ = false;
+};
+
+// Progress counter shared by two threads of a pipeline: one publishes "chunks 0..n-1 are done",
+// the other waits for a given chunk.  Waiting spins briefly (a chunk takes tens of microseconds)
+// and then yields.
+class Progress {
+public:
+    void reset() { value_.store(0, std::memory_order_relaxed); }
+    void publish(uint64_t n) { value_.store(n, std::memory_order_release); }
+    uint64_t get() const { return value_.load(std::memory_order_acquire); }
+    // Returns false if `abort` became non-zero while waiting.
+    bool wait_for(uint64_t n, const std::atomic<int> &abort) const
+    {
+        unsigned spins = 0;
+        while (value_.load(std::memory_order_acquire) < n) {
+            if (abort.load(std::memory_order_relaxed))
+                return false;
+            if (++spins > 2000)
+                std::this_thread::yield();
+        }
+        return true;
+    }
+
+private:
+    std::atomic<uint64_t> value_{0};
+};
+
+// Chunk schedule of the copy-engine pipeline: small chunks first and last, so that the time
+// during which only one direction of the link is busy (the first chunk's inbound copy, the last
+// chunk's outbound copy) is short, and large chunks in between, where per-chunk overhead counts.
+// Sizes double from c_min up to c_max and mirror at the end; every boundary is a multiple of 64
+// frames so that 16-byte alignment carries over from the block start for every frame width.
+struct ChunkSpan {
+    size_t first, frames;
+};
+
+inline std::vector<ChunkSpan> plan_chunks(size_t length, size_t c_min, size_t c_max)
+{
+    auto round64 = [](size_t v) { return (v + 63) & ~size_t(63); };
+    if (c_max < 64)
+        c_max = 64;
+    c_max = round64(c_max);
+    c_min = (c_min == 0 || c_min > c_max) ? c_max : round64(c_min);
+    std::vector<size_t> front, back;
+    size_t rem = length, c = c_min;
+    while (c < c_max && rem >= 4 * c) {
+        front.push_back(c);
+        back.push_back(c);
+        rem -= 2 * c;
+        c *= 2;
+    }
+    if (c > c_max)
+        c = c_max;
+    std::vector<ChunkSpan> out;
+    size_t at = 0;
+    for (size_t f : front) {
+        out.push_back({at, f});
+        at += f;
+    }
+    if (rem > 0) {
+        const size_t n_mid = (rem + c - 1) / c;
+        const size_t each = round64((rem + n_mid - 1) / n_mid);
+        size_t left = rem;
+        while (left > 0) {
+            const size_t take = left < each ? left : each;
+            out.push_back({at, take});
+            at += take;
+            left -= take;
+        }
+    }
+    for (size_t i = back.size(); i-- > 0;) {
+        out.push_back({at, back[i]});
+        at += back[i];
+    }
+    return out;
+}
+
+} // namespace sxhost

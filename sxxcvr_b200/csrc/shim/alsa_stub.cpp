@@ -17,8 +17,12 @@
 
 namespace {
 
-// Linked PCMs share one of these (snd_pcm_link, reference SoapySX.cpp:786).
+// Linked PCMs share one of these (snd_pcm_link, reference SoapySX.cpp:786).  The group is also
+// the unit of locking: PCMs that share a clock are serialised against each other, PCMs of
+// different devices are not -- an RX thread and a TX thread of one device contend exactly as
+// two threads on one sound card would, and N devices on N threads do not contend at all.
 struct ClockGroup {
+    std::recursive_mutex mutex;
     std::vector<snd_pcm_t *> members;
 };
 
@@ -92,10 +96,38 @@ struct _snd_pcm {
 
 namespace {
 
-std::recursive_mutex g_mutex; // the stub is off the data path; one lock keeps it simple
+std::mutex g_registry;   // guards g_open and every PCM's `group` pointer
+std::mutex g_link_mutex; // one snd_pcm_link at a time (it needs two groups)
 std::vector<snd_pcm_t *> g_open;
 
-typedef std::lock_guard<std::recursive_mutex> Guard;
+// Holds the lock of the clock group `pcm` belongs to.  The group pointer only changes inside
+// snd_pcm_link, which holds both groups' locks while it re-points the members; so a group that
+// is still the PCM's group after its lock was taken stays so until the lock is released.
+class Guard {
+public:
+    explicit Guard(snd_pcm_t *pcm)
+    {
+        for (;;) {
+            {
+                std::lock_guard<std::mutex> r(g_registry);
+                group_ = pcm->group;
+            }
+            group_->mutex.lock();
+            {
+                std::lock_guard<std::mutex> r(g_registry);
+                if (pcm->group == group_)
+                    return;
+            }
+            group_->mutex.unlock();
+        }
+    }
+    ~Guard() { group_->mutex.unlock(); }
+    Guard(const Guard &) = delete;
+    Guard &operator=(const Guard &) = delete;
+
+private:
+    std::shared_ptr<ClockGroup> group_;
+};
 
 bool takeFault(snd_pcm_t *pcm, sx_alsa_op op, int *err)
 {
@@ -149,29 +181,43 @@ int startGroup(snd_pcm_t *pcm)
     return 0;
 }
 
-uint64_t captureFrame(const snd_pcm_t *pcm, int64_t k)
+// Frames first .. first + n - 1 of the capture stream.  A table is a periodic signal: whole
+// runs are copied, as snd_pcm_readi copies out of the DMA ring.
+void captureFrames(const snd_pcm_t *pcm, int64_t first, uint64_t *out, size_t n)
 {
-    if (!pcm->table.empty())
-        return pcm->table[size_t(uint64_t(k) % pcm->table.size())];
-    return sx_synth_frame(pcm->seed, uint64_t(k));
+    if (pcm->table.empty()) {
+        for (size_t i = 0; i < n; i++)
+            out[i] = sx_synth_frame(pcm->seed, uint64_t(first) + i);
+        return;
+    }
+    const size_t size = pcm->table.size();
+    size_t at = size_t(uint64_t(first) % size);
+    while (n > 0) {
+        const size_t run = std::min(n, size - at);
+        std::memcpy(out, &pcm->table[at], run * sizeof(uint64_t));
+        out += run;
+        n -= run;
+        at = 0;
+    }
 }
 
+// Frames [position, position + n) go into the timeline; what falls outside [0, sink_limit) is
+// only counted.  One copy for the part that is kept, as the DMA ring of a sound card would take it.
 void sinkStore(snd_pcm_t *pcm, int64_t position, const uint64_t *frames, size_t n)
 {
-    for (size_t i = 0; i < n; i++) {
-        int64_t p = position + int64_t(i);
-        if (p < 0 || size_t(p) >= pcm->sink_limit) {
-            pcm->dropped_beyond_limit++;
-            continue;
-        }
-        if (size_t(p) >= pcm->timeline.size()) {
-            size_t grown = std::min(pcm->sink_limit, std::max(size_t(p) + 1, pcm->timeline.size() * 2));
-            pcm->timeline.resize(grown, 0);
-            pcm->written.resize(grown, 0);
-        }
-        pcm->timeline[size_t(p)] = frames[i];
-        pcm->written[size_t(p)] = 1;
+    const int64_t lo = std::max<int64_t>(position, 0);
+    const int64_t hi = std::min<int64_t>(position + int64_t(n), int64_t(std::min<size_t>(pcm->sink_limit, size_t(INT64_MAX))));
+    const size_t kept = hi > lo ? size_t(hi - lo) : 0;
+    pcm->dropped_beyond_limit += n - kept;
+    if (kept == 0)
+        return;
+    if (size_t(hi) > pcm->timeline.size()) {
+        size_t grown = std::min(pcm->sink_limit, std::max(size_t(hi), pcm->timeline.size() * 2));
+        pcm->timeline.resize(grown, 0);
+        pcm->written.resize(grown, 0);
     }
+    std::memcpy(&pcm->timeline[size_t(lo)], frames + (lo - position), kept * sizeof(uint64_t));
+    std::memset(&pcm->written[size_t(lo)], 1, kept);
 }
 
 } // namespace
@@ -185,12 +231,12 @@ const char *snd_strerror(int errnum)
 
 int snd_pcm_open(snd_pcm_t **out, const char *name, snd_pcm_stream_t stream, int)
 {
-    Guard lock(g_mutex);
     snd_pcm_t *pcm = new _snd_pcm();
     pcm->name = name ? name : "";
     pcm->dir = stream;
     pcm->group = std::make_shared<ClockGroup>();
     pcm->group->members.push_back(pcm);
+    std::lock_guard<std::mutex> r(g_registry);
     g_open.push_back(pcm);
     *out = pcm;
     return 0;
@@ -198,10 +244,13 @@ int snd_pcm_open(snd_pcm_t **out, const char *name, snd_pcm_stream_t stream, int
 
 int snd_pcm_close(snd_pcm_t *pcm)
 {
-    Guard lock(g_mutex);
-    auto &members = pcm->group->members;
-    members.erase(std::remove(members.begin(), members.end(), pcm), members.end());
-    g_open.erase(std::remove(g_open.begin(), g_open.end(), pcm), g_open.end());
+    {
+        Guard lock(pcm);
+        std::lock_guard<std::mutex> r(g_registry);
+        auto &members = pcm->group->members;
+        members.erase(std::remove(members.begin(), members.end(), pcm), members.end());
+        g_open.erase(std::remove(g_open.begin(), g_open.end(), pcm), g_open.end());
+    }
     delete pcm;
     return 0;
 }
@@ -211,7 +260,7 @@ int snd_pcm_close(snd_pcm_t *pcm)
 // sx_alsa_sink_clear() to wipe it.
 int snd_pcm_prepare(snd_pcm_t *pcm)
 {
-    Guard lock(g_mutex);
+    Guard lock(pcm);
     if (pcm->state == SND_PCM_STATE_OPEN)
         return -EBADFD;
     for (snd_pcm_t *m : pcm->group->members)
@@ -230,7 +279,7 @@ int snd_pcm_prepare(snd_pcm_t *pcm)
 // appl_ptr = hw_ptr: forget queued / pending frames.
 int snd_pcm_reset(snd_pcm_t *pcm)
 {
-    Guard lock(g_mutex);
+    Guard lock(pcm);
     if (pcm->state != SND_PCM_STATE_RUNNING && pcm->state != SND_PCM_STATE_PREPARED)
         return -EBADFD;
     for (snd_pcm_t *m : pcm->group->members)
@@ -241,7 +290,7 @@ int snd_pcm_reset(snd_pcm_t *pcm)
 
 int snd_pcm_start(snd_pcm_t *pcm)
 {
-    Guard lock(g_mutex);
+    Guard lock(pcm);
     int err;
     if (takeFault(pcm, SX_ALSA_OP_START, &err))
         return err;
@@ -251,7 +300,7 @@ int snd_pcm_start(snd_pcm_t *pcm)
 // Stops this stream and everything linked to it; pending frames are dropped.
 int snd_pcm_drop(snd_pcm_t *pcm)
 {
-    Guard lock(g_mutex);
+    Guard lock(pcm);
     if (pcm->state == SND_PCM_STATE_OPEN)
         return -EBADFD;
     for (snd_pcm_t *m : pcm->group->members)
@@ -263,15 +312,18 @@ int snd_pcm_drop(snd_pcm_t *pcm)
 
 snd_pcm_state_t snd_pcm_state(snd_pcm_t *pcm)
 {
-    Guard lock(g_mutex);
+    Guard lock(pcm);
     return pcm->state;
 }
 
 int snd_pcm_link(snd_pcm_t *a, snd_pcm_t *b)
 {
-    Guard lock(g_mutex);
+    std::lock_guard<std::mutex> one_link(g_link_mutex);
+    Guard lock_a(a);
     if (a->group == b->group)
         return -EALREADY;
+    Guard lock_b(b);
+    std::lock_guard<std::mutex> r(g_registry);
     std::shared_ptr<ClockGroup> old = b->group;
     for (snd_pcm_t *m : old->members) {
         m->group = a->group;
@@ -290,7 +342,7 @@ int snd_pcm_link(snd_pcm_t *a, snd_pcm_t *b)
 // ends with a stream error and no test can hang.
 int snd_pcm_wait(snd_pcm_t *pcm, int)
 {
-    Guard lock(g_mutex);
+    Guard lock(pcm);
     if (pcm->state == SND_PCM_STATE_XRUN)
         return -EPIPE;
     int64_t need = int64_t(pcm->sw.avail_min) - pcm->avail();
@@ -309,7 +361,7 @@ int snd_pcm_wait(snd_pcm_t *pcm, int)
 
 int snd_pcm_avail_delay(snd_pcm_t *pcm, snd_pcm_sframes_t *availp, snd_pcm_sframes_t *delayp)
 {
-    Guard lock(g_mutex);
+    Guard lock(pcm);
     int err;
     if (takeFault(pcm, SX_ALSA_OP_AVAIL_DELAY, &err))
         return err;
@@ -324,7 +376,7 @@ int snd_pcm_avail_delay(snd_pcm_t *pcm, snd_pcm_sframes_t *availp, snd_pcm_sfram
 
 snd_pcm_sframes_t snd_pcm_forwardable(snd_pcm_t *pcm)
 {
-    Guard lock(g_mutex);
+    Guard lock(pcm);
     int err;
     if (takeFault(pcm, SX_ALSA_OP_FORWARDABLE, &err))
         return err;
@@ -339,7 +391,7 @@ snd_pcm_sframes_t snd_pcm_forwardable(snd_pcm_t *pcm)
 
 snd_pcm_sframes_t snd_pcm_forward(snd_pcm_t *pcm, snd_pcm_uframes_t frames)
 {
-    Guard lock(g_mutex);
+    Guard lock(pcm);
     int err;
     if (takeFault(pcm, SX_ALSA_OP_FORWARD, &err))
         return err;
@@ -353,7 +405,7 @@ snd_pcm_sframes_t snd_pcm_forward(snd_pcm_t *pcm, snd_pcm_uframes_t frames)
 
 snd_pcm_sframes_t snd_pcm_readi(snd_pcm_t *pcm, void *buffer, snd_pcm_uframes_t size)
 {
-    Guard lock(g_mutex);
+    Guard lock(pcm);
     int err;
     if (takeFault(pcm, SX_ALSA_OP_READI, &err))
         return err;
@@ -377,9 +429,7 @@ snd_pcm_sframes_t snd_pcm_readi(snd_pcm_t *pcm, void *buffer, snd_pcm_uframes_t 
         have = std::max<int64_t>(pcm->avail(), 0);
     }
     int64_t n = std::min(want, have);
-    uint64_t *out = static_cast<uint64_t *>(buffer);
-    for (int64_t i = 0; i < n; i++)
-        out[i] = captureFrame(pcm, pcm->appl_ptr + i);
+    captureFrames(pcm, pcm->appl_ptr, static_cast<uint64_t *>(buffer), size_t(n));
     pcm->appl_ptr += n;
     pcm->transferred += uint64_t(n);
     return snd_pcm_sframes_t(n);
@@ -387,7 +437,7 @@ snd_pcm_sframes_t snd_pcm_readi(snd_pcm_t *pcm, void *buffer, snd_pcm_uframes_t 
 
 snd_pcm_sframes_t snd_pcm_writei(snd_pcm_t *pcm, const void *buffer, snd_pcm_uframes_t size)
 {
-    Guard lock(g_mutex);
+    Guard lock(pcm);
     int err;
     if (takeFault(pcm, SX_ALSA_OP_WRITEI, &err))
         return err;
@@ -488,7 +538,7 @@ int snd_pcm_hw_params_get_periods(const snd_pcm_hw_params_t *params, unsigned in
 }
 int snd_pcm_hw_params(snd_pcm_t *pcm, snd_pcm_hw_params_t *params)
 {
-    Guard lock(g_mutex);
+    Guard lock(pcm);
     if (pcm->state == SND_PCM_STATE_RUNNING)
         return -EBUSY;
     pcm->hw = *params;
@@ -510,7 +560,7 @@ int snd_pcm_sw_params_malloc(snd_pcm_sw_params_t **ptr)
 void snd_pcm_sw_params_free(snd_pcm_sw_params_t *obj) { delete obj; }
 int snd_pcm_sw_params_current(snd_pcm_t *pcm, snd_pcm_sw_params_t *params)
 {
-    Guard lock(g_mutex);
+    Guard lock(pcm);
     *params = pcm->sw;
     return 0;
 }
@@ -539,7 +589,7 @@ int snd_pcm_sw_params_set_silence_size(snd_pcm_t *, snd_pcm_sw_params_t *params,
 }
 int snd_pcm_sw_params(snd_pcm_t *pcm, snd_pcm_sw_params_t *params)
 {
-    Guard lock(g_mutex);
+    Guard lock(pcm);
     pcm->sw = *params;
     return 0;
 }
@@ -547,83 +597,84 @@ int snd_pcm_sw_params(snd_pcm_t *pcm, snd_pcm_sw_params_t *params)
 // ---- stub control surface ---------------------------------------------------------------
 size_t sx_alsa_pcm_count(void)
 {
-    Guard lock(g_mutex);
+    std::lock_guard<std::mutex> r(g_registry);
     return g_open.size();
 }
 snd_pcm_t *sx_alsa_pcm_at(size_t index)
 {
-    Guard lock(g_mutex);
+    std::lock_guard<std::mutex> r(g_registry);
     return index < g_open.size() ? g_open[index] : nullptr;
 }
 int sx_alsa_pcm_is_capture(snd_pcm_t *pcm) { return pcm->capture() ? 1 : 0; }
 
 void sx_alsa_advance(snd_pcm_t *pcm, int64_t frames)
 {
-    Guard lock(g_mutex);
+    Guard lock(pcm);
     advanceGroup(pcm, frames);
 }
 void sx_alsa_set_free_run(snd_pcm_t *pcm, int free_run)
 {
-    Guard lock(g_mutex);
+    Guard lock(pcm);
     pcm->free_run = free_run != 0;
 }
 void sx_alsa_set_max_transfer(snd_pcm_t *pcm, snd_pcm_uframes_t frames)
 {
-    Guard lock(g_mutex);
+    Guard lock(pcm);
     pcm->max_transfer = frames;
 }
 void sx_alsa_set_capture_seed(snd_pcm_t *pcm, uint64_t seed)
 {
-    Guard lock(g_mutex);
+    Guard lock(pcm);
     pcm->seed = seed;
     pcm->table.clear();
 }
 void sx_alsa_set_capture_table(snd_pcm_t *pcm, const int32_t *frames, size_t nframes)
 {
-    Guard lock(g_mutex);
+    Guard lock(pcm);
     pcm->table.resize(nframes);
     std::memcpy(pcm->table.data(), frames, nframes * sizeof(uint64_t));
 }
 void sx_alsa_set_sink_limit(snd_pcm_t *pcm, size_t max_frames)
 {
-    Guard lock(g_mutex);
+    Guard lock(pcm);
     pcm->sink_limit = max_frames;
 }
 size_t sx_alsa_sink_read(snd_pcm_t *pcm, int64_t position, size_t nframes, int32_t *out)
 {
-    Guard lock(g_mutex);
+    Guard lock(pcm);
     uint64_t *o = reinterpret_cast<uint64_t *>(out);
-    for (size_t i = 0; i < nframes; i++) {
-        int64_t p = position + int64_t(i);
-        o[i] = (p >= 0 && size_t(p) < pcm->timeline.size()) ? pcm->timeline[size_t(p)] : 0;
-    }
+    std::memset(o, 0, nframes * sizeof(uint64_t));
+    const int64_t lo = std::max<int64_t>(position, 0);
+    const int64_t hi = std::min<int64_t>(position + int64_t(nframes), int64_t(pcm->timeline.size()));
+    if (hi > lo)
+        std::memcpy(o + (lo - position), &pcm->timeline[size_t(lo)], size_t(hi - lo) * sizeof(uint64_t));
     return nframes;
 }
 void sx_alsa_sink_clear(snd_pcm_t *pcm)
 {
-    Guard lock(g_mutex);
+    Guard lock(pcm);
     pcm->timeline.clear();
     pcm->written.clear();
     pcm->dropped_beyond_limit = 0;
 }
 int sx_alsa_sink_written(snd_pcm_t *pcm, int64_t position)
 {
-    Guard lock(g_mutex);
+    Guard lock(pcm);
     return (position >= 0 && size_t(position) < pcm->written.size()) ? pcm->written[size_t(position)] : 0;
 }
 int64_t sx_alsa_hw_ptr(snd_pcm_t *pcm)
 {
-    Guard lock(g_mutex);
+    Guard lock(pcm);
     return pcm->hw_ptr;
 }
 int64_t sx_alsa_appl_ptr(snd_pcm_t *pcm)
 {
-    Guard lock(g_mutex);
+    Guard lock(pcm);
     return pcm->appl_ptr;
 }
 uint64_t sx_alsa_frames_transferred(snd_pcm_t *pcm)
 {
-    Guard lock(g_mutex);
+    Guard lock(pcm);
     return pcm->transferred;
 }
 snd_pcm_uframes_t sx_alsa_buffer_size(snd_pcm_t *pcm) { return pcm->hw.buffer_size; }
@@ -631,7 +682,7 @@ snd_pcm_uframes_t sx_alsa_period_size(snd_pcm_t *pcm) { return pcm->hw.period_si
 
 void sx_alsa_inject_error(snd_pcm_t *pcm, sx_alsa_op op, int err, unsigned skip)
 {
-    Guard lock(g_mutex);
+    Guard lock(pcm);
     if (op < 0 || op >= SX_ALSA_OP_COUNT_)
         return;
     pcm->faults[op].err = err;

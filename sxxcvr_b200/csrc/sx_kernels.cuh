@@ -665,6 +665,38 @@ __global__ void batch_slice_kernel(const BlockDesc *__restrict__ blocks, uint32_
 }
 
 // ---------------------------------------------------------------------------------------
+// Small synchronous calls on host buffers (readStream / writeStream of one period,
+// SoapySX.cpp:451: 256 frames = 2 KiB): the kernel reads and writes the pinned host buffers
+// across PCIe itself and, when the last CTA is done, stores the call's sequence number into a
+// flag in pinned host memory.  The host spins on that flag instead of synchronising the stream,
+// which takes the driver's completion detection (several microseconds) out of a call whose whole
+// duration is of that order.
+// ---------------------------------------------------------------------------------------
+struct FlaggedArgs {
+    BlockDesc block;              // src / dst are device-visible addresses of host (or device) memory
+    unsigned int *arrivals;       // device memory, zero between launches
+    unsigned long long *h_flag;   // pinned host memory
+    unsigned long long seq;
+};
+
+template <class Op>
+__global__ void __launch_bounds__(256) flagged_convert_kernel(const FlaggedArgs a)
+{
+    convert_span<Op>(a.block, 0, a.block.length, blockIdx.x * blockDim.x + threadIdx.x,
+                     gridDim.x * blockDim.x);
+    __threadfence_system(); // this thread's stores are visible to the host ...
+    __syncthreads();        // ... and so are every other thread's of this CTA
+    if (threadIdx.x == 0) {
+        const unsigned int arrived = atomicAdd(a.arrivals, 1u) + 1u;
+        if (arrived == gridDim.x) {
+            *a.arrivals = 0; // ready for the next launch (launches on one stream do not overlap)
+            __threadfence_system();
+            asm volatile("st.global.wt.u64 [%0], %1;" ::"l"(a.h_flag), "l"(a.seq) : "memory");
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Silence, synthetic capture frames, statistics
 // ---------------------------------------------------------------------------------------
 __global__ void fill_silence_kernel(char *i2s, uint64_t nframes)

@@ -12,9 +12,13 @@
 //           stores done = seq
 //   host:   polls `done`.
 //
-// The kernel exits by itself after kIdleNs without work (so it can never pin the GPU: device
-// synchronisation, cudaFree and process exit wait at most that long); the host relaunches it
-// on the next small call.  `alive` tells the host whether a kernel is listening; the exit
+// The kernel can never pin the GPU.  It leaves (a) after kResidentIdleNs without work, (b) at
+// once when the host sets `quit` -- the library does so before every device-wide
+// synchronisation of its own (sxgpu_destroy, sxgpu_bank_destroy, growing the staging ring) --
+// and (c) after kResidentLifeNs in total even when it is busy, so that a device-wide
+// synchronisation the APPLICATION issues (cudaDeviceSynchronize, cudaFree, another library's)
+// waits for at most that long while a stream calls in every period.  The host relaunches it on
+// the next small call.  `alive` tells the host whether a kernel is listening; the exit
 // handshake is: clear `alive`, fence, poll once more and serve a request that raced in.
 #pragma once
 
@@ -32,7 +36,8 @@ struct alignas(64) Mailbox {
     char *dst;
     unsigned int nframes;       // bits 0..30: frames; bit 31: op (0 = RX S32->CF32, 1 = TX CF32->S32)
     unsigned int thr2_bits_op;  // tx_threshold2 as float bits (unused for RX)
-    unsigned long long pad0[4];
+    unsigned long long quit;    // non-zero: leave now (set by the host around device-wide syncs)
+    unsigned long long pad0[3];
     // written by the device (own cache line)
     unsigned long long done; // sequence number of the last request served
     unsigned long long served;
@@ -40,7 +45,8 @@ struct alignas(64) Mailbox {
     int pad1[11];
 };
 
-constexpr unsigned long long kResidentIdleNs = 2000000ull; // 2 ms
+constexpr unsigned long long kResidentIdleNs = 2000000ull;  // 2 ms without a request
+constexpr unsigned long long kResidentLifeNs = 20000000ull; // 20 ms in total, busy or not
 
 __device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long *p)
 {
@@ -69,17 +75,20 @@ struct Request {
     unsigned int nframes;
     unsigned int thr2_bits;
     int op;
+    unsigned long long quit;
 };
 // The 32-byte record as two 16-byte loads.
 __device__ __forceinline__ Request ld_request(const Mailbox *box)
 {
-    unsigned long long a, b, c, d;
+    unsigned long long a, b, c, d, q;
     asm volatile("ld.global.cv.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(box) : "memory");
     asm volatile("ld.global.cv.v2.u64 {%0,%1}, [%2];"
                  : "=l"(c), "=l"(d)
                  : "l"(reinterpret_cast<const char *>(box) + 16)
                  : "memory");
+    asm volatile("ld.global.cv.u64 %0, [%1];" : "=l"(q) : "l"(reinterpret_cast<const char *>(box) + 32) : "memory");
     Request r;
+    r.quit = q;
     r.seq = a;
     r.src = reinterpret_cast<const char *>(b);
     r.dst = reinterpret_cast<char *>(c);
@@ -129,11 +138,11 @@ __global__ void __launch_bounds__(256) resident_kernel(Mailbox *box, unsigned lo
     __shared__ float s_thr2;
     __shared__ int s_op;
 
-    unsigned long long idle_since = 0; // thread 0 only
+    unsigned long long idle_since = 0, born = 0; // thread 0 only
     if (threadIdx.x == 0) {
         box->alive = 1;
         __threadfence_system();
-        idle_since = global_timer_ns();
+        idle_since = born = global_timer_ns();
     }
     for (;;) {
         if (threadIdx.x == 0) {
@@ -152,7 +161,8 @@ __global__ void __launch_bounds__(256) resident_kernel(Mailbox *box, unsigned lo
                 }
                 if (leaving)
                     break;
-                if (global_timer_ns() - idle_since > kResidentIdleNs) {
+                const unsigned long long now = global_timer_ns();
+                if (req.quit || now - idle_since > kResidentIdleNs || now - born > kResidentLifeNs) {
                     box->alive = 0;
                     __threadfence_system();
                     leaving = true;
@@ -188,6 +198,8 @@ __global__ void __launch_bounds__(256) resident_kernel(Mailbox *box, unsigned lo
         }
         if (leave)
             return; // `alive` is already clear; the host relaunches for the next block
+        // (a kernel past its lifetime leaves through the poll loop above: it clears `alive`,
+        // looks once more, and goes)
     }
 }
 

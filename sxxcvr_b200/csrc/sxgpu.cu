@@ -22,6 +22,8 @@
 #include <mutex>
 #include <string>
 #include <tuple>
+#include <type_traits>
+#include <vector>
 
 #include <sched.h>
 
@@ -46,6 +48,36 @@ struct HostRing {
     bool events = false;
 };
 
+// Completion flag of the small-call kernel (flagged_convert_kernel): pinned, device-mapped.
+struct alignas(64) SmallFlag {
+    volatile unsigned long long done;
+};
+
+// One direction of the host-buffer path.  The reference locks per stream (one mutex in each
+// AlsaPcm, SoapySX.cpp:373, taken at :878 and :979) so that an RX thread and a TX thread run
+// side by side (example/plot_rxtx_response.py:65-77); so does this: each direction has its own
+// lock, streams, device ring, bounce threads and small-call machinery, and shares nothing with
+// the other but the GPU.
+struct HostLane {
+    std::mutex mutex;
+    cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
+    HostRing ring;
+    std::unique_ptr<sxhost::ParallelCopier> copier_in, copier_out; // bounce copies of pageable callers
+    sxhost::Sidekick retirer;                                      // runs the outbound half of the pipeline
+    sxhost::Progress issued, retired;
+    std::atomic<int> pipeline_error{0};
+
+    // small synchronous calls
+    SmallFlag *flag = nullptr;       // pinned
+    unsigned int *d_arrivals = nullptr;
+    unsigned long long flag_seq = 0;
+
+    // resident converter (sx_resident.cuh)
+    Mailbox *mailbox = nullptr;
+    cudaStream_t s_resident = nullptr;
+    unsigned long long resident_seq = 0;
+};
+
 } // namespace
 
 struct sxgpu_ctx {
@@ -62,7 +94,9 @@ struct sxgpu_ctx {
     int64_t bulk_load_policy = 0, bulk_store_policy = 0; // L2 eviction: 0 first, 1 normal, 2 last, 3 unchanged
     int64_t bulk_contiguous = 0;            // 0 round-robin tiles, 1 one contiguous range per CTA
     int64_t host_chunk_frames = 0;          // 0 auto (see pick_chunk_frames)
+    int64_t host_chunk_min_frames = 1 << 16; // first and last chunk of the ramped schedule; 0 = no ramp
     int64_t host_mode = 0;                  // 0 auto, 1 copy engines, 2 zero-copy
+    int64_t small_mode = 0;                 // completion of small calls: 0 auto (= 2), 1 stream sync, 2 host flag
     int64_t zero_copy_max_frames = 1 << 18; // measured crossover, profiles/r01_sweep_host_path.json
     int64_t resident_max_frames = 0;        // > 0: blocks up to this size go to the resident converter
     int64_t zero_copy_variant = 1;          // schedule of the zero-copy kernel (1 vec128, 2 vec256, 3 bulk)
@@ -75,18 +109,11 @@ struct sxgpu_ctx {
     cpu_set_t local_cpus;
     bool have_local_cpus = false;
 
-    // resident converter (sx_resident.cuh); guarded by host_mutex
-    Mailbox *mailbox = nullptr;
-    cudaStream_t s_resident = nullptr;
-    unsigned long long resident_seq = 0;
-    std::atomic<uint64_t> resident_launches{0}, resident_calls{0};
+    std::atomic<uint64_t> resident_launches{0}, resident_calls{0}, flagged_calls{0};
     std::atomic<int> live_banks{0}; // banks keep a pointer to their context
 
-    // host pipeline
-    std::mutex host_mutex;
-    std::unique_ptr<sxhost::ParallelCopier> copier; // guarded by host_mutex
-    cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
-    HostRing ring;
+    // host pipeline: lane 0 serves the RX conversions, lane 1 the TX conversions
+    HostLane lanes[2];
 
     // statistics scratch
     StatsAcc *d_stats = nullptr;
@@ -98,6 +125,7 @@ struct sxgpu_ctx {
 
     std::mutex err_mutex;
     std::string last_error;
+    uint64_t error_serial = 0; // bumped with every new message, see sxgpu_last_error
 
     // occupancy of each (kernel, block, smem) seen so far: the query costs about a microsecond,
     // which matters when the whole call is a 2 KiB block
@@ -108,6 +136,7 @@ struct sxgpu_ctx {
     {
         std::lock_guard<std::mutex> lock(err_mutex);
         last_error = std::string(what) + ": " + cudaGetErrorString(e);
+        error_serial++;
         cudaGetLastError(); // clear the sticky-free error state
         return (e == cudaErrorMemoryAllocation) ? SXGPU_ERR_NOMEM : SXGPU_ERR_CUDA;
     }
@@ -115,6 +144,7 @@ struct sxgpu_ctx {
     {
         std::lock_guard<std::mutex> lock(err_mutex);
         last_error = what;
+        error_serial++;
         return SXGPU_ERR_INVALID;
     }
 };
@@ -515,9 +545,9 @@ HostPtrInfo classify_pointer(const sxgpu_ctx *ctx, const void *p)
     return info;
 }
 
-// Chunk size of the copy-engine pipeline.  Measured on B200 / PCIe Gen5 (profiles/
+// Largest chunk of the copy-engine pipeline.  Measured on B200 / PCIe Gen5 (profiles/
 // r01_sweep_host_path.json): about an eighth of the block, between 2 MiB and 32 MiB per
-// side, keeps both copy engines busy while bounding the fill and drain of the pipeline.
+// side, keeps both copy engines busy; the first and last chunks are smaller (plan_chunks).
 size_t pick_chunk_frames(const sxgpu_ctx *ctx, size_t length)
 {
     if (ctx->host_chunk_frames > 0)
@@ -528,16 +558,16 @@ size_t pick_chunk_frames(const sxgpu_ctx *ctx, size_t length)
     return chunk;
 }
 
-int ensure_ring(sxgpu_ctx *ctx, size_t frames, bool bounce_in, bool bounce_out)
+int ensure_lane(sxgpu_ctx *ctx, HostLane &lane)
 {
-    HostRing &r = ctx->ring;
-    if (!ctx->s_h2d) {
-        // Ordinary streams as well (they still run concurrently with each other): a device buffer
-        // the caller produced on the default stream is safe to hand to the synchronous calls.
-        SX_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamDefault));
-        SX_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamDefault));
-        SX_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamDefault));
+    if (!lane.s_h2d) {
+        // Ordinary streams (they still run concurrently with each other): a device buffer the
+        // caller produced on the default stream is safe to hand to the synchronous calls.
+        SX_CUDA(ctx, cudaStreamCreateWithFlags(&lane.s_h2d, cudaStreamDefault));
+        SX_CUDA(ctx, cudaStreamCreateWithFlags(&lane.s_comp, cudaStreamDefault));
+        SX_CUDA(ctx, cudaStreamCreateWithFlags(&lane.s_d2h, cudaStreamDefault));
     }
+    HostRing &r = lane.ring;
     if (!r.events) {
         for (int i = 0; i < kRingSlots; i++) {
             SX_CUDA(ctx, cudaEventCreateWithFlags(&r.copied_in[i], cudaEventDisableTiming));
@@ -546,7 +576,35 @@ int ensure_ring(sxgpu_ctx *ctx, size_t frames, bool bounce_in, bool bounce_out)
         }
         r.events = true;
     }
+    if (!lane.flag) {
+        SX_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(&lane.flag), sizeof(SmallFlag),
+                                   cudaHostAllocMapped | cudaHostAllocPortable));
+        lane.flag->done = 0;
+        SX_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&lane.d_arrivals), sizeof(unsigned int)));
+        SX_CUDA(ctx, cudaMemset(lane.d_arrivals, 0, sizeof(unsigned int)));
+    }
+    return SXGPU_OK;
+}
+
+// Ask the lane's resident converter, if one is listening, to leave, and wait until it has.
+// Called (lane lock held) before anything that synchronises the whole device.
+void resident_stop(sxgpu_ctx *, HostLane &lane)
+{
+    if (!lane.mailbox || !lane.s_resident)
+        return;
+    volatile Mailbox *box = lane.mailbox;
+    box->quit = 1;
+    std::atomic_thread_fence(std::memory_order_seq_cst);
+    cudaStreamSynchronize(lane.s_resident);
+    box->quit = 0;
+}
+
+int ensure_ring(sxgpu_ctx *ctx, HostLane &lane, size_t frames, bool bounce_in, bool bounce_out)
+{
+    SX_TRY(ensure_lane(ctx, lane));
+    HostRing &r = lane.ring;
     if (frames > r.chunk_frames) { // grow-only, like the reference's staging vectors (:944, :1087)
+        resident_stop(ctx, lane); // cudaFree synchronises the device
         for (int i = 0; i < kRingSlots; i++) {
             if (r.d_in[i]) cudaFree(r.d_in[i]);
             if (r.d_out[i]) cudaFree(r.d_out[i]);
@@ -571,26 +629,27 @@ int ensure_ring(sxgpu_ctx *ctx, size_t frames, bool bounce_in, bool bounce_out)
     return SXGPU_OK;
 }
 
-// Hand one small block to the resident converter and wait for it.  `src` and `dst` are
+// Hand one small block to the lane's resident converter and wait for it.  `src` and `dst` are
 // device-visible addresses of distinct buffers.  Every wait is bounded.
-int resident_convert_call(sxgpu_ctx *ctx, int op, const void *src, void *dst, size_t length, float thr2)
+int resident_convert_call(sxgpu_ctx *ctx, HostLane &lane, int op, const void *src, void *dst, size_t length,
+                          float thr2)
 {
     using clock = std::chrono::steady_clock;
-    if (!ctx->mailbox) {
-        SX_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(&ctx->mailbox), sizeof(Mailbox),
+    if (!lane.mailbox) {
+        SX_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(&lane.mailbox), sizeof(Mailbox),
                                    cudaHostAllocMapped | cudaHostAllocPortable));
-        std::memset(ctx->mailbox, 0, sizeof(Mailbox));
-        SX_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_resident, cudaStreamNonBlocking));
+        std::memset(lane.mailbox, 0, sizeof(Mailbox));
+        SX_CUDA(ctx, cudaStreamCreateWithFlags(&lane.s_resident, cudaStreamNonBlocking));
     }
-    volatile Mailbox *box = ctx->mailbox;
+    volatile Mailbox *box = lane.mailbox;
 
     auto ensure_listening = [&]() -> int {
         if (box->alive)
             return SXGPU_OK;
-        // No kernel is listening (never started, or it left after its idle timeout).  Wait for
-        // the old one to be completely gone, then start a new one and wait until it says so.
-        SX_CUDA(ctx, cudaStreamSynchronize(ctx->s_resident));
-        resident_kernel<<<1, 256, 0, ctx->s_resident>>>(ctx->mailbox, ctx->resident_seq);
+        // No kernel is listening (never started, or it left: idle, lifetime, or asked to).  Wait
+        // for the old one to be completely gone, then start a new one and wait until it says so.
+        SX_CUDA(ctx, cudaStreamSynchronize(lane.s_resident));
+        resident_kernel<<<1, 256, 0, lane.s_resident>>>(lane.mailbox, lane.resident_seq);
         SX_CUDA(ctx, cudaGetLastError());
         ctx->launches++;
         ctx->resident_launches++;
@@ -603,7 +662,7 @@ int resident_convert_call(sxgpu_ctx *ctx, int op, const void *src, void *dst, si
     };
     SX_TRY(ensure_listening());
 
-    const unsigned long long seq = ++ctx->resident_seq;
+    const unsigned long long seq = ++lane.resident_seq;
     unsigned thr2_bits;
     std::memcpy(&thr2_bits, &thr2, sizeof thr2_bits);
     box->src = static_cast<const char *>(src);
@@ -622,12 +681,12 @@ int resident_convert_call(sxgpu_ctx *ctx, int op, const void *src, void *dst, si
             // The kernel left.  Once it is really gone either it served this request in its last
             // look (done == seq) or it never saw it: then a fresh kernel, started with
             // last_seen = seq - 1, picks it up from the mailbox.
-            SX_CUDA(ctx, cudaStreamSynchronize(ctx->s_resident));
+            SX_CUDA(ctx, cudaStreamSynchronize(lane.s_resident));
             if (box->done == seq)
                 break;
-            ctx->resident_seq = seq - 1;
+            lane.resident_seq = seq - 1;
             SX_TRY(ensure_listening());
-            ctx->resident_seq = seq;
+            lane.resident_seq = seq;
             t0 = clock::now();
         }
         if (clock::now() - t0 > std::chrono::seconds(2))
@@ -651,11 +710,50 @@ template <> constexpr int resident_op<TxCf32>()
     return 1;
 }
 
-// Bounce copy between a pageable caller buffer and pinned staging (host_mutex held).  Half of
-// this process's share of the hardware threads, at most eight, take a large copy together: one
-// thread moves 5-7 GB/s each way through the pipeline, eight 16-23, the link behind the staging
-// buffer 46 (profiles/r01_bench_pageable.json).  Under torchrun the share is 1 / LOCAL_WORLD_SIZE.
-void bounce_copy(sxgpu_ctx *ctx, void *dst, const void *src, size_t bytes)
+// One small block, one launch, completion through a flag in pinned memory (sx_kernels.cuh,
+// flagged_convert_kernel).  `src` and `dst` are device-visible and frame-aligned.
+template <class Op>
+int flagged_convert_call(sxgpu_ctx *ctx, HostLane &lane, const void *src, void *dst, size_t length, float thr2)
+{
+    using clock = std::chrono::steady_clock;
+    FlaggedArgs a;
+    a.block.src = static_cast<const char *>(src);
+    a.block.dst = static_cast<char *>(dst);
+    a.block.length = length;
+    a.block.thr2 = thr2;
+    a.block.reserved = 0;
+    a.arrivals = lane.d_arrivals;
+    a.h_flag = const_cast<unsigned long long *>(&lane.flag->done);
+    a.seq = ++lane.flag_seq;
+    // 1024 frames per CTA: a period is one CTA, the largest small call one CTA per SM.
+    const int grid = int(std::min<uint64_t>((length + 1023) / 1024, uint64_t(ctx->prop.multiProcessorCount)));
+    flagged_convert_kernel<Op><<<grid, 256, 0, lane.s_comp>>>(a);
+    SX_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+    unsigned spins = 0;
+    auto t0 = clock::now();
+    while (lane.flag->done != a.seq) {
+        if ((++spins & 0xFFF) != 0)
+            continue;
+        // Every few thousand looks make sure the kernel has not died under us.
+        cudaError_t q = cudaStreamQuery(lane.s_comp);
+        if (q != cudaSuccess && q != cudaErrorNotReady)
+            return ctx->fail(q, "small-call kernel");
+        if (q == cudaSuccess && lane.flag->done != a.seq && clock::now() - t0 > std::chrono::milliseconds(100))
+            return ctx->invalid("small-call kernel finished without raising its flag");
+        if (clock::now() - t0 > std::chrono::seconds(5))
+            return ctx->invalid("small-call kernel did not finish");
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    ctx->flagged_calls++;
+    return SXGPU_OK;
+}
+
+// Threads that share one bounce copy between a pageable caller buffer and pinned staging: half
+// of this process's share of the hardware threads, at most eight.  One thread moves 5-7 GB/s
+// through the pipeline, eight 32-46, the link behind the staging buffer 46
+// (profiles/r01_bench_pageable.json).  Under torchrun the share is 1 / LOCAL_WORLD_SIZE.
+unsigned bounce_thread_count(const sxgpu_ctx *ctx)
 {
     unsigned threads = unsigned(std::min<int64_t>(ctx->bounce_threads, 64));
     if (threads == 0) {
@@ -664,9 +762,24 @@ void bounce_copy(sxgpu_ctx *ctx, void *dst, const void *src, size_t bytes)
             ranks = unsigned(std::max(1, std::atoi(env)));
         threads = std::max(1u, std::min(8u, std::thread::hardware_concurrency() / (2 * ranks)));
     }
-    if (!ctx->copier || ctx->copier->helpers() != threads - 1)
-        ctx->copier.reset(new sxhost::ParallelCopier(threads - 1));
-    ctx->copier->copy(dst, src, bytes);
+    return threads;
+}
+
+void bounce_copy(sxgpu_ctx *ctx, std::unique_ptr<sxhost::ParallelCopier> &copier, void *dst, const void *src,
+                 size_t bytes)
+{
+    const unsigned threads = bounce_thread_count(ctx);
+    if (!copier || copier->helpers() != threads - 1)
+        copier.reset(new sxhost::ParallelCopier(threads - 1));
+    copier->copy(dst, src, bytes);
+}
+
+template <class Op> constexpr int lane_of()
+{
+    return (std::is_same<Op, TxCf32>::value || std::is_same<Op, TxCs16>::value ||
+            std::is_same<Op, TxCf32S16>::value)
+               ? 1
+               : 0;
 }
 
 template <class Op>
@@ -685,7 +798,8 @@ int convert_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset, void *h_d
     const char *src = static_cast<const char *>(h_src) + src_offset * SFB;
     char *dst = static_cast<char *>(h_dest) + dest_offset * DFB;
 
-    std::lock_guard<std::mutex> lock(ctx->host_mutex);
+    HostLane &lane = ctx->lanes[lane_of<Op>()];
+    std::lock_guard<std::mutex> lock(lane.mutex);
     SX_CUDA(ctx, cudaSetDevice(ctx->device));
 
     HostPtrInfo si = classify_pointer(ctx, src), di = classify_pointer(ctx, dst);
@@ -702,86 +816,141 @@ int convert_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset, void *h_d
                        (ctx->host_mode == 0 && length <= size_t(ctx->zero_copy_max_frames));
     if (both_on_device || small) {
         const bool bounce_in = !si.device_alias, bounce_out = !di.device_alias;
-        SX_TRY(ensure_ring(ctx, (bounce_in || bounce_out) ? length : 0, bounce_in, bounce_out));
+        SX_TRY(ensure_ring(ctx, lane, (bounce_in || bounce_out) ? length : 0, bounce_in, bounce_out));
         const void *kernel_in = si.device_alias;
         void *kernel_out = di.device_alias;
         if (bounce_in) {
-            bounce_copy(ctx, ctx->ring.h_in[0], src, length * SFB);
-            kernel_in = ctx->ring.h_in[0]; // pinned memory is device-addressable at the same address (UVA)
+            bounce_copy(ctx, lane.copier_in, lane.ring.h_in[0], src, length * SFB);
+            kernel_in = lane.ring.h_in[0]; // pinned memory is device-addressable at the same address (UVA)
         }
         if (bounce_out)
-            kernel_out = ctx->ring.h_out[0];
-        const bool frame_aligned = reinterpret_cast<uintptr_t>(kernel_in) % 8 == 0 &&
-                                   reinterpret_cast<uintptr_t>(kernel_out) % 8 == 0;
+            kernel_out = lane.ring.h_out[0];
+        const bool frame_aligned = reinterpret_cast<uintptr_t>(kernel_in) % SFB == 0 &&
+                                   reinterpret_cast<uintptr_t>(kernel_out) % DFB == 0;
         if (resident_op<Op>() >= 0 && !both_on_device && length <= size_t(ctx->resident_max_frames) &&
-            length < (size_t(1) << 31) &&
-            frame_aligned && kernel_in != kernel_out) {
-            SX_TRY(resident_convert_call(ctx, resident_op<Op>(), kernel_in, kernel_out, length, thr2));
+            length < (size_t(1) << 31) && frame_aligned && kernel_in != kernel_out) {
+            SX_TRY(resident_convert_call(ctx, lane, resident_op<Op>(), kernel_in, kernel_out, length, thr2));
+        } else if (!both_on_device && ctx->small_mode != 1 && frame_aligned && ctx->host_mode != 2) {
+            SX_TRY(flagged_convert_call<Op>(ctx, lane, kernel_in, kernel_out, length, thr2));
         } else {
             SX_TRY(launch_convert<Op>(ctx, kernel_in, kernel_out, length, thr2,
-                                      both_on_device ? variant : ctx->zero_copy_variant, ctx->s_comp));
-            SX_CUDA(ctx, cudaStreamSynchronize(ctx->s_comp));
+                                      both_on_device ? variant : ctx->zero_copy_variant, lane.s_comp));
+            SX_CUDA(ctx, cudaStreamSynchronize(lane.s_comp));
         }
         if (bounce_out)
-            bounce_copy(ctx, dst, ctx->ring.h_out[0], length * DFB);
+            bounce_copy(ctx, lane.copier_out, dst, lane.ring.h_out[0], length * DFB);
         ctx->h2d_bytes += in_bytes;
         ctx->d2h_bytes += out_bytes;
         return SXGPU_OK;
     }
 
-    // Copy-engine pipeline over the ring.  A side that is device memory skips its copy: the
-    // kernel reads the caller's device buffer, or writes into it, directly.
-    size_t chunk = std::min<size_t>(length, pick_chunk_frames(ctx, length));
-    SX_TRY(ensure_ring(ctx, chunk, !si.pinned && !si.on_device, !di.pinned && !di.on_device));
-    HostRing &r = ctx->ring;
-    chunk = std::min(chunk, r.chunk_frames);
-    const size_t nchunks = (length + chunk - 1) / chunk;
+    // Copy-engine pipeline over the lane's ring.  A side that is device memory skips its copy:
+    // the kernel reads the caller's device buffer, or writes into it, directly.  A side that is
+    // pageable host memory is bounced through pinned staging: the inbound copies by this thread
+    // (and its helpers) just before each chunk is queued, the outbound copies by the lane's
+    // sidekick thread (and its helpers) as each chunk's device-to-host copy completes -- so the
+    // two directions' CPU copies, the DMA and the kernels of different chunks all overlap.
+    const bool bounce_in = !si.pinned && !si.on_device, bounce_out = !di.pinned && !di.on_device;
+    const size_t c_max = std::min<size_t>(length, pick_chunk_frames(ctx, length));
+    SX_TRY(ensure_ring(ctx, lane, c_max, bounce_in, bounce_out));
+    HostRing &r = lane.ring;
+    const std::vector<sxhost::ChunkSpan> chunks =
+        sxhost::plan_chunks(length, size_t(ctx->host_chunk_min_frames), std::min(c_max, r.chunk_frames));
+    const size_t nchunks = chunks.size();
 
-    auto chunk_len = [&](size_t i) { return std::min(chunk, length - i * chunk); };
-    auto retire = [&](size_t i) -> int { // chunk i's last operation was issued into slot i % K
-        int slot = int(i % kRingSlots);
-        SX_CUDA(ctx, cudaEventSynchronize(r.done[slot]));
-        if (!di.pinned && !di.on_device)
-            bounce_copy(ctx, dst + i * chunk * DFB, r.h_out[slot], chunk_len(i) * DFB);
+    lane.issued.reset();
+    lane.retired.reset();
+    lane.pipeline_error.store(0);
+    const bool use_sidekick = bounce_out;
+    if (use_sidekick) {
+        lane.retirer.start([ctx, &lane, &r, &chunks, nchunks, dst] {
+            if (cudaSetDevice(ctx->device) != cudaSuccess) {
+                lane.pipeline_error.store(int(cudaGetLastError()) | 0x10000);
+                return;
+            }
+            for (size_t i = 0; i < nchunks; i++) {
+                if (!lane.issued.wait_for(i + 1, lane.pipeline_error))
+                    return;
+                const int slot = int(i % kRingSlots);
+                cudaError_t e = cudaEventSynchronize(r.done[slot]);
+                if (e != cudaSuccess) {
+                    lane.pipeline_error.store(int(e) | 0x10000);
+                    return;
+                }
+                bounce_copy(ctx, lane.copier_out, dst + chunks[i].first * DFB, r.h_out[slot], chunks[i].frames * DFB);
+                lane.retired.publish(i + 1);
+            }
+        });
+    }
+    // Whatever happens below, the sidekick is told (pipeline_error) and waited for before return.
+    auto finish = [&](int rc) -> int {
+        if (use_sidekick) {
+            if (rc != SXGPU_OK)
+                lane.pipeline_error.store(1);
+            lane.retirer.finish();
+            const int pe = lane.pipeline_error.load();
+            if (rc == SXGPU_OK && (pe & 0x10000))
+                rc = ctx->fail(cudaError_t(pe & 0xFFFF), "host pipeline (outbound side)");
+        }
+        return rc;
+    };
+    // Slot i % K is free again once chunk i - K has left it: its device-to-host copy is complete
+    // (and, for a pageable destination, bounced out).
+    auto wait_slot_free = [&](size_t i) -> int {
+        if (i < size_t(kRingSlots))
+            return SXGPU_OK;
+        if (use_sidekick) {
+            if (!lane.retired.wait_for(i - kRingSlots + 1, lane.pipeline_error))
+                return SXGPU_ERR_CUDA;
+            return SXGPU_OK;
+        }
+        SX_CUDA(ctx, cudaEventSynchronize(r.done[int(i % kRingSlots)]));
         return SXGPU_OK;
     };
 
-    for (size_t i = 0; i < nchunks; i++) {
-        int slot = int(i % kRingSlots);
-        if (i >= size_t(kRingSlots))
-            SX_TRY(retire(i - kRingSlots)); // frees the slot's device and bounce buffers
-        size_t n = chunk_len(i);
+    auto issue_all = [&]() -> int {
+        for (size_t i = 0; i < nchunks; i++) {
+            const int slot = int(i % kRingSlots);
+            SX_TRY(wait_slot_free(i));
+            const size_t first = chunks[i].first, n = chunks[i].frames;
 
-        const void *kernel_in = r.d_in[slot];
-        if (si.on_device) {
-            kernel_in = static_cast<const char *>(si.device_alias) + i * chunk * SFB;
-        } else {
-            const void *from = src + i * chunk * SFB;
-            if (!si.pinned) {
-                bounce_copy(ctx, r.h_in[slot], from, n * SFB);
-                from = r.h_in[slot];
+            const void *kernel_in = r.d_in[slot];
+            if (si.on_device) {
+                kernel_in = static_cast<const char *>(si.device_alias) + first * SFB;
+            } else {
+                const void *from = src + first * SFB;
+                if (bounce_in) {
+                    bounce_copy(ctx, lane.copier_in, r.h_in[slot], from, n * SFB);
+                    from = r.h_in[slot];
+                }
+                SX_CUDA(ctx, cudaMemcpyAsync(r.d_in[slot], from, n * SFB, cudaMemcpyHostToDevice, lane.s_h2d));
+                SX_CUDA(ctx, cudaEventRecord(r.copied_in[slot], lane.s_h2d));
+                SX_CUDA(ctx, cudaStreamWaitEvent(lane.s_comp, r.copied_in[slot], 0));
             }
-            SX_CUDA(ctx, cudaMemcpyAsync(r.d_in[slot], from, n * SFB, cudaMemcpyHostToDevice, ctx->s_h2d));
-            SX_CUDA(ctx, cudaEventRecord(r.copied_in[slot], ctx->s_h2d));
-            SX_CUDA(ctx, cudaStreamWaitEvent(ctx->s_comp, r.copied_in[slot], 0));
-        }
 
-        void *kernel_out = di.on_device ? static_cast<void *>(static_cast<char *>(di.device_alias) + i * chunk * DFB)
-                                        : r.d_out[slot];
-        SX_TRY(launch_convert<Op>(ctx, kernel_in, kernel_out, n, thr2, variant, ctx->s_comp));
+            void *kernel_out = di.on_device ? static_cast<void *>(static_cast<char *>(di.device_alias) + first * DFB)
+                                            : r.d_out[slot];
+            SX_TRY(launch_convert<Op>(ctx, kernel_in, kernel_out, n, thr2, variant, lane.s_comp));
 
-        if (di.on_device) {
-            SX_CUDA(ctx, cudaEventRecord(r.done[slot], ctx->s_comp));
-        } else {
-            SX_CUDA(ctx, cudaEventRecord(r.converted[slot], ctx->s_comp));
-            SX_CUDA(ctx, cudaStreamWaitEvent(ctx->s_d2h, r.converted[slot], 0));
-            void *to = di.pinned ? static_cast<void *>(dst + i * chunk * DFB) : r.h_out[slot];
-            SX_CUDA(ctx, cudaMemcpyAsync(to, r.d_out[slot], n * DFB, cudaMemcpyDeviceToHost, ctx->s_d2h));
-            SX_CUDA(ctx, cudaEventRecord(r.done[slot], ctx->s_d2h));
+            if (di.on_device) {
+                SX_CUDA(ctx, cudaEventRecord(r.done[slot], lane.s_comp));
+            } else {
+                SX_CUDA(ctx, cudaEventRecord(r.converted[slot], lane.s_comp));
+                SX_CUDA(ctx, cudaStreamWaitEvent(lane.s_d2h, r.converted[slot], 0));
+                void *to = bounce_out ? r.h_out[slot] : static_cast<void *>(dst + first * DFB);
+                SX_CUDA(ctx, cudaMemcpyAsync(to, r.d_out[slot], n * DFB, cudaMemcpyDeviceToHost, lane.s_d2h));
+                SX_CUDA(ctx, cudaEventRecord(r.done[slot], lane.s_d2h));
+            }
+            lane.issued.publish(i + 1);
         }
-    }
-    for (size_t i = (nchunks > size_t(kRingSlots) ? nchunks - kRingSlots : 0); i < nchunks; i++)
-        SX_TRY(retire(i));
+        if (!use_sidekick) {
+            // The last K chunks are still in flight; events complete in stream order.
+            for (size_t i = (nchunks > size_t(kRingSlots) ? nchunks - kRingSlots : 0); i < nchunks; i++)
+                SX_CUDA(ctx, cudaEventSynchronize(r.done[int(i % kRingSlots)]));
+        }
+        return SXGPU_OK;
+    };
+    SX_TRY(finish(issue_all()));
 
     ctx->h2d_bytes += in_bytes;
     ctx->d2h_bytes += out_bytes;
@@ -819,11 +988,32 @@ int convert_batch(sxgpu_ctx *ctx, const sxgpu_block *blocks, uint32_t nblocks, i
         }
         // Stream-ordered staging: safe against back-to-back batches on any stream.
         SX_CUDA(ctx, cudaMallocAsync(&staged, size_t(nblocks) * sizeof(BlockDesc), st));
-        SX_CUDA(ctx, cudaMemcpyAsync(staged, blocks, size_t(nblocks) * sizeof(BlockDesc),
-                                     cudaMemcpyHostToDevice, st));
-        d_blocks = static_cast<const BlockDesc *>(staged);
     } else if (max_length == 0) {
         return ctx->invalid("max_length is required for device-resident block lists");
+    }
+    // From here on every return path gives the staging memory back.
+    struct StagedGuard {
+        void *p;
+        cudaStream_t st;
+        ~StagedGuard()
+        {
+            if (p)
+                cudaFreeAsync(p, st);
+        }
+    } guard = {staged, st};
+    if (staged) {
+        // The caller may reuse `blocks` as soon as this call returns: when the list sits in pinned
+        // memory cudaMemcpyAsync is truly asynchronous and would read it later, so the copy is
+        // waited for here (a few microseconds for a list of this size; the kernels stay asynchronous).
+        SX_CUDA(ctx, cudaMemcpyAsync(staged, blocks, size_t(nblocks) * sizeof(BlockDesc),
+                                     cudaMemcpyHostToDevice, st));
+        if (classify_pointer(ctx, blocks).pinned) {
+            cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+            cudaStreamIsCapturing(st, &capturing);
+            if (capturing == cudaStreamCaptureStatusNone)
+                SX_CUDA(ctx, cudaStreamSynchronize(st));
+        }
+        d_blocks = static_cast<const BlockDesc *>(staged);
     }
 
     const int sms = ctx->prop.multiProcessorCount;
@@ -843,8 +1033,6 @@ int convert_batch(sxgpu_ctx *ctx, const sxgpu_block *blocks, uint32_t nblocks, i
     }
     SX_CUDA(ctx, cudaGetLastError());
     ctx->launches++;
-    if (staged)
-        SX_CUDA(ctx, cudaFreeAsync(staged, st));
     return SXGPU_OK;
 }
 
@@ -865,7 +1053,9 @@ int64_t *option_slot(sxgpu_ctx *ctx, const char *key)
         {"bulk_store_policy", &ctx->bulk_store_policy},
         {"bulk_contiguous", &ctx->bulk_contiguous},
         {"host_chunk_frames", &ctx->host_chunk_frames},
+        {"host_chunk_min_frames", &ctx->host_chunk_min_frames},
         {"host_mode", &ctx->host_mode},
+        {"small_mode", &ctx->small_mode},
         {"zero_copy_max_frames", &ctx->zero_copy_max_frames},
         {"resident_max_frames", &ctx->resident_max_frames},
         {"zero_copy_variant", &ctx->zero_copy_variant},
@@ -919,10 +1109,14 @@ const char *sxgpu_strerror(int code)
 
 const char *sxgpu_last_error(sxgpu_ctx *ctx)
 {
+    // The message is copied into storage of the calling thread, so the pointer stays valid (and
+    // its contents unchanged) until this thread asks again, whatever other threads do meanwhile.
+    static thread_local std::string mine;
     if (!ctx)
         return "";
     std::lock_guard<std::mutex> lock(ctx->err_mutex);
-    return ctx->last_error.c_str();
+    mine = ctx->last_error;
+    return mine.c_str();
 }
 
 int sxgpu_init(int device, sxgpu_ctx **out)
@@ -938,6 +1132,10 @@ int sxgpu_init(int device, sxgpu_ctx **out)
     sxgpu_ctx *ctx = new sxgpu_ctx();
     ctx->device = device;
     auto bail = [&](int code) {
+        if (ctx->d_stats) cudaFree(ctx->d_stats);
+        if (ctx->h_stats) cudaFreeHost(ctx->h_stats);
+        if (ctx->stream) cudaStreamDestroy(ctx->stream);
+        cudaGetLastError();
         delete ctx;
         return code;
     };
@@ -972,24 +1170,32 @@ int sxgpu_destroy(sxgpu_ctx *ctx)
     if (ctx->live_banks.load() != 0)
         return ctx->invalid("destroy the context's stream banks first");
     cudaSetDevice(ctx->device);
-    cudaDeviceSynchronize();
-    HostRing &r = ctx->ring;
-    for (int i = 0; i < kRingSlots; i++) {
-        if (r.d_in[i]) cudaFree(r.d_in[i]);
-        if (r.d_out[i]) cudaFree(r.d_out[i]);
-        if (r.h_in[i]) cudaFreeHost(r.h_in[i]);
-        if (r.h_out[i]) cudaFreeHost(r.h_out[i]);
-        if (r.events) {
-            cudaEventDestroy(r.copied_in[i]);
-            cudaEventDestroy(r.converted[i]);
-            cudaEventDestroy(r.done[i]);
-        }
+    for (HostLane &lane : ctx->lanes) {
+        std::lock_guard<std::mutex> lock(lane.mutex);
+        resident_stop(ctx, lane);
     }
-    if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
-    if (ctx->s_comp) cudaStreamDestroy(ctx->s_comp);
-    if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
-    if (ctx->s_resident) cudaStreamDestroy(ctx->s_resident); // the resident kernel has left: device was synchronised
-    if (ctx->mailbox) cudaFreeHost(ctx->mailbox);
+    cudaDeviceSynchronize();
+    for (HostLane &lane : ctx->lanes) {
+        HostRing &r = lane.ring;
+        for (int i = 0; i < kRingSlots; i++) {
+            if (r.d_in[i]) cudaFree(r.d_in[i]);
+            if (r.d_out[i]) cudaFree(r.d_out[i]);
+            if (r.h_in[i]) cudaFreeHost(r.h_in[i]);
+            if (r.h_out[i]) cudaFreeHost(r.h_out[i]);
+            if (r.events) {
+                cudaEventDestroy(r.copied_in[i]);
+                cudaEventDestroy(r.converted[i]);
+                cudaEventDestroy(r.done[i]);
+            }
+        }
+        if (lane.s_h2d) cudaStreamDestroy(lane.s_h2d);
+        if (lane.s_comp) cudaStreamDestroy(lane.s_comp);
+        if (lane.s_d2h) cudaStreamDestroy(lane.s_d2h);
+        if (lane.s_resident) cudaStreamDestroy(lane.s_resident); // its kernel has left: asked to, and the device was synchronised
+        if (lane.mailbox) cudaFreeHost(lane.mailbox);
+        if (lane.flag) cudaFreeHost(lane.flag);
+        if (lane.d_arrivals) cudaFree(lane.d_arrivals);
+    }
     if (ctx->d_stats) cudaFree(ctx->d_stats);
     if (ctx->h_stats) cudaFreeHost(ctx->h_stats);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1237,6 +1443,10 @@ int sxgpu_bank_destroy(sxgpu_bank *bank)
     if (!bank)
         return SXGPU_ERR_INVALID;
     cudaSetDevice(bank->ctx->device);
+    for (HostLane &lane : bank->ctx->lanes) { // a resident converter would hold the device-wide sync up
+        std::lock_guard<std::mutex> lock(lane.mutex);
+        resident_stop(bank->ctx, lane);
+    }
     cudaDeviceSynchronize();
     cudaFree(bank->arena);
     bank->ctx->live_banks--;
@@ -1640,7 +1850,7 @@ int sxgpu_set_option(sxgpu_ctx *ctx, const char *key, int64_t value)
         return ctx->invalid("option values are non-negative");
     if (slot == &ctx->numa_node)
         return ctx->invalid("numa_node is read-only");
-    std::lock_guard<std::mutex> lock(ctx->host_mutex);
+    std::scoped_lock lock(ctx->lanes[0].mutex, ctx->lanes[1].mutex);
     *slot = value;
     return SXGPU_OK;
 }
@@ -1667,6 +1877,7 @@ int sxgpu_get_counter(sxgpu_ctx *ctx, const char *key, uint64_t *value)
     else if (!std::strcmp(key, "d2h_bytes")) *value = ctx->d2h_bytes;
     else if (!std::strcmp(key, "resident_launches")) *value = ctx->resident_launches;
     else if (!std::strcmp(key, "resident_calls")) *value = ctx->resident_calls;
+    else if (!std::strcmp(key, "flagged_calls")) *value = ctx->flagged_calls;
     else return ctx->invalid("unknown counter");
     return SXGPU_OK;
 }

@@ -1,0 +1,152 @@
+"""ctypes view of the flat sxh_* harness over a SoapySDR "driver=sx" device (csrc/host/harness_capi.cpp).
+
+The harness talks only to the public SoapySDR::Device interface, so the same binding drives the
+product module (lib/libsxsoapy.so: SoapySXB200, CUDA converters) and -- when handed its path --
+any other build of the same harness.  bench.py uses it to time readStream/writeStream; nothing
+here converts a sample.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+from . import _build
+
+RX, TX = 1, 0            # SOAPY_SDR_RX / SOAPY_SDR_TX
+HAS_TIME = 1 << 2
+THREW = -1000
+
+_P, _S, _LL = C.c_void_p, C.c_size_t, C.c_longlong
+
+SIGNATURES = {
+    "sxh_last_error": (C.c_char_p, []),
+    "sxh_set_log_level": (None, [C.c_int]),
+    "sxh_make": (C.c_int, [C.c_char_p, C.POINTER(_P)]),
+    "sxh_unmake": (C.c_int, [_P]),
+    "sxh_pcm": (_P, [_P, C.c_int]),
+    "sxh_setup_stream": (_P, [_P, C.c_int, C.c_char_p, C.c_char_p]),
+    "sxh_close_stream": (C.c_int, [_P, _P]),
+    "sxh_activate": (C.c_int, [_P, _P, C.c_int, _LL, _S]),
+    "sxh_deactivate": (C.c_int, [_P, _P, C.c_int, _LL]),
+    "sxh_read": (C.c_int, [_P, _P, _P, _S, C.POINTER(C.c_int), C.POINTER(_LL), C.c_long]),
+    "sxh_write": (C.c_int, [_P, _P, _P, _S, C.POINTER(C.c_int), _LL, C.c_long]),
+    "sxh_set_sample_rate": (C.c_int, [_P, C.c_int, C.c_double]),
+    "sxh_bench_pairs": (C.c_int, [_P, _P, _P, _P, _S, C.c_int, _LL, C.POINTER(C.c_double), _P]),
+    "sxh_bench_reads": (C.c_int, [_P, _P, _P, _S, C.c_int, C.POINTER(C.c_double)]),
+    "sxh_bench_writes": (C.c_int, [_P, _P, _P, _S, C.c_int, C.POINTER(C.c_double)]),
+    "sx_alsa_set_capture_table": (None, [_P, _P, _S]),
+    "sx_alsa_set_capture_seed": (None, [_P, C.c_uint64]),
+    "sx_alsa_set_sink_limit": (None, [_P, _S]),
+    "sx_alsa_sink_read": (_S, [_P, C.c_int64, _S, _P]),
+}
+
+
+class PluginError(RuntimeError):
+    pass
+
+
+class Harness:
+    """One loaded build of the harness (default: the product module)."""
+
+    def __init__(self, path: str | Path | None = None):
+        path = Path(path) if path else _build.build_soapy_module()
+        if not path.exists():
+            raise RuntimeError(f"{path} is missing: build it with __graft_entry__.build()")
+        self.path = path
+        self.lib = lib = C.CDLL(str(path))
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        lib.sxh_set_log_level(2)  # keep the driver's per-call log lines out of the way
+
+    def error(self) -> str:
+        return self.lib.sxh_last_error().decode()
+
+    def device(self, args: str = "driver=sx") -> "Device":
+        return Device(self, args)
+
+
+class Device:
+    def __init__(self, h: Harness, args: str):
+        self.h, self.lib = h, h.lib
+        p = _P()
+        if self.lib.sxh_make(args.encode(), C.byref(p)) != 0:
+            raise PluginError(h.error())
+        self.p = p
+        self.capture = self.lib.sxh_pcm(p, 1)
+        self.playback = self.lib.sxh_pcm(p, 0)
+
+    def close(self):
+        if self.p:
+            self.lib.sxh_unmake(self.p)
+            self.p = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _ck(self, rc, what):
+        if rc == THREW:
+            raise PluginError(f"{what}: {self.h.error()}")
+        return rc
+
+    def set_rate(self, rate: float):
+        self._ck(self.lib.sxh_set_sample_rate(self.p, RX, rate), "setSampleRate")
+        self._ck(self.lib.sxh_set_sample_rate(self.p, TX, rate), "setSampleRate")
+
+    def setup(self, direction: int, fmt: str = "CF32", args: str = ""):
+        s = self.lib.sxh_setup_stream(self.p, direction, fmt.encode(), args.encode())
+        if not s:
+            raise PluginError(self.h.error())
+        return s
+
+    def activate(self, stream):
+        return self._ck(self.lib.sxh_activate(self.p, stream, 0, 0, 0), "activateStream")
+
+    def deactivate(self, stream):
+        return self._ck(self.lib.sxh_deactivate(self.p, stream, 0, 0), "deactivateStream")
+
+    def read(self, stream, addr: int, n: int, timeout_us: int = 1000000):
+        flags, t = C.c_int(0), _LL(0)
+        ret = self._ck(self.lib.sxh_read(self.p, stream, addr, n, C.byref(flags), C.byref(t), timeout_us), "readStream")
+        return ret, flags.value, t.value
+
+    def write(self, stream, addr: int, n: int, flags: int = 0, time_ns: int = 0, timeout_us: int = 1000000):
+        f = C.c_int(flags)
+        return self._ck(self.lib.sxh_write(self.p, stream, addr, n, C.byref(f), time_ns, timeout_us), "writeStream")
+
+    # ---- the ALSA stand-in behind the device -----------------------------------------------------
+    def capture_table(self, addr: int, nframes: int):
+        """Capture frame k = table[k % nframes] (the table is copied)."""
+        self.lib.sx_alsa_set_capture_table(self.capture, addr, nframes)
+
+    def sink_limit(self, frames: int):
+        self.lib.sx_alsa_set_sink_limit(self.playback, frames)
+
+    def sink(self, position: int, nframes: int, out_addr: int):
+        self.lib.sx_alsa_sink_read(self.playback, position, nframes, out_addr)
+
+    # ---- native timing loops (no interpreter between the calls) ----------------------------------
+    def bench_pairs(self, rx, tx, addr: int, n: int, iters: int, latency_ns: int, per_iter_addr: int = 0) -> float:
+        sec = C.c_double(0)
+        rc = self._ck(self.lib.sxh_bench_pairs(self.p, rx, tx, addr, n, iters, latency_ns, C.byref(sec), per_iter_addr),
+                      "bench_pairs")
+        if rc != 0:
+            raise PluginError(f"bench_pairs: a stream call returned {rc}")
+        return sec.value
+
+    def bench_reads(self, rx, addr: int, n: int, iters: int) -> float:
+        sec = C.c_double(0)
+        rc = self._ck(self.lib.sxh_bench_reads(self.p, rx, addr, n, iters, C.byref(sec)), "bench_reads")
+        if rc != 0:
+            raise PluginError(f"bench_reads: readStream returned {rc}")
+        return sec.value
+
+    def bench_writes(self, tx, addr: int, n: int, iters: int) -> float:
+        sec = C.c_double(0)
+        rc = self._ck(self.lib.sxh_bench_writes(self.p, tx, addr, n, iters, C.byref(sec)), "bench_writes")
+        if rc != 0:
+            raise PluginError(f"bench_writes: writeStream returned {rc}")
+        return sec.value
