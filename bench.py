@@ -51,16 +51,107 @@ def env_int(name, default):
 
 
 # ---------------------------------------------------------------------------------------------
-# CPU arm: the reference's own converters on host cores.  This is the only place bench.py
-# touches oracle/.
+# The plugin call: readStream + timed writeStream through the flat sxh_* harness.  The same
+# function drives the product module (SoapySXB200, CUDA converters) and -- for the CPU arm, the
+# only place bench.py touches oracle/ -- the unmodified reference driver built in oracle/_ref.
 # ---------------------------------------------------------------------------------------------
+RATE = 600000.0            # the SX1255's highest sample rate (SoapySX.cpp:196-206)
+RING = 65536               # frames in the I2S DMA ring (SoapySX.cpp:464)
+REF_PLUGIN = ROOT / "oracle" / "_ref" / "libsx_ref.so"
+
+
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def capture_table(seed):
+    """One ring of synthetic I2S frames: the stand-in's capture signal is this table, repeated
+    (snd_pcm_readi is then one copy out of the ring, as it is on a sound card)."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    return rng.integers(-2**31, 2**31, size=2 * RING, dtype=np.int64).astype(np.int32)
+
+
+class PluginStreams:
+    """D independent driver=sx devices, one caller thread each; a step is readStream(n) followed by
+    writeStream(n, HAS_TIME, that block's time + 3n frames) on every device (the repeater
+    iteration of example/linear_repeater.py:50-71 with an identity process()), n = frames / D.
+    `kind`: "pageable" (a numpy array, what the reference's callers pass), "pin" (the same with the
+    stream argument pin=1) or "pinned" (memory from sxgpu_malloc_host; product only)."""
+
+    def __init__(self, harness, frames, nstreams, kind="pageable", dev_args="", ctx=None, seed=SEED):
+        import numpy as np
+        from sxxcvr_b200 import plugin
+        self.plugin, self.h, self.kind, self.ctx = plugin, harness, kind, ctx
+        self.n = max(1, frames // nstreams)
+        self.devs, self.rx, self.tx, self.bufs, self.addrs, self.pinned = [], [], [], [], [], []
+        table = capture_table(seed)
+        period = min(self.n, RING)
+        pin = ", pin=1" if kind == "pin" else ""
+        for k in range(nstreams):
+            d = harness.device("driver=sx" + dev_args)
+            d.set_rate(RATE)
+            rx = d.setup(plugin.RX, args=f"period={period}{pin}")
+            tx = d.setup(plugin.TX, args=f"period={period}{pin}")
+            d.activate(rx), d.activate(tx)
+            d.sink_limit(0)                         # the played frames are not kept: only timing matters
+            d.capture_table(table.ctypes.data, RING)
+            if kind == "pinned":
+                addr = ctx.malloc_host(8 * self.n)
+                self.pinned.append(addr)
+                buf = None
+            else:
+                buf = np.ones(2 * self.n, np.float32)   # written once, so every page exists
+                addr = buf.ctypes.data
+            self.devs.append(d), self.rx.append(rx), self.tx.append(tx), self.bufs.append(buf), self.addrs.append(addr)
+        self.lat_ns = int(round(3 * self.n * 1e9 / RATE))
+
+    def run(self, iters, warmup=1):
+        """Seconds per step: every stream thread times its own `iters` pairs natively; the step time
+        is the slowest thread's."""
+        secs = [0.0] * len(self.devs)
+        gate = threading.Barrier(len(self.devs))
+
+        def work(k):
+            d = self.devs[k]
+            if warmup:
+                d.bench_pairs(self.rx[k], self.tx[k], self.addrs[k], self.n, warmup, self.lat_ns)
+            gate.wait()
+            secs[k] = d.bench_pairs(self.rx[k], self.tx[k], self.addrs[k], self.n, iters, self.lat_ns)
+
+        if len(self.devs) == 1:
+            work(0)
+        else:
+            ts = [threading.Thread(target=work, args=(k,)) for k in range(len(self.devs))]
+            for t in ts:
+                t.start()
+            for t in ts:
+                t.join()
+        return max(secs) / iters
+
+    def close(self):
+        for d in self.devs:
+            d.close()
+        for addr in self.pinned:
+            self.ctx.free_host(addr)
+        self.devs, self.bufs = [], []
+
+
+def reference_harness():
+    """The unmodified reference driver (oracle/_ref), or None where it was never built."""
+    from sxxcvr_b200 import plugin
+    return plugin.Harness(REF_PLUGIN) if REF_PLUGIN.exists() else None
+
+
 def load_cpu_converters():
-    """(kind, rx, tx): oracle/_ref (the unmodified reference, kind 'reference') if it was built,
-    else the plain-C restatement (kind 'port')."""
+    """(kind, rx, tx) bare converters: oracle/_ref (the unmodified reference, kind 'reference') if it
+    was built, else the plain-C restatement (kind 'port')."""
     P, S = C.c_void_p, C.c_size_t
-    ref = ROOT / "oracle" / "_ref" / "libsx_ref.so"
-    if ref.exists():
-        lib = C.CDLL(str(ref))
+    if REF_PLUGIN.exists():
+        lib = C.CDLL(str(REF_PLUGIN))
         rx, tx, kind = lib.sxref_convert_rx_buffer, lib.sxref_convert_tx_buffer, "reference"
     else:
         port = ROOT / "oracle" / "libsx_oracle.so"
@@ -73,9 +164,9 @@ def load_cpu_converters():
     return kind, rx, tx
 
 
-class CpuArm:
-    """Splits one RX block and one TX block across `threads` host threads (ctypes releases the
-    GIL), each thread converting a contiguous slice with the reference's scalar loop."""
+class CpuConverters:
+    """The bare converter loops split across host threads (ctypes releases the GIL): used when the
+    reference driver itself could not be built, and as an extra row beside the plugin figure."""
 
     def __init__(self, frames: int, threads: int):
         import numpy as np
@@ -113,29 +204,37 @@ class CpuArm:
         return (time.perf_counter() - t0) / steps
 
 
-def host_threads() -> int:
+def cpu_plugin_arm(frames, threads, steps, warmup):
+    """The reference driver's readStream + writeStream on `threads` host threads (one device per
+    thread: a SoapySX device converts on its caller's thread, so this is how it uses them all),
+    `frames` per direction per step in total.  Returns (kind, seconds per step, description)."""
+    h = reference_harness()
+    if h is None:
+        arm = CpuConverters(frames, threads)
+        return arm.kind, arm.time_steps(steps, warmup), "bare converter loops (the reference driver was not built here)"
+    streams = PluginStreams(h, frames, threads)
     try:
-        return len(os.sched_getaffinity(0))
-    except AttributeError:
-        return os.cpu_count() or 1
+        sec = streams.run(steps, warmup)
+    finally:
+        streams.close()
+    return "reference", sec, (f"unmodified SoapySX readStream + timed writeStream over the ALSA stand-in, {threads} device(s) on "
+                              f"{threads} thread(s), {streams.n} frames per call, pageable caller buffers")
 
 
 def run_reference_arm(args, rank: int):
     if rank != 0:
         return
     threads = host_threads()
-    frames = 1 << args.cpu_log2_frames
-    arm = CpuArm(frames, threads)
-    sec = arm.time_steps(args.steps, args.warmup)
+    frames = 1 << args.log2_frames
+    kind, sec, what = cpu_plugin_arm(frames, threads, args.steps, args.warmup)
     value = 2 * frames / sec / 1e6
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "s32<->f32", "data": "synthetic",
         "config": workload_config(args, per_gpu_frames=frames),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": arm.kind,
-                         "sample": f"RX 2^{args.cpu_log2_frames} + TX 2^{args.cpu_log2_frames} frames per step, "
-                                   f"split over {threads} host threads"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
+                         "sample": f"RX 2^{args.log2_frames} + TX 2^{args.log2_frames} frames per step: {what}"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -356,14 +455,19 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
     roof_rx = roof(rx_ms, "bulk_convert_kernel<RxCf32>")
     roof_tx = roof(tx_ms, "bulk_convert_kernel<TxCf32>")
     dominant = roof_tx if sum(tx_ms) >= sum(rx_ms) else roof_rx
-    # DRAM bytes per launch from the committed `ncu --set full` capture -- only valid for the
-    # launch size it was captured at.
-    traffic_file = ROOT / "profiles" / "r01_traffic.json"
-    if traffic_file.exists():
+    # DRAM bytes per launch come from an `ncu --set full` capture, which cannot run inside a timed
+    # bench: the committed capture of this same launch (same kernel, same frames per launch) is
+    # quoted, with its file named, and only when its launch size matches this run's.
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        traffic_file = ROOT / "profiles" / name
+        if not traffic_file.exists():
+            continue
         try:
             t = json.loads(traffic_file.read_text())
             if t.get("frames_per_launch") == frames:
                 roof_rx["traffic"], roof_tx["traffic"] = t.get("rx_bytes_per_launch"), t.get("tx_bytes_per_launch")
+                roof_rx["traffic_source"] = roof_tx["traffic_source"] = f"profiles/{name} (ncu --set full, one launch)"
+                break
         except ValueError:
             pass
 
@@ -372,11 +476,109 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
     stats = ctx.stats_words(i2s_out.data_ptr(), 2 * frames, 0, st)
     checks = [list(c) for c in sharding.gather_stats(stats, device="cuda")]
 
-    # ---- end to end: host buffers through the C ABI, PCIe copies inside the timed region -------
-    e2e_frames = min(1 << args.e2e_log2_frames, frames)   # its inputs are a prefix of the device-resident ones
-    # Pinned host buffers from the library's own allocator: it places them on the GPU's NUMA
-    # node (option numa_local_alloc), which is what lets N ranks use N PCIe links at once.
-    ctx.set_option("numa_local_alloc", args.numa_local)
+    # ---- sustained figure: the same step for at least --min-seconds ----------------------------
+    sustained = None
+    if args.min_seconds > 0:
+        per_step = max(step_ms, 1e-3) * 1e-3
+        nsus = max(args.steps, int(args.min_seconds / per_step) + 1)
+        sampler2 = ClockSampler(local_rank, bus)
+        barrier()
+        sampler2.start()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(side)
+        for _ in range(nsus):
+            rx()
+            tx()
+        s1.record(side)
+        barrier()
+        sus_ms = max_over_ranks(s0.elapsed_time(s1) / nsus)
+        sustained = {"value": world * 2 * frames / (sus_ms * 1e-3) / 1e6, "unit": UNIT, "steps": nsus,
+                     "seconds": sus_ms * nsus * 1e-3, "ms_per_step": sus_ms,
+                     "hbm_gbs_per_gpu": 2 * frames * BYTES_PER_FRAME / (sus_ms * 1e-3) / 1e9,
+                     "clocks": sampler2.stop()}
+
+    # ---- raw link: copy engines only, both directions loaded, every rank at once ----------------
+    # The ceiling for anything that takes host buffers: 8 B/frame must cross each way.
+    link_bytes = 256 << 20
+    h_up = torch.empty(link_bytes, dtype=torch.uint8, pin_memory=True)
+    h_down = torch.empty(link_bytes, dtype=torch.uint8, pin_memory=True)
+    d_up = torch.empty(link_bytes, dtype=torch.uint8, device="cuda")
+    d_down = torch.empty(link_bytes, dtype=torch.uint8, device="cuda")
+    s_up, s_down = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def link_pass(up: bool, down: bool, reps=4):
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            if up:
+                with torch.cuda.stream(s_up):
+                    d_up.copy_(h_up, non_blocking=True)
+            if down:
+                with torch.cuda.stream(s_down):
+                    h_down.copy_(d_down, non_blocking=True)
+        s_up.synchronize(), s_down.synchronize()
+        return reps * link_bytes / (time.perf_counter() - t0) / 1e9
+
+    link_pass(True, True, 1)
+    link = {"h2d_alone_gbs": all_ranks(link_pass(True, False)), "d2h_alone_gbs": all_ranks(link_pass(False, True)),
+            "both_each_way_gbs": all_ranks(link_pass(True, True))}
+    del h_up, h_down, d_up, d_down
+
+    # ---- end to end: the plugin call.  SoapySXB200::readStream + timed writeStream on host buffers,
+    # the ALSA stand-in underneath, both PCIe copies and the stand-in's own copies inside the timed
+    # region.  D devices on D caller threads share this rank's GPU, as D SX1255 front-ends would. ---
+    from sxxcvr_b200 import plugin
+    product = plugin.Harness()
+    threads_here = max(1, host_threads() // max(1, env_int("LOCAL_WORLD_SIZE", world)))
+    e2e_streams = args.e2e_streams or max(1, min(8, threads_here // 2))
+    e2e_frames = min(1 << args.e2e_log2_frames, frames)
+    bounce = max(1, threads_here // e2e_streams - 1)
+    dev_args = f", gpu={local_rank}, sxgpu.bounce_threads={bounce}"
+    streams = PluginStreams(product, e2e_frames, e2e_streams, args.e2e_buffers, dev_args, ctx, SEED + rank)
+    try:
+        barrier()
+        e2e_sec = streams.run(args.steps, max(args.warmup, 3))
+        barrier()
+        e2e_launches = sum(d.counter("launches") for d in streams.devs)
+    finally:
+        streams.close()
+    e2e_per_rank = [2 * e2e_frames / t / 1e6 for t in all_ranks(e2e_sec)]
+    e2e_sec = max_over_ranks(e2e_sec)
+    e2e_value = world * 2 * e2e_frames / e2e_sec / 1e6
+    # bytes that crossed the link each way per second on this rank, against what the link carries
+    e2e_link_gbs = [v * 1e6 * 8 / 1e9 for v in e2e_per_rank]
+    frac_of_link = [a / b if b else None for a, b in zip(e2e_link_gbs, link["both_each_way_gbs"])]
+
+    # ---- one stream at a time: frames per call x caller buffer, product beside the reference -----
+    rows = []
+    if rank == 0 and not args.no_rows:
+        ref = reference_harness() if world == 1 else None
+        sizes = [(256, 4000), (4096, 2000), (65536, 200), (1 << 20, 20), (min(frames, 1 << 27), 2)]
+        for n, iters in sizes:
+            row = {"frames_per_call": n}
+
+            def pair_us(h, kind, extra=""):
+                st_ = PluginStreams(h, n, 1, kind, extra, ctx, SEED)
+                try:
+                    return st_.run(iters, 1 if n > (1 << 22) else 5) * 1e6
+                finally:
+                    st_.close()
+
+            one = f", gpu={local_rank}"
+            row["product_pageable_us"] = pair_us(product, "pageable", one)
+            row["product_pin1_us"] = pair_us(product, "pin", one)
+            row["product_library_pinned_us"] = pair_us(product, "pinned", one)
+            if n <= 4096:
+                row["product_lowlatency_us"] = pair_us(product, "pageable", one + ", lowlatency=1")
+            if ref is not None:
+                row["reference_us"] = pair_us(ref, "pageable")
+            for k in list(row):
+                if k.endswith("_us"):
+                    row[k.replace("_us", "_msps")] = round(2 * n / row[k], 1)
+                    row[k] = round(row[k], 2)
+            rows.append(row)
+
+    # ---- small-block latency through the C ABI (period-sized calls, the reference's native regime)
     pinned = []
 
     def pinned_words(nwords, dtype):
@@ -385,70 +587,51 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
         pinned.append(addr)
         return torch.frombuffer((ctypes.c_char * (4 * nwords)).from_address(addr), dtype=dtype)
 
-    h_i2s = pinned_words(2 * e2e_frames, torch.int32)
-    h_cf_out = pinned_words(2 * e2e_frames, torch.float32)
-    h_cf_in = pinned_words(2 * e2e_frames, torch.float32)
-    h_i2s_out = pinned_words(2 * e2e_frames, torch.int32)
-    h_i2s.copy_(i2s_in[: 2 * e2e_frames].cpu())
-    h_cf_in.copy_(cf[: 2 * e2e_frames].cpu())
-
-    def e2e_step():
-        ctx.convert_rx_buffer_host(h_i2s.data_ptr(), 0, h_cf_out.data_ptr(), 0, e2e_frames)
-        ctx.convert_tx_buffer_host(h_cf_in.data_ptr(), 0, h_i2s_out.data_ptr(), 0, e2e_frames, THR2)
-        return int(h_i2s_out[-1])  # the step's result is read on the host
-
-    for _ in range(max(args.warmup, 3)):
-        e2e_step()
-    barrier()
-    l0 = ctx.counter("launches")
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
-    torch.cuda.synchronize()
-    e2e_sec = (time.perf_counter() - t0) / args.steps
-    barrier()
-    e2e_launches = ctx.counter("launches") - l0
-    e2e_per_rank = [2 * e2e_frames / t / 1e6 for t in all_ranks(e2e_sec)]
-    numa_nodes = [int(v) for v in all_ranks(float(ctx.get_option("numa_node")))]
-    e2e_sec = max_over_ranks(e2e_sec)
-    e2e_value = world * 2 * e2e_frames / e2e_sec / 1e6
-
-    # ---- small-block latency rows (period-sized calls, the reference's native regime) ----------
+    h_i2s = pinned_words(2 * 65536, torch.int32)
+    h_cf_out = pinned_words(2 * 65536, torch.float32)
+    h_i2s.copy_(i2s_in[: 2 * 65536].cpu())
     small = {}
-    for nf in (256, 4096, 65536):
-        for _ in range(5):
-            ctx.convert_rx_buffer_host(h_i2s.data_ptr(), 0, h_cf_out.data_ptr(), 0, nf)
-        reps = 200
-        t0 = time.perf_counter()
-        for _ in range(reps):
-            ctx.convert_rx_buffer_host(h_i2s.data_ptr(), 0, h_cf_out.data_ptr(), 0, nf)
-        small[f"rx_host_{nf}_frames_us_per_call"] = (time.perf_counter() - t0) / reps * 1e6
-    # the same period-sized call through the opt-in resident converter (doorbell in pinned memory)
+    for mode, label in ((2, "flag"), (1, "stream_sync")):
+        ctx.set_option("small_mode", mode)
+        for nf in (256, 4096, 65536):
+            for _ in range(5):
+                ctx.convert_rx_buffer_host(h_i2s.data_ptr(), 0, h_cf_out.data_ptr(), 0, nf)
+            reps = 300
+            a_, b_ = h_i2s.data_ptr(), h_cf_out.data_ptr()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                ctx.convert_rx_buffer_host(a_, 0, b_, 0, nf)
+            small[f"rx_host_{nf}_frames_us_per_call_{label}"] = (time.perf_counter() - t0) / reps * 1e6
+    ctx.set_option("small_mode", 0)
     ctx.set_option("resident_max_frames", 4096)
     for nf in (256, 4096):
         for _ in range(5):
             ctx.convert_rx_buffer_host(h_i2s.data_ptr(), 0, h_cf_out.data_ptr(), 0, nf)
         reps = 500
+        a_, b_ = h_i2s.data_ptr(), h_cf_out.data_ptr()
         t0 = time.perf_counter()
         for _ in range(reps):
-            ctx.convert_rx_buffer_host(h_i2s.data_ptr(), 0, h_cf_out.data_ptr(), 0, nf)
+            ctx.convert_rx_buffer_host(a_, 0, b_, 0, nf)
         small[f"rx_host_{nf}_frames_us_per_call_resident"] = (time.perf_counter() - t0) / reps * 1e6
     ctx.set_option("resident_max_frames", 0)
 
-    # ---- CPU baseline beside it (rank 0, N=1 only) ---------------------------------------------
+    # ---- CPU baseline beside it (rank 0, N=1 only): the reference driver on this box's cores ------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = host_threads()
-        arm_all = CpuArm(1 << args.cpu_log2_frames, threads)
-        sec_all = arm_all.time_steps(3, 1)
-        arm_one = CpuArm(1 << (args.cpu_log2_frames - 2), 1)
-        sec_one = arm_one.time_steps(2, 1)
-        cpu = {"value": 2 * arm_all.frames / sec_all / 1e6, "unit": UNIT, "cores": threads, "kind": arm_all.kind,
-               "sample": f"3 steps of RX 2^{args.cpu_log2_frames} + TX 2^{args.cpu_log2_frames} frames over "
-                         f"{threads} host threads",
-               "single_thread": {"value": 2 * arm_one.frames / sec_one / 1e6, "cores": 1,
-                                 "sample": f"2 steps of RX+TX 2^{args.cpu_log2_frames - 2} frames, one thread "
-                                           f"(the reference converts on the calling thread)"}}
+        cpu_frames = 1 << args.cpu_log2_frames
+        kind, sec_all, what = cpu_plugin_arm(cpu_frames, threads, 3, 1)
+        _, sec_one, what_one = cpu_plugin_arm(cpu_frames >> 2, 1, 2, 1)
+        conv = CpuConverters(cpu_frames, threads)
+        sec_conv = conv.time_steps(3, 1)
+        cpu = {"value": 2 * cpu_frames / sec_all / 1e6, "unit": UNIT, "cores": threads, "kind": kind,
+               "sample": f"3 steps of RX 2^{args.cpu_log2_frames} + TX 2^{args.cpu_log2_frames} frames: {what}",
+               "single_thread": {"value": 2 * (cpu_frames >> 2) / sec_one / 1e6, "cores": 1,
+                                 "sample": f"2 steps of RX+TX 2^{args.cpu_log2_frames - 2} frames: {what_one} "
+                                           f"(how the reference runs: it converts on the calling thread)"},
+               "bare_converters": {"value": 2 * cpu_frames / sec_conv / 1e6, "cores": threads, "kind": conv.kind,
+                                   "sample": "convert_rx_buffer + convert_tx_buffer alone, no stream calls, "
+                                             f"2^{args.cpu_log2_frames} frames split over {threads} threads"}}
 
     if rank == 0:
         info = ctx.info()
@@ -457,24 +640,32 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
             "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "s32<->f32", "data": "synthetic",
             "config": workload_config(args, frames),
-            "roofline": dominant, "roofline_rx": roof_rx, "roofline_tx": roof_tx,
+            "roofline": dominant, "roofline_rx": roof_rx, "roofline_tx": roof_tx, "sustained": sustained,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * 8 * e2e_frames,
                     "d2h_bytes_per_step": 2 * 8 * e2e_frames, "frames_per_block": e2e_frames,
                     "ms_per_step": e2e_sec * 1e3, "gpu_launches": e2e_launches,
-                    "api": "sxgpu_convert_rx_buffer_host + sxgpu_convert_tx_buffer_host, pinned host buffers",
-                    "bound": "PCIe: 16 B/frame cross the link each way",
+                    "api": "SoapySXB200::readStream + writeStream(HAS_TIME) through the sxh_* harness "
+                           "(csrc/host/harness_capi.cpp), ALSA stand-in underneath",
+                    "caller_buffers": {"pageable": "pageable numpy arrays, default stream arguments",
+                                       "pin": "pageable numpy arrays, stream argument pin=1",
+                                       "pinned": "sxgpu_malloc_host memory"}[args.e2e_buffers],
+                    "streams_per_gpu": e2e_streams, "frames_per_call": e2e_frames // e2e_streams,
+                    "bounce_threads_per_stream": bounce,
+                    "bound": "PCIe: 8 B/frame cross the link each way per conversion",
                     "per_rank": [round(v, 1) for v in e2e_per_rank],
-                    "host_numa": {"gpu_numa_node_per_rank": numa_nodes,
-                                  "pinned_memory_on_gpu_node": bool(args.numa_local)}},
+                    "raw_link_gbs_per_rank": {k: [round(x, 2) for x in v] for k, v in link.items()},
+                    "link_gbs_each_way_per_rank": [round(v, 2) for v in e2e_link_gbs],
+                    "frac_of_link": [round(v, 3) if v is not None else None for v in frac_of_link],
+                    "plugin_rows": rows},
             "gpu_launches": launches, "clocks": clocks, "cpu_baseline": cpu, "small_blocks": small,
             "checksums": {"fields": list(sharding.STATS_FIELDS), "per_rank": checks,
                           "combined": list(sharding.combine_stats(checks)),
                           "gathered_with": "nccl all_gather" if world > 1 else "local"},
-            "device": info.name.decode(), "sm_count": info.sm_count,
+            "device": info.name.decode(), "sm_count": info.sm_count, "host_threads": host_threads(),
         }
         emit(json.dumps(line))
 
-    del h_i2s, h_cf_out, h_cf_in, h_i2s_out
+    del h_i2s, h_cf_out
     for addr in pinned:
         ctx.free_host(addr)
     ctx.close()
@@ -639,11 +830,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log2-frames", type=int, default=27, help="frames per block per GPU (2^27 = 1 GiB in)")
-    ap.add_argument("--e2e-log2-frames", type=int, default=27, help="frames per block of the host-buffer leg (same as --log2-frames by default)")
-    ap.add_argument("--cpu-log2-frames", type=int, default=26)
+    ap.add_argument("--e2e-log2-frames", type=int, default=27, help="frames per block of the plugin leg (capped at --log2-frames)")
+    ap.add_argument("--e2e-streams", type=int, default=0, help="devices (caller threads) per GPU in the plugin leg; 0 = auto")
+    ap.add_argument("--e2e-buffers", default="pageable", choices=["pageable", "pin", "pinned"],
+                    help="caller buffers of the plugin leg: pageable numpy (default, what the reference's callers pass), "
+                         "the same with pin=1, or sxgpu_malloc_host memory")
+    ap.add_argument("--min-seconds", type=float, default=1.0,
+                    help="also report the device-resident figure sustained over at least this long (0 = skip)")
+    ap.add_argument("--no-rows", action="store_true", help="skip the one-stream frames-per-call x buffer-kind table")
+    ap.add_argument("--cpu-log2-frames", type=int, default=27, help="frames per step of the cpu_baseline sample inside the GPU arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--numa-local", type=int, default=1, choices=[0, 1],
-                    help="place the host-buffer leg's pinned memory on the GPU's NUMA node (default 1)")
     ap.add_argument("--workload", default="blocks", choices=["blocks", "bank"],
                     help="blocks: the judged RX+TX block workload (default); bank: BASELINE config 4")
     ap.add_argument("--streams", type=int, default=65536, help="--workload bank: stream pairs per GPU")

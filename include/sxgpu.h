@@ -174,6 +174,26 @@ int sxgpu_bank_write(sxgpu_bank *bank, const void *d_cf32, int flags, const long
  * each stream's three stages run back to back on one warp, so the intermediate reads are served
  * from L2 and only the writes reach HBM. */
 int sxgpu_bank_repeat(sxgpu_bank *bank, void *d_cf32, long long rx_time_offset_ns, sxgpu_stream stream);
+/* Frames from outside instead of the synthetic capture: copy one period of I2S frames for each
+ * of `nstreams` consecutive streams, i2s[stream - first_stream][period], into their capture
+ * slots.  `i2s` may be pinned or pageable host memory or device memory; the copy is ordered on
+ * `stream`.  From the first call on (nstreams == 0 just switches the mode) the bank no longer
+ * synthesises: sxgpu_bank_read / sxgpu_bank_repeat convert whatever the slots hold, with the
+ * same bookkeeping.  This is the entry for frames produced by real front-ends (or by N host-side
+ * ALSA stand-ins): what snd_pcm_readi delivers in SoapySX.cpp:948, for many streams at once. */
+int sxgpu_bank_ingest(sxgpu_bank *bank, uint32_t first_stream, uint32_t nstreams, const void *i2s,
+                      sxgpu_stream stream);
+/* The other end: for each of `nstreams` consecutive streams copy the last `nframes` frames it
+ * wrote (the frames ending at its TX counter; silence before frame 0) out of its playback ring
+ * to i2s[stream - first_stream][nframes] -- what snd_pcm_writei would be handed in
+ * SoapySX.cpp:1093.  `i2s`: device memory, or pinned host memory (written across PCIe by the
+ * kernel itself).  Asynchronous on `stream`. */
+int sxgpu_bank_drain(sxgpu_bank *bank, uint32_t first_stream, uint32_t nstreams, size_t nframes, void *i2s,
+                     sxgpu_stream stream);
+/* For include/sx_hook.cuh: the bank's device-side view (struct sx::BankState), so that a fused
+ * iteration with a user functor compiled into it can be launched from the caller's own
+ * translation unit.  out_bytes must be sizeof(sx::BankState). */
+int sxgpu_bank_device_view(sxgpu_bank *bank, void *out, size_t out_bytes, int *external_capture);
 /* Per-stream results of the last read / write and the counters, copied to host arrays of
  * nstreams elements (any pointer may be NULL).  These synchronise with `stream`. */
 int sxgpu_bank_last_read(sxgpu_bank *bank, int32_t *h_ret, int32_t *h_flags, int64_t *h_time_ns,
@@ -260,11 +280,25 @@ int sxgpu_stream_sync(sxgpu_ctx *ctx, sxgpu_stream stream); /* NULL = context st
  *   "resident_max_frames"       0 = off (default).  N > 0: synchronous CF32 calls of up to N
  *                               frames on host buffers are served by a resident single-CTA
  *                               kernel through a doorbell in pinned memory instead of a kernel
- *                               launch + stream sync each (period-sized blocks, SoapySX.cpp:451);
- *                               the kernel leaves by itself after 2 ms without work
+ *                               launch each (period-sized blocks, SoapySX.cpp:451); the kernel
+ *                               leaves after 2 ms without work, after 20 ms in any case, and at
+ *                               once when the library is about to synchronise the device
  *   "bank_repeat_variant"       schedule of sxgpu_bank_repeat: 0 = auto (by stream count),
- *                               K in {1, 2, 4, 8} = a warp takes K streams per round,
- *                               100 = a CTA takes 32 streams per round
+ *                               K in {1, 2, 4, 8} = a warp takes K streams per round, stage by
+ *                               stage through memory; 100 = a CTA takes 32 streams per round;
+ *                               200 + K, K in {1, 2, 4} = a warp takes K streams per round and
+ *                               keeps every intermediate in registers (stores only)
+ *   "batch_variant"             blocks above 4096 frames in sxgpu_convert_*_batch: 0 = auto
+ *                               (tiles of all blocks on the bulk-async schedule), 1 = slices of
+ *                               CTAs on vector accesses
+ *   "loopback_variant"          sxgpu_convert_loopback: 0 = auto (bulk-async), 1 = vector accesses
+ *   "small_mode"                completion of synchronous calls of up to zero_copy_max_frames
+ *                               frames on host buffers: 0 = auto (= 2), 1 = stream
+ *                               synchronisation, 2 = the kernel raises a flag in pinned memory
+ *                               that the caller spins on
+ *   "host_chunk_min_frames"     first and last chunk of the *_host pipeline; chunk sizes double
+ *                               from here up to host_chunk_frames and mirror at the end
+ *                               (0 = uniform chunks)
  *   "bounce_threads"            threads that share the copy of a pageable caller buffer to or
  *                               from pinned staging in the *_host calls (copies of 2 MiB and more):
  *                               0 = auto (half of the hardware threads, shared between the
@@ -280,7 +314,7 @@ int sxgpu_stream_sync(sxgpu_ctx *ctx, sxgpu_stream stream); /* NULL = context st
 int sxgpu_set_option(sxgpu_ctx *ctx, const char *key, int64_t value);
 int sxgpu_get_option(sxgpu_ctx *ctx, const char *key, int64_t *value);
 /* Counters: "launches" (kernels launched by this context), "frames_rx", "frames_tx",
- * "h2d_bytes", "d2h_bytes", "resident_launches", "resident_calls". */
+ * "h2d_bytes", "d2h_bytes", "resident_launches", "resident_calls", "flagged_calls". */
 int sxgpu_get_counter(sxgpu_ctx *ctx, const char *key, uint64_t *value);
 
 #ifdef __cplusplus

@@ -188,6 +188,17 @@ SoapySXB200::SoapySXB200(const SoapySDR::Kwargs &args)
     // that is rung through a doorbell in pinned memory -- no launch, no stream sync per call.
     if (kwarg(args, "lowlatency", "0") == "1")
         sxgpu_set_option(gpu_, "resident_max_frames", 4096);
+    // sxgpu.<option>=<integer>: any tuning option of the C ABI (include/sxgpu.h), e.g.
+    // sxgpu.bounce_threads=2 when several devices share the host's cores.
+    for (const auto &kv : args) {
+        if (kv.first.rfind("sxgpu.", 0) != 0)
+            continue;
+        if (sxgpu_set_option(gpu_, kv.first.c_str() + 6, std::atoll(kv.second.c_str())) != SXGPU_OK) {
+            const std::string why = sxgpu_last_error(gpu_);
+            sxgpu_destroy(gpu_);
+            throw std::runtime_error("SoapySXB200: bad device argument " + kv.first + ": " + why);
+        }
+    }
     master_clock_ = std::stod(kwarg(args, "clock", "38.4e6"));
     sample_rate_ = master_clock_ / 256.0;
     antenna_[SOAPY_SDR_RX] = "RX";
@@ -705,11 +716,22 @@ void SoapySXB200::writeSetting(const std::string &key, const std::string &value)
     std::scoped_lock lock(settings_mutex_);
     if (key == "PA" && (value == "ON" || value == "OFF" || value == "AUTO"))
         pa_mode_ = value; // reference :1472-1493 drives two GPIO lines here
+    else if (key.rfind("sxgpu.", 0) == 0) // a tuning option of the C ABI; unknown keys are ignored like any other
+        sxgpu_set_option(gpu_, key.c_str() + 6, std::atoll(value.c_str()));
 }
 
 std::string SoapySXB200::readSetting(const std::string &key) const
 {
     std::scoped_lock lock(settings_mutex_);
+    if (key.rfind("sxgpu.", 0) == 0) { // counters ("sxgpu.launches", ...) and options of the C ABI
+        uint64_t counter = 0;
+        int64_t option = 0;
+        if (sxgpu_get_counter(gpu_, key.c_str() + 6, &counter) == SXGPU_OK)
+            return std::to_string(counter);
+        if (sxgpu_get_option(gpu_, key.c_str() + 6, &option) == SXGPU_OK)
+            return std::to_string(option);
+        return "";
+    }
     return key == "PA" ? pa_mode_ : "";
 }
 
@@ -754,6 +776,11 @@ unsigned long sxplan_overrun_skip(long pending, unsigned long buffer, unsigned l
 unsigned long sxplan_trim_nonblocking(unsigned long wanted, long available, long timeoutUs)
 {
     return sxplan::trim_nonblocking(wanted, available, timeoutUs);
+}
+
+int64_t sxplan_clock_after_forward(int64_t clock, int64_t position, int64_t target, int64_t ring, int64_t period)
+{
+    return sxplan::clock_after_forward(clock, position, target, ring, period);
 }
 
 void sxplan_place_tx_block(int64_t position, long queued, int has_time, int64_t time_ticks,

@@ -213,7 +213,9 @@ private:
 // during which only one direction of the link is busy (the first chunk's inbound copy, the last
 // chunk's outbound copy) is short, and large chunks in between, where per-chunk overhead counts.
 // Sizes double from c_min up to c_max and mirror at the end; every boundary is a multiple of 64
-// frames so that 16-byte alignment carries over from the block start for every frame width.
+// frames so that 16-byte alignment carries over from the block start for every frame width
+// (the up to 63 frames by which the length exceeds a multiple of 64 ride on the last chunk,
+// which may therefore be that much longer than c_max).
 struct ChunkSpan {
     size_t first, frames;
 };
@@ -226,7 +228,8 @@ inline std::vector<ChunkSpan> plan_chunks(size_t length, size_t c_min, size_t c_
     c_max = round64(c_max);
     c_min = (c_min == 0 || c_min > c_max) ? c_max : round64(c_min);
     std::vector<size_t> front, back;
-    size_t rem = length, c = c_min;
+    const size_t ragged = length % 64;
+    size_t rem = length - ragged, c = c_min;
     while (c < c_max && rem >= 4 * c) {
         front.push_back(c);
         back.push_back(c);
@@ -255,6 +258,12 @@ inline std::vector<ChunkSpan> plan_chunks(size_t length, size_t c_min, size_t c_
     for (size_t i = back.size(); i-- > 0;) {
         out.push_back({at, back[i]});
         at += back[i];
+    }
+    if (ragged) {
+        if (out.empty())
+            out.push_back({0, ragged});
+        else
+            out.back().frames += ragged;
     }
     return out;
 }

@@ -87,4 +87,27 @@ SXPLAN_HD TxPlacement place_tx_block(int64_t position, long queued, bool has_tim
     return p;
 }
 
+// Virtual-clock model of the forward loop (:1043-1073) for a stream whose hardware is simulated
+// (the stream bank): the write pointer is forwarded from `position` to `target` (> position)
+// through a ring of `ring` frames that drains as `clock` advances; room = clock + ring - pointer.
+// The reference forwards what fits and, while the gap is not closed, waits until a period of
+// room is free (snd_pcm_wait with avail_min = period).  Step by step: if the gap is below the
+// room it is closed at once.  Otherwise the pointer takes all the room (leaving min(room, 0)),
+// the wait brings the room to exactly one period, and from then on every turn moves one period
+// and waits one period until less than a period of gap is left, which then fits.  The clock
+// the loop ends with, without running it:
+SXPLAN_HD int64_t clock_after_forward(int64_t clock, int64_t position, int64_t target, int64_t ring, int64_t period)
+{
+    const int64_t gap = target - position;
+    if (gap <= 0)
+        return clock;
+    const int64_t room = clock + ring - position;
+    const int64_t fits = room > 0 ? room : 0;
+    if (gap < fits)
+        return clock;
+    clock += period - (room < 0 ? room : 0);     // first wait: room becomes exactly one period
+    clock += (gap - fits) / period * period;     // one more period of waiting per whole period of gap left
+    return clock;
+}
+
 } // namespace sxplan

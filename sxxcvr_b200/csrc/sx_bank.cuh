@@ -131,7 +131,7 @@ __global__ void bank_plan_read_kernel(BankState b, char *cf32_out)
         bank_plan_read(b, s, cf32_out);
 }
 
-__global__ void bank_capture_kernel(BankState b, char *cf32_out, bool fused)
+__global__ void bank_capture_kernel(BankState b, char *cf32_out, bool fused, bool synth)
 {
     const uint32_t lane = threadIdx.x & 31, warps_per_cta = blockDim.x >> 5;
     const uint64_t nwarps = uint64_t(gridDim.x) * warps_per_cta;
@@ -141,6 +141,8 @@ __global__ void bank_capture_kernel(BankState b, char *cf32_out, bool fused)
             first_ll = fused ? bank_plan_read(b, s, cf32_out).first : b.rx_first_frame[s];
         }
         const uint64_t first = uint64_t(__shfl_sync(0xffffffffu, first_ll, 0));
+        if (!synth) // the slot was filled from outside (sxgpu_bank_ingest)
+            continue;
         char *out = b.capture_stage + s * b.period * 8;
         for (uint32_t i = lane; i < b.period; i += 32) {
             uint64_t z = sx_synth_frame(b.seed + s, first + i);
@@ -178,25 +180,14 @@ __device__ __forceinline__ BankWritePlan bank_plan_write_core(const BankState &b
         return plan;
     }
 
-    // :1043-1073: forward the write pointer to the block's position, waiting for ring space.
-    long long gap = where.write_position - pos;
-    if (gap > 0)
+    // :1043-1073: forward the write pointer to the block's position, waiting for ring space --
+    // in closed form (sxplan::clock_after_forward), so that a far-future or garbage timestamp
+    // costs the same few instructions as any other instead of one loop turn per period of gap.
+    const long long gap = where.write_position - pos;
+    if (gap > 0) {
         plan.gap = gap;
-    while (gap > 0) {
-        long long fits = clock + ring - pos;
-        if (fits < 0)
-            fits = 0;
-        long long moved;
-        if (gap < fits) {
-            moved = gap;
-        } else {
-            moved = fits;
-            long long room_after = clock + ring - (pos + moved);
-            if (room_after < period) // snd_pcm_wait: until a period of space is free
-                clock += period - room_after;
-        }
-        pos += moved;
-        gap -= moved;
+        clock = sxplan::clock_after_forward(clock, pos, where.write_position, ring, period);
+        pos = where.write_position;
     }
 
     // blocking snd_pcm_writei of one period (:1093)
@@ -321,10 +312,11 @@ __global__ void bank_tx_kernel(BankState b, const char *cf32_in, int flags, cons
 // them back (as it would after a real DMA) into the caller's CF32 block, and the TX conversion
 // reads that block into the playback ring.
 __device__ __forceinline__ void bank_repeat_stream(const BankState &b, uint64_t s, char *cf32, uint64_t first,
-                                                   long long at, long long gap, long long start, uint32_t lane)
+                                                   long long at, long long gap, long long start, uint32_t lane,
+                                                   bool capture_in_slot)
 {
     char *slot = b.capture_stage + s * b.period * 8;
-    for (uint32_t i = lane; i < b.period; i += 32) {
+    for (uint32_t i = lane; i < b.period && !capture_in_slot; i += 32) {
         uint64_t z = sx_synth_frame(b.seed + s, first + i);
         Pack<2> p;
         p.w[0] = uint32_t(z);
@@ -343,6 +335,125 @@ __device__ __forceinline__ void bank_repeat_stream(const BankState &b, uint64_t 
     bank_play_block(b, s, cf32, at, gap, start, lane);
 }
 
+// The same share with every intermediate kept in registers: a lane owns 16-byte vectors
+// v = lane, lane + 32, ... of the period (two frames each), produces their capture frames,
+// converts them to CF32 and on to I2S words without a trip through memory, and issues the three
+// stores -- capture slot, caller's CF32 block, playback ring -- back to back.  Nothing is read
+// back, so a stream costs its plan's one round trip (the three counters) and then only stores.
+// `capture_in_slot`: the capture slot was filled from outside (sxgpu_bank_ingest); it is read
+// (one round trip, all vectors in flight at once) instead of being produced here.
+// Needs an even period and 16-byte aligned CF32 blocks; a ring position that is odd or wraps
+// inside the block falls back to frame-wide stores for the ring side.
+template <class Hook>
+__device__ __forceinline__ void bank_repeat_stream_reg(const BankState &b, uint64_t s, char *cf32, uint64_t first,
+                                                       long long at, long long gap, long long start, uint32_t lane,
+                                                       bool capture_in_slot, const Hook &hook)
+{
+    char *slot = b.capture_stage + s * b.period * 8;
+    char *cf = cf32 + s * b.period * 8;
+    char *ring = b.playback_ring + s * b.ring * 8;
+    const uint32_t nvec = b.period / 2;
+
+    if (at >= 0 && gap > 0) { // silence for a forwarded-over region (rare: late start, underrun)
+        long long g = gap, st0 = start;
+        if (g > (long long)b.ring) {
+            st0 += g - (long long)b.ring;
+            g = (long long)b.ring;
+        }
+        Pack<2> zero;
+        zero.w[0] = zero.w[1] = 0;
+        for (long long i = lane; i < g; i += 32)
+            st_stream<8>(ring + size_t(uint64_t(st0 + i) % b.ring) * 8, zero);
+        __syncwarp(); // a gap of a lap or more silences the slots the block is about to take
+    }
+    const uint64_t offset = at >= 0 ? uint64_t(at) % b.ring : 0;
+    const bool ring_vec = at >= 0 && (offset & 1) == 0 && offset + b.period <= b.ring;
+
+    constexpr int U = 4;
+    for (uint32_t base = 0; base < nvec; base += 32 * U) {
+        Pack<4> cap[U], mid[U], out[U];
+        if (capture_in_slot) {
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const uint32_t v = base + lane + 32 * u;
+                if (v < nvec)
+                    cap[u] = ld_stream<16>(slot + size_t(v) * 16);
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const uint32_t v = base + lane + 32 * u;
+                const uint64_t z0 = sx_synth_frame(b.seed + s, first + 2 * uint64_t(v));
+                const uint64_t z1 = sx_synth_frame(b.seed + s, first + 2 * uint64_t(v) + 1);
+                cap[u].w[0] = uint32_t(z0), cap[u].w[1] = uint32_t(z0 >> 32);
+                cap[u].w[2] = uint32_t(z1), cap[u].w[3] = uint32_t(z1 >> 32);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            RxCf32::apply<2>(cap[u], mid[u], 0.0f);
+            if (base + lane + 32 * u < nvec)
+                hook(mid[u], s, 2 * (base + lane + 32 * u)); // user DSP between RX and TX, identity by default
+            TxCf32::apply<2>(mid[u], out[u], b.thr2);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint32_t v = base + lane + 32 * u;
+            if (v >= nvec)
+                continue;
+            if (!capture_in_slot)
+                st_stream<16>(slot + size_t(v) * 16, cap[u]);
+            st_stream<16>(cf + size_t(v) * 16, mid[u]);
+            if (ring_vec) {
+                st_stream<16>(ring + (offset + 2 * size_t(v)) * 8, out[u]);
+            } else if (at >= 0) {
+                Pack<2> f0, f1;
+                f0.w[0] = out[u].w[0], f0.w[1] = out[u].w[1], f1.w[0] = out[u].w[2], f1.w[1] = out[u].w[3];
+                st_stream<8>(ring + size_t((offset + 2 * uint64_t(v)) % b.ring) * 8, f0);
+                st_stream<8>(ring + size_t((offset + 2 * uint64_t(v) + 1) % b.ring) * 8, f1);
+            }
+        }
+    }
+}
+
+// The hook the fused iteration applies to each pair of CF32 samples between the RX and the TX
+// conversion.  Identity here; csrc/sx_hook.cuh has the interface and an example.
+struct IdentityHook {
+    __device__ __forceinline__ void operator()(Pack<4> &, uint64_t, uint32_t) const {}
+};
+
+// Warp-per-K-streams schedule of the fused iteration, intermediates in registers (above).
+template <int K, class Hook>
+__global__ void __launch_bounds__(256) bank_repeat_reg_kernel(BankState b, char *cf32, long long rx_time_offset_ns,
+                                                              bool capture_in_slot, Hook hook)
+{
+    const uint32_t lane = threadIdx.x & 31, warps_per_cta = blockDim.x >> 5;
+    const uint64_t nwarps = uint64_t(gridDim.x) * warps_per_cta;
+    const uint64_t nchunks = (uint64_t(b.nstreams) + K - 1) / K;
+    for (uint64_t c = uint64_t(blockIdx.x) * warps_per_cta + (threadIdx.x >> 5); c < nchunks; c += nwarps) {
+        const uint64_t base = c * K;
+        const uint32_t count = uint32_t(b.nstreams - base < K ? b.nstreams - base : K);
+        long long my_first = 0, my_at = -1, my_gap = 0, my_start = 0;
+        if (lane < count) {
+            BankWritePlan w;
+            bank_plan_repeat(b, base + lane, cf32, rx_time_offset_ns, my_first, w);
+            my_at = w.at;
+            my_gap = w.gap;
+            my_start = w.start;
+        }
+#pragma unroll
+        for (uint32_t j = 0; j < K; j++) {
+            const uint64_t first = uint64_t(__shfl_sync(0xffffffffu, my_first, j));
+            const long long at = __shfl_sync(0xffffffffu, my_at, j);
+            const long long gap = __shfl_sync(0xffffffffu, my_gap, j);
+            const long long start = __shfl_sync(0xffffffffu, my_start, j);
+            if (j >= count)
+                break;
+            bank_repeat_stream_reg(b, base + j, cf32, first, at, gap, start, lane, capture_in_slot, hook);
+        }
+    }
+}
+
 // The repeater iteration in one launch: readStream(period) on every stream, then
 // writeStream(period, HAS_TIME, that read's timestamp + rx_time_offset_ns) of the block just
 // read (example/linear_repeater.py:50-71 without the filters).  State and results are exactly
@@ -355,7 +466,8 @@ __device__ __forceinline__ void bank_repeat_stream(const BankState &b, uint64_t 
 // 40 B/frame over five launches.
 constexpr int kRepeatGroup = 32;
 
-__global__ void __launch_bounds__(256) bank_repeat_kernel(BankState b, char *cf32, long long rx_time_offset_ns)
+__global__ void __launch_bounds__(256) bank_repeat_kernel(BankState b, char *cf32, long long rx_time_offset_ns,
+                                                          bool capture_in_slot)
 {
     __shared__ long long s_first[kRepeatGroup], s_at[kRepeatGroup], s_gap[kRepeatGroup], s_start[kRepeatGroup];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps_per_cta = blockDim.x >> 5;
@@ -376,7 +488,7 @@ __global__ void __launch_bounds__(256) bank_repeat_kernel(BankState b, char *cf3
         __syncthreads();
         for (uint32_t j = warp; j < count; j += warps_per_cta) {
             const uint64_t s = base + j;
-            bank_repeat_stream(b, s, cf32, uint64_t(s_first[j]), s_at[j], s_gap[j], s_start[j], lane);
+            bank_repeat_stream(b, s, cf32, uint64_t(s_first[j]), s_at[j], s_gap[j], s_start[j], lane, capture_in_slot);
         }
         __syncthreads(); // the next group's plans overwrite the shared arrays
     }
@@ -388,7 +500,8 @@ __global__ void __launch_bounds__(256) bank_repeat_kernel(BankState b, char *cf3
 // evenly over the resident warps, large K spends fewer issue slots on the (one-lane-per-stream)
 // decisions.
 template <int K>
-__global__ void __launch_bounds__(256) bank_repeat_warp_kernel(BankState b, char *cf32, long long rx_time_offset_ns)
+__global__ void __launch_bounds__(256) bank_repeat_warp_kernel(BankState b, char *cf32, long long rx_time_offset_ns,
+                                                               bool capture_in_slot)
 {
     const uint32_t lane = threadIdx.x & 31, warps_per_cta = blockDim.x >> 5;
     const uint64_t nwarps = uint64_t(gridDim.x) * warps_per_cta;
@@ -413,7 +526,30 @@ __global__ void __launch_bounds__(256) bank_repeat_warp_kernel(BankState b, char
             const long long start = __shfl_sync(0xffffffffu, my_start, j);
             if (j >= count) // count is the same in every lane
                 break;
-            bank_repeat_stream(b, base + j, cf32, first, at, gap, start, lane);
+            bank_repeat_stream(b, base + j, cf32, first, at, gap, start, lane, capture_in_slot);
+        }
+    }
+}
+
+// The last `nframes` frames each stream wrote (ending at its TX counter), copied out of the
+// playback rings into dst[stream - first_stream][nframes]: what the I2S DMA would fetch next.
+// One warp per stream; dst is device memory or device-mapped pinned host memory.
+__global__ void bank_drain_kernel(BankState b, uint32_t first_stream, uint32_t count, uint32_t nframes, char *dst)
+{
+    const uint32_t lane = threadIdx.x & 31, warps_per_cta = blockDim.x >> 5;
+    const uint64_t nwarps = uint64_t(gridDim.x) * warps_per_cta;
+    for (uint64_t j = uint64_t(blockIdx.x) * warps_per_cta + (threadIdx.x >> 5); j < count; j += nwarps) {
+        const uint64_t s = first_stream + j;
+        const long long end = b.tx_position[s];
+        const char *ring = b.playback_ring + s * b.ring * 8;
+        char *out = dst + j * uint64_t(nframes) * 8;
+        for (uint32_t i = lane; i < nframes; i += 32) {
+            const long long p = end - (long long)nframes + i;
+            Pack<2> f;
+            f.w[0] = f.w[1] = 0; // before the stream's first frame: silence
+            if (p >= 0)
+                f = ld_stream<8>(ring + size_t(uint64_t(p) % b.ring) * 8);
+            st_stream<8>(out + size_t(i) * 8, f);
         }
     }
 }

@@ -665,6 +665,293 @@ __global__ void batch_slice_kernel(const BlockDesc *__restrict__ blocks, uint32_
 }
 
 // ---------------------------------------------------------------------------------------
+// Batched blocks on the bulk-async schedule: many mid-size blocks (BASELINE config 5's small
+// end: 1 MiB - 64 MiB each) in ONE launch at the large-block kernel's throughput.
+//
+// Every block is cut into tiles of TILE frames; tile_start[b] = number of tiles in blocks
+// 0..b-1 (exclusive prefix sum, tile_start[nblocks] = total).  Persistent CTAs take global
+// tiles c, c + G, c + 2G, ... exactly like bulk_convert_kernel takes the tiles of one block,
+// and run the same pipeline (bulk loads into a STAGES-deep shared-memory ring on mbarriers,
+// shared -> shared conversion by all threads, bulk stores gated by wait_group.read).  The
+// producer thread finds a tile's block by walking tile_start forward (binary search once, for
+// its first tile) and leaves a small record per stage for the consumers.
+//
+// A block whose buffers are not 16-byte aligned cannot be moved by bulk copies: its tiles are
+// converted with ordinary vector accesses by the same CTA ("direct" tiles), in the same pass.
+// An odd last frame (8 bytes past the 16-byte units) is converted directly by one thread.
+// ---------------------------------------------------------------------------------------
+struct BatchBulkArgs {
+    const BlockDesc *blocks;
+    const unsigned long long *tile_start; // [nblocks + 1]
+    uint32_t nblocks;
+    int load_policy, store_policy;
+};
+
+struct TileRecord {
+    const char *src; // first frame of the tile
+    char *dst;
+    uint32_t bulk_frames; // frames moved by the bulk copies (even); 0 = direct tile
+    uint32_t frames;      // frames in the tile, bulk + direct remainder
+    float thr2;
+    uint32_t pad;
+};
+
+template <int TILE>
+__device__ __forceinline__ void batch_tile_record(const BatchBulkArgs &a, uint64_t t, uint32_t &b, TileRecord &rec,
+                                                  int src_frame_bytes, int dst_frame_bytes)
+{
+    while (b + 1 < a.nblocks && a.tile_start[b + 1] <= t) // also steps over empty blocks
+        b++;
+    const BlockDesc d = a.blocks[b];
+    const uint64_t lo = (t - a.tile_start[b]) * uint64_t(TILE);
+    const uint64_t left = d.length - lo;
+    const uint32_t n = uint32_t(left < uint64_t(TILE) ? left : uint64_t(TILE));
+    rec.src = d.src + lo * src_frame_bytes;
+    rec.dst = d.dst + lo * dst_frame_bytes;
+    rec.frames = n;
+    rec.thr2 = d.thr2;
+    rec.pad = 0;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(d.src) | reinterpret_cast<uintptr_t>(d.dst)) & 15) == 0;
+    // whole 16-byte units on both sides: groups of 4 frames when one side has 4-byte frames
+    const uint32_t unit = (src_frame_bytes == 4 || dst_frame_bytes == 4) ? 4u : 2u;
+    rec.bulk_frames = aligned ? (n / unit) * unit : 0u;
+}
+
+template <class Op, int TILE, int STAGES>
+__global__ void __launch_bounds__(256) bulk_batch_kernel(const BatchBulkArgs a)
+{
+    constexpr int SFB = Op::kSrcWords * 4, DFB = Op::kDstWords * 4;
+    constexpr size_t IN_STAGE = size_t(TILE) * SFB, OUT_STAGE = size_t(TILE) * DFB;
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char *in_buf = smem;
+    unsigned char *out_buf = smem + size_t(STAGES) * IN_STAGE;
+    uint64_t *full = reinterpret_cast<uint64_t *>(out_buf + size_t(STAGES) * OUT_STAGE);
+    TileRecord *recs = reinterpret_cast<TileRecord *>(full + STAGES);
+
+    const uint64_t ntiles = a.tile_start[a.nblocks];
+    const uint64_t first = blockIdx.x, stride = gridDim.x;
+    if (first >= ntiles)
+        return;
+    const uint64_t mine = (ntiles - first + stride - 1) / stride;
+    const uint64_t pol = bulk::make_policy(a.load_policy), pol_store = bulk::make_policy(a.store_policy);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; s++)
+            bulk::mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // Producer state (thread 0): the block the next tile to be loaded belongs to.
+    uint32_t blk = 0;
+    auto produce = [&](uint64_t i) { // fills recs[i % STAGES] and, for a bulk tile, starts its load
+        const int s = int(i % STAGES);
+        TileRecord rec;
+        batch_tile_record<TILE>(a, first + i * stride, blk, rec, SFB, DFB);
+        recs[s] = rec;
+        if (rec.bulk_frames) {
+            bulk::mbar_expect_tx(&full[s], rec.bulk_frames * SFB);
+            bulk::load_g2s(in_buf + size_t(s) * IN_STAGE, rec.src, rec.bulk_frames * SFB, &full[s], pol);
+        }
+    };
+    if (threadIdx.x == 0) {
+        // binary search: the last block whose first tile is <= this CTA's first tile
+        uint32_t lo = 0, hi = a.nblocks - 1;
+        while (lo < hi) {
+            const uint32_t mid = lo + (hi - lo + 1) / 2;
+            if (a.tile_start[mid] <= first)
+                lo = mid;
+            else
+                hi = mid - 1;
+        }
+        blk = lo;
+        for (uint64_t i = 0; i < uint64_t(STAGES) && i < mine; i++)
+            produce(i);
+    }
+    __syncthreads(); // the first records are visible to everybody
+
+    uint32_t phases = 0; // bit s: parity of the next completion of full[s]; same in every thread
+    for (uint64_t i = 0; i < mine; i++) {
+        const int s = int(i % STAGES);
+        // out_buf[s] was last read by the bulk store of tile i - STAGES (every tile commits a
+        // group, empty for direct tiles, so the count of pending groups is the count of tiles).
+        if (threadIdx.x == 0)
+            bulk::wait_group_read<STAGES - 1>();
+        __syncthreads();
+        const TileRecord rec = recs[s];
+
+        if (rec.bulk_frames) {
+            bulk::mbar_wait(&full[s], (phases >> s) & 1u);
+            phases ^= 1u << s;
+            const unsigned char *ib = in_buf + size_t(s) * IN_STAGE;
+            unsigned char *ob = out_buf + size_t(s) * OUT_STAGE;
+            constexpr int FR = (Op::kSrcWords == 1 || Op::kDstWords == 1) ? 4 : 2;
+            for (uint32_t v = threadIdx.x; v * FR < rec.bulk_frames; v += blockDim.x) {
+                Pack<Op::kSrcWords * FR> in;
+                Pack<Op::kDstWords * FR> out;
+                const uint4 *ip = reinterpret_cast<const uint4 *>(ib + size_t(v) * FR * SFB);
+#pragma unroll
+                for (int q = 0; q < Op::kSrcWords * FR / 4; q++) {
+                    uint4 t = ip[q];
+                    in.w[4 * q] = t.x, in.w[4 * q + 1] = t.y, in.w[4 * q + 2] = t.z, in.w[4 * q + 3] = t.w;
+                }
+                Op::template apply<FR>(in, out, rec.thr2);
+                uint4 *op = reinterpret_cast<uint4 *>(ob + size_t(v) * FR * DFB);
+#pragma unroll
+                for (int q = 0; q < Op::kDstWords * FR / 4; q++)
+                    op[q] = make_uint4(out.w[4 * q], out.w[4 * q + 1], out.w[4 * q + 2], out.w[4 * q + 3]);
+            }
+        }
+        if (rec.bulk_frames < rec.frames) { // a direct tile, or the frames past the last 16-byte unit
+            BlockDesc d;
+            d.src = rec.src;
+            d.dst = rec.dst;
+            d.length = rec.frames;
+            d.thr2 = rec.thr2;
+            d.reserved = 0;
+            convert_span<Op>(d, rec.bulk_frames, rec.frames, threadIdx.x, blockDim.x);
+        }
+        bulk::fence_async_smem(); // generic-proxy writes to out_buf visible to the bulk store
+        __syncthreads();          // ... and everybody is done with recs[s] and in_buf[s]
+
+        if (threadIdx.x == 0) {
+            if (rec.bulk_frames)
+                bulk::store_s2g(rec.dst, out_buf + size_t(s) * OUT_STAGE, rec.bulk_frames * DFB, pol_store);
+            bulk::commit_group();
+            if (i + STAGES < mine)
+                produce(i + STAGES);
+        }
+    }
+    if (threadIdx.x == 0)
+        bulk::wait_group_all();
+}
+
+// tile_start for a descriptor list that lives on the device: one CTA, every thread sums a
+// contiguous run of blocks, the run totals are scanned in shared memory, every thread then
+// writes its run's prefix.  (Host-resident lists are summed on the host.)
+template <int TILE>
+__global__ void __launch_bounds__(1024) batch_tile_scan_kernel(const BlockDesc *__restrict__ blocks, uint32_t nblocks,
+                                                               unsigned long long *tile_start)
+{
+    __shared__ unsigned long long run_total[1024];
+    const uint32_t per = (nblocks + blockDim.x - 1) / blockDim.x;
+    const uint32_t lo = threadIdx.x * per, hi = lo + per < nblocks ? lo + per : nblocks;
+    unsigned long long sum = 0;
+    for (uint32_t b = lo; b < hi; b++)
+        sum += (blocks[b].length + TILE - 1) / TILE;
+    run_total[threadIdx.x] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long acc = 0;
+        for (uint32_t t = 0; t < blockDim.x; t++) {
+            const unsigned long long v = run_total[t];
+            run_total[t] = acc;
+            acc += v;
+        }
+        tile_start[nblocks] = acc;
+    }
+    __syncthreads();
+    unsigned long long acc = run_total[threadIdx.x];
+    for (uint32_t b = lo; b < hi; b++) {
+        tile_start[b] = acc;
+        acc += (blocks[b].length + TILE - 1) / TILE;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Fused repeater on the bulk-async schedule: one bulk load of I2S frames per tile, RX
+// conversion shared -> shared, TX conversion shared -> shared, and two bulk stores (the CF32
+// intermediate -- an API-visible buffer in the reference -- and the I2S output).  24 B/frame.
+// ---------------------------------------------------------------------------------------
+struct BulkLoopbackArgs {
+    const char *i2s_in; // 16-byte aligned
+    char *cf32;         // 16-byte aligned, may be null
+    char *i2s_out;      // 16-byte aligned
+    uint64_t nframes;   // even
+    float thr2;
+    int load_policy, store_policy;
+};
+
+template <int TILE, int STAGES>
+__global__ void __launch_bounds__(256) bulk_loopback_kernel(const BulkLoopbackArgs a)
+{
+    constexpr size_t STAGE = size_t(TILE) * 8;
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char *in_buf = smem;
+    unsigned char *mid_buf = smem + size_t(STAGES) * STAGE;
+    unsigned char *out_buf = smem + 2 * size_t(STAGES) * STAGE;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + 3 * size_t(STAGES) * STAGE);
+
+    const uint64_t ntiles = (a.nframes + TILE - 1) / TILE;
+    const uint64_t first = blockIdx.x, stride = gridDim.x;
+    if (first >= ntiles)
+        return;
+    const uint64_t mine = (ntiles - first + stride - 1) / stride;
+    const uint64_t pol = bulk::make_policy(a.load_policy), pol_store = bulk::make_policy(a.store_policy);
+    auto tile_frames = [&](uint64_t i) -> uint32_t {
+        const uint64_t left = a.nframes - (first + i * stride) * TILE;
+        return uint32_t(left < uint64_t(TILE) ? left : uint64_t(TILE));
+    };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; s++)
+            bulk::mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (uint64_t i = 0; i < uint64_t(STAGES) && i < mine; i++) {
+            const uint32_t nf = tile_frames(i);
+            bulk::mbar_expect_tx(&full[i], nf * 8);
+            bulk::load_g2s(in_buf + i * STAGE, a.i2s_in + (first + i * stride) * TILE * 8, nf * 8, &full[i], pol);
+        }
+    }
+
+    for (uint64_t i = 0; i < mine; i++) {
+        const int s = int(i % STAGES);
+        const uint32_t nf = tile_frames(i);
+        // mid_buf[s] / out_buf[s] were last read by the stores of tile i - STAGES (one group per tile)
+        if (threadIdx.x == 0)
+            bulk::wait_group_read<STAGES - 1>();
+        __syncthreads();
+        bulk::mbar_wait(&full[s], uint32_t(i / STAGES) & 1u);
+
+        const uint4 *ip = reinterpret_cast<const uint4 *>(in_buf + size_t(s) * STAGE);
+        uint4 *mp = reinterpret_cast<uint4 *>(mid_buf + size_t(s) * STAGE);
+        uint4 *op = reinterpret_cast<uint4 *>(out_buf + size_t(s) * STAGE);
+        for (uint32_t v = threadIdx.x; v * 2 < nf; v += blockDim.x) {
+            const uint4 t = ip[v];
+            Pack<4> in, mid, out;
+            in.w[0] = t.x, in.w[1] = t.y, in.w[2] = t.z, in.w[3] = t.w;
+            RxCf32::apply<2>(in, mid, 0.0f);
+            TxCf32::apply<2>(mid, out, a.thr2);
+            if (a.cf32)
+                mp[v] = make_uint4(mid.w[0], mid.w[1], mid.w[2], mid.w[3]);
+            op[v] = make_uint4(out.w[0], out.w[1], out.w[2], out.w[3]);
+        }
+        bulk::fence_async_smem();
+        __syncthreads();
+
+        if (threadIdx.x == 0) {
+            const uint64_t at = (first + i * stride) * TILE * 8;
+            if (a.cf32)
+                bulk::store_s2g(a.cf32 + at, mid_buf + size_t(s) * STAGE, nf * 8, pol_store);
+            bulk::store_s2g(a.i2s_out + at, out_buf + size_t(s) * STAGE, nf * 8, pol_store);
+            bulk::commit_group();
+            const uint64_t nxt = i + STAGES;
+            if (nxt < mine) {
+                const uint32_t nnf = tile_frames(nxt);
+                bulk::mbar_expect_tx(&full[s], nnf * 8);
+                bulk::load_g2s(in_buf + size_t(s) * STAGE, a.i2s_in + (first + nxt * stride) * TILE * 8, nnf * 8,
+                               &full[s], pol);
+            }
+        }
+    }
+    if (threadIdx.x == 0)
+        bulk::wait_group_all();
+}
+
+// ---------------------------------------------------------------------------------------
 // Small synchronous calls on host buffers (readStream / writeStream of one period,
 // SoapySX.cpp:451: 256 frames = 2 KiB): the kernel reads and writes the pinned host buffers
 // across PCIe itself and, when the last CTA is done, stores the call's sequence number into a

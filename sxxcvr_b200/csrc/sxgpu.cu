@@ -100,6 +100,8 @@ struct sxgpu_ctx {
     int64_t zero_copy_max_frames = 1 << 18; // measured crossover, profiles/r01_sweep_host_path.json
     int64_t resident_max_frames = 0;        // > 0: blocks up to this size go to the resident converter
     int64_t zero_copy_variant = 1;          // schedule of the zero-copy kernel (1 vec128, 2 vec256, 3 bulk)
+    int64_t batch_variant = 0;              // blocks above 4096 frames: 0 auto (= bulk-async tiles), 1 = slices of CTAs on vector accesses
+    int64_t loopback_variant = 0;           // 0 auto (= bulk-async), 1 = vector accesses
     int64_t bank_repeat_variant = 0;        // 0 auto; 1, 2, 4, 8 = K streams per warp round; 100 = 32 per CTA round
     int64_t bounce_threads = 0;             // threads copying a pageable caller's buffer: 0 auto, 1 = the caller alone
     int64_t numa_local_alloc = 1;           // place pinned host memory on the GPU's NUMA node
@@ -852,10 +854,11 @@ int convert_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset, void *h_d
     // two directions' CPU copies, the DMA and the kernels of different chunks all overlap.
     const bool bounce_in = !si.pinned && !si.on_device, bounce_out = !di.pinned && !di.on_device;
     const size_t c_max = std::min<size_t>(length, pick_chunk_frames(ctx, length));
-    SX_TRY(ensure_ring(ctx, lane, c_max, bounce_in, bounce_out));
+    // + 128: the cap is rounded up to 64 frames and the last chunk carries the ragged end (< 64)
+    SX_TRY(ensure_ring(ctx, lane, c_max + 128, bounce_in, bounce_out));
     HostRing &r = lane.ring;
     const std::vector<sxhost::ChunkSpan> chunks =
-        sxhost::plan_chunks(length, size_t(ctx->host_chunk_min_frames), std::min(c_max, r.chunk_frames));
+        sxhost::plan_chunks(length, size_t(ctx->host_chunk_min_frames), std::min(c_max, r.chunk_frames - 128));
     const size_t nchunks = chunks.size();
 
     lane.issued.reset();
@@ -962,6 +965,15 @@ int convert_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset, void *h_d
 // ---------------------------------------------------------------------------------------
 static_assert(sizeof(sxgpu_block) == sizeof(BlockDesc), "descriptor layouts must match");
 
+// Tile shape of the batched bulk kernel and of the bulk loopback: the large-block default.
+constexpr int kBatchTile = 2048, kBatchStages = 4;
+template <class Op> constexpr size_t batch_smem_bytes()
+{
+    return size_t(kBatchStages) * (size_t(kBatchTile) * (Op::kSrcWords + Op::kDstWords) * 4 + 8 + sizeof(TileRecord));
+}
+constexpr int kLoopTile = 2048, kLoopStages = 4;
+constexpr size_t kLoopSmem = 3 * size_t(kLoopStages) * kLoopTile * 8 + size_t(kLoopStages) * 8;
+
 template <class Op>
 int convert_batch(sxgpu_ctx *ctx, const sxgpu_block *blocks, uint32_t nblocks, int on_device,
                   size_t max_length, sxgpu_stream stream)
@@ -986,8 +998,10 @@ int convert_batch(sxgpu_ctx *ctx, const sxgpu_block *blocks, uint32_t nblocks, i
                 return ctx->invalid("batched blocks must be frame-aligned");
             max_length = std::max<size_t>(max_length, blocks[i].length);
         }
-        // Stream-ordered staging: safe against back-to-back batches on any stream.
-        SX_CUDA(ctx, cudaMallocAsync(&staged, size_t(nblocks) * sizeof(BlockDesc), st));
+        // Stream-ordered staging: safe against back-to-back batches on any stream.  The
+        // descriptors are followed by the exclusive prefix sum of their tile counts.
+        SX_CUDA(ctx, cudaMallocAsync(&staged, size_t(nblocks) * sizeof(BlockDesc) +
+                                                  (size_t(nblocks) + 1) * sizeof(unsigned long long), st));
     } else if (max_length == 0) {
         return ctx->invalid("max_length is required for device-resident block lists");
     }
@@ -1000,8 +1014,18 @@ int convert_batch(sxgpu_ctx *ctx, const sxgpu_block *blocks, uint32_t nblocks, i
             if (p)
                 cudaFreeAsync(p, st);
         }
-    } guard = {staged, st};
+    } guard = {staged, st}, scan_guard = {nullptr, st};
+    uint64_t host_tiles = 0;
     if (staged) {
+        std::vector<unsigned long long> tile_start(size_t(nblocks) + 1);
+        for (uint32_t i = 0; i < nblocks; i++) {
+            tile_start[i] = host_tiles;
+            host_tiles += (blocks[i].length + kBatchTile - 1) / kBatchTile;
+        }
+        tile_start[nblocks] = host_tiles;
+        // pageable source: copied before cudaMemcpyAsync returns
+        SX_CUDA(ctx, cudaMemcpyAsync(static_cast<char *>(staged) + size_t(nblocks) * sizeof(BlockDesc), tile_start.data(),
+                                     tile_start.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
         // The caller may reuse `blocks` as soon as this call returns: when the list sits in pinned
         // memory cudaMemcpyAsync is truly asynchronous and would read it later, so the copy is
         // waited for here (a few microseconds for a list of this size; the kernels stay asynchronous).
@@ -1023,13 +1047,35 @@ int convert_batch(sxgpu_ctx *ctx, const sxgpu_block *blocks, uint32_t nblocks, i
         uint64_t ctas = (uint64_t(nblocks) + warps - 1) / warps;
         int grid = int(std::min<uint64_t>(ctas, uint64_t(sms) * 8));
         batch_warp_kernel<Op><<<grid, block, 0, st>>>(d_blocks, nblocks);
-    } else {
+    } else if (ctx->batch_variant == 1) {
         int block = 256;
         uint64_t slices = (max_length + 16383) / 16384; // ~128 KiB of frames per CTA pass
         uint64_t want = uint64_t(sms) * 8;
         uint32_t gy = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(slices, (want + nblocks - 1) / nblocks)));
         uint32_t gx = uint32_t(std::min<uint64_t>(nblocks, std::max<uint64_t>(1, want / gy)));
         batch_slice_kernel<Op><<<dim3(gx, gy), block, 0, st>>>(d_blocks, nblocks);
+    } else {
+        // Mid-size and large blocks: every block cut into tiles, all tiles of all blocks walked by
+        // one persistent CTA per SM on the bulk-async schedule (bulk_batch_kernel).
+        constexpr int TILE = kBatchTile;
+        unsigned long long *d_tile_start = nullptr;
+        uint64_t ntiles_hint = uint64_t(sms); // device-resident lists: the kernel reads the total itself
+        if (staged) {
+            d_tile_start = reinterpret_cast<unsigned long long *>(static_cast<char *>(staged) +
+                                                                  size_t(nblocks) * sizeof(BlockDesc));
+            ntiles_hint = host_tiles;
+        } else {
+            SX_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void **>(&d_tile_start),
+                                         (size_t(nblocks) + 1) * sizeof(unsigned long long), st));
+            scan_guard.p = d_tile_start;
+            batch_tile_scan_kernel<TILE><<<1, 1024, 0, st>>>(d_blocks, nblocks, d_tile_start);
+            SX_CUDA(ctx, cudaGetLastError());
+            ctx->launches++;
+        }
+        BatchBulkArgs a = {d_blocks, d_tile_start, nblocks, int(ctx->bulk_load_policy), int(ctx->bulk_store_policy)};
+        auto k = bulk_batch_kernel<Op, TILE, kBatchStages>;
+        int grid = persistent_grid(ctx, k, 256, batch_smem_bytes<Op>(), ntiles_hint);
+        k<<<grid, 256, batch_smem_bytes<Op>(), st>>>(a);
     }
     SX_CUDA(ctx, cudaGetLastError());
     ctx->launches++;
@@ -1060,6 +1106,8 @@ int64_t *option_slot(sxgpu_ctx *ctx, const char *key)
         {"resident_max_frames", &ctx->resident_max_frames},
         {"zero_copy_variant", &ctx->zero_copy_variant},
         {"bank_repeat_variant", &ctx->bank_repeat_variant},
+        {"batch_variant", &ctx->batch_variant},
+        {"loopback_variant", &ctx->loopback_variant},
         {"bounce_threads", &ctx->bounce_threads},
         {"numa_local_alloc", &ctx->numa_local_alloc},
         {"numa_node", &ctx->numa_node},
@@ -1158,6 +1206,13 @@ int sxgpu_init(int device, sxgpu_ctx **out)
     if (prepare_bulk_kernels<RxCf32>(ctx) != SXGPU_OK || prepare_bulk_kernels<TxCf32>(ctx) != SXGPU_OK ||
         prepare_bulk_kernels<RxCs16>(ctx) != SXGPU_OK || prepare_bulk_kernels<TxCs16>(ctx) != SXGPU_OK ||
         prepare_bulk_kernels<RxS16Cf32>(ctx) != SXGPU_OK || prepare_bulk_kernels<TxCf32S16>(ctx) != SXGPU_OK)
+        return bail(SXGPU_ERR_CUDA);
+    if (cudaFuncSetAttribute(bulk_batch_kernel<RxCf32, kBatchTile, kBatchStages>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, int(batch_smem_bytes<RxCf32>())) != cudaSuccess ||
+        cudaFuncSetAttribute(bulk_batch_kernel<TxCf32, kBatchTile, kBatchStages>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, int(batch_smem_bytes<TxCf32>())) != cudaSuccess ||
+        cudaFuncSetAttribute(bulk_loopback_kernel<kLoopTile, kLoopStages>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, int(kLoopSmem)) != cudaSuccess)
         return bail(SXGPU_ERR_CUDA);
     *out = ctx;
     return SXGPU_OK;
@@ -1308,15 +1363,36 @@ int sxgpu_convert_loopback(sxgpu_ctx *ctx, const void *d_i2s_in, void *d_cf32, v
         return ctx->invalid("loopback buffers must be 16-byte aligned");
     SX_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
-    LoopbackArgs a = {static_cast<const char *>(d_i2s_in), static_cast<char *>(d_cf32),
-                      static_cast<char *>(d_i2s_out), length / 2, length, tx_threshold2};
-    int block = int(ctx->block ? ctx->block : 256);
-    constexpr int U = 4;
-    uint64_t tiles = (a.nvec + uint64_t(block) * U - 1) / (uint64_t(block) * U);
-    int grid = persistent_grid(ctx, loopback_kernel<U>, block, 0, tiles);
-    loopback_kernel<U><<<grid, block, 0, st>>>(a);
-    SX_CUDA(ctx, cudaGetLastError());
-    ctx->launches++;
+    if (ctx->loopback_variant != 1 && length >= 2) {
+        // Bulk-async schedule over the even part; an odd last frame goes through the vector kernel.
+        const uint64_t even = uint64_t(length) & ~uint64_t(1);
+        BulkLoopbackArgs b = {static_cast<const char *>(d_i2s_in), static_cast<char *>(d_cf32),
+                              static_cast<char *>(d_i2s_out), even, tx_threshold2, int(ctx->bulk_load_policy),
+                              int(ctx->bulk_store_policy)};
+        auto k = bulk_loopback_kernel<kLoopTile, kLoopStages>;
+        const uint64_t ntiles = (even + kLoopTile - 1) / kLoopTile;
+        k<<<persistent_grid(ctx, k, 256, kLoopSmem, ntiles), 256, kLoopSmem, st>>>(b);
+        SX_CUDA(ctx, cudaGetLastError());
+        ctx->launches++;
+        if (length & 1) {
+            const size_t off = even * 8;
+            LoopbackArgs t = {static_cast<const char *>(d_i2s_in) + off, d_cf32 ? static_cast<char *>(d_cf32) + off : nullptr,
+                              static_cast<char *>(d_i2s_out) + off, 0, 1, tx_threshold2};
+            loopback_kernel<4><<<1, 32, 0, st>>>(t);
+            SX_CUDA(ctx, cudaGetLastError());
+            ctx->launches++;
+        }
+    } else {
+        LoopbackArgs a = {static_cast<const char *>(d_i2s_in), static_cast<char *>(d_cf32),
+                          static_cast<char *>(d_i2s_out), length / 2, length, tx_threshold2};
+        int block = int(ctx->block ? ctx->block : 256);
+        constexpr int U = 4;
+        uint64_t tiles = (a.nvec + uint64_t(block) * U - 1) / (uint64_t(block) * U);
+        int grid = persistent_grid(ctx, loopback_kernel<U>, block, 0, tiles);
+        loopback_kernel<U><<<grid, block, 0, st>>>(a);
+        SX_CUDA(ctx, cudaGetLastError());
+        ctx->launches++;
+    }
     ctx->frames_rx += length;
     ctx->frames_tx += length;
     return SXGPU_OK;
@@ -1329,6 +1405,7 @@ struct sxgpu_bank {
     sxgpu_ctx *ctx = nullptr;
     BankState st = {};
     void *arena = nullptr; // one allocation for every per-stream array
+    bool external_capture = false; // capture slots are filled by sxgpu_bank_ingest, not synthesised
 };
 
 namespace {
@@ -1490,7 +1567,8 @@ int sxgpu_bank_read(sxgpu_bank *bank, void *d_cf32, sxgpu_stream stream)
     const bool fused = b.nstreams <= kBankFusedPlanStreams;
     if (!fused)
         bank_plan_read_kernel<<<per_stream_grid(b.nstreams, 256), 256, 0, st>>>(b, static_cast<char *>(d_cf32));
-    bank_capture_kernel<<<per_warp_grid(ctx, b.nstreams, 256), 256, 0, st>>>(b, static_cast<char *>(d_cf32), fused);
+    bank_capture_kernel<<<per_warp_grid(ctx, b.nstreams, 256), 256, 0, st>>>(b, static_cast<char *>(d_cf32), fused,
+                                                                             !bank->external_capture);
     batch_warp_kernel<RxCf32><<<per_warp_grid(ctx, b.nstreams, 256), 256, 0, st>>>(b.rx_blocks, b.nstreams);
     SX_CUDA(ctx, cudaGetLastError());
     ctx->launches += fused ? 2 : 3;
@@ -1532,33 +1610,110 @@ int sxgpu_bank_repeat(sxgpu_bank *bank, void *d_cf32, long long rx_time_offset_n
     cudaStream_t st = bank_stream(bank, stream);
     const BankState &b = bank->st;
     char *cf = static_cast<char *>(d_cf32);
+    const bool ext = bank->external_capture;
     auto warp_variant = [&](auto kernel, uint64_t k) {
         const uint64_t chunks = (uint64_t(b.nstreams) + k - 1) / k;
-        kernel<<<persistent_grid(ctx, kernel, 256, 0, (chunks + 7) / 8), 256, 0, st>>>(b, cf, rx_time_offset_ns);
+        kernel<<<persistent_grid(ctx, kernel, 256, 0, (chunks + 7) / 8), 256, 0, st>>>(b, cf, rx_time_offset_ns, ext);
+    };
+    auto reg_variant = [&](auto kernel, uint64_t k) { // intermediates in registers, stores only
+        const uint64_t chunks = (uint64_t(b.nstreams) + k - 1) / k;
+        kernel<<<persistent_grid(ctx, kernel, 256, 0, (chunks + 7) / 8), 256, 0, st>>>(b, cf, rx_time_offset_ns, ext,
+                                                                                       IdentityHook());
     };
     auto group_variant = [&](auto kernel) { // a CTA takes 32 streams per round, its first warp decides for all of them
         const uint64_t groups = (uint64_t(b.nstreams) + kRepeatGroup - 1) / kRepeatGroup;
-        kernel<<<persistent_grid(ctx, kernel, 256, 0, groups), 256, 0, st>>>(b, cf, rx_time_offset_ns);
+        kernel<<<persistent_grid(ctx, kernel, 256, 0, groups), 256, 0, st>>>(b, cf, rx_time_offset_ns, ext);
     };
-    // Streams per warp round.  Lanes 0..K-1 take K streams' decisions side by side, so a larger K
-    // spends fewer issue slots on the timestamp arithmetic; a smaller K spreads few streams over
-    // more warps (a warp needs 1-2 us per stream: dependent round trips through L2).  Measured
-    // crossovers: profiles/r01_sweep_bank_repeat.json.
+    // Schedules.  K streams per warp round: lanes 0..K-1 take K streams' decisions side by side, so
+    // a larger K spends fewer issue slots on the timestamp arithmetic; a smaller K spreads few
+    // streams over more warps.  1/2/4/8 and 100 carry each stream through memory stage by stage
+    // (each stage reading from L2 what the previous one wrote); 201/202/204 keep the stages'
+    // intermediates in registers and only store.  Measured crossovers: profiles/r02_summary.md.
+    const bool reg_ok = (b.period % 2 == 0) && reinterpret_cast<uintptr_t>(d_cf32) % 16 == 0;
     int64_t k = ctx->bank_repeat_variant;
-    if (k == 0)
-        k = b.nstreams <= 2048 ? 1 : b.nstreams <= 8192 ? 2 : b.nstreams <= 32768 ? 4 : 100;
+    if (k == 0) {
+        if (reg_ok)
+            k = b.nstreams <= 2048 ? 201 : b.nstreams <= 16384 ? 202 : 204;
+        else
+            k = b.nstreams <= 2048 ? 1 : b.nstreams <= 8192 ? 2 : b.nstreams <= 32768 ? 4 : 100;
+    }
+    if (k >= 200 && !reg_ok)
+        return ctx->invalid("the register schedules need an even period and a 16-byte aligned CF32 buffer");
     switch (k) {
     case 1: warp_variant(bank_repeat_warp_kernel<1>, 1); break;
     case 2: warp_variant(bank_repeat_warp_kernel<2>, 2); break;
     case 4: warp_variant(bank_repeat_warp_kernel<4>, 4); break;
     case 8: warp_variant(bank_repeat_warp_kernel<8>, 8); break;
     case 100: group_variant(bank_repeat_kernel); break;
-    default: return ctx->invalid("bank_repeat_variant must be 0 (auto), 1, 2, 4, 8 or 100");
+    case 201: reg_variant(bank_repeat_reg_kernel<1, IdentityHook>, 1); break;
+    case 202: reg_variant(bank_repeat_reg_kernel<2, IdentityHook>, 2); break;
+    case 204: reg_variant(bank_repeat_reg_kernel<4, IdentityHook>, 4); break;
+    default: return ctx->invalid("bank_repeat_variant must be 0 (auto), 1, 2, 4, 8, 100, 201, 202 or 204");
     }
     SX_CUDA(ctx, cudaGetLastError());
     ctx->launches += 1;
     ctx->frames_rx += uint64_t(b.nstreams) * b.period;
     ctx->frames_tx += uint64_t(b.nstreams) * b.period;
+    return SXGPU_OK;
+}
+
+int sxgpu_bank_ingest(sxgpu_bank *bank, uint32_t first_stream, uint32_t nstreams, const void *i2s,
+                      sxgpu_stream stream)
+{
+    if (!bank)
+        return SXGPU_ERR_INVALID;
+    sxgpu_ctx *ctx = bank->ctx;
+    const BankState &b = bank->st;
+    if (nstreams == 0) {
+        bank->external_capture = true;
+        return SXGPU_OK;
+    }
+    if (!i2s || uint64_t(first_stream) + nstreams > b.nstreams)
+        return ctx->invalid("ingest range outside the bank");
+    SX_CUDA(ctx, cudaSetDevice(ctx->device));
+    // The capture slots of consecutive streams are contiguous: one copy, from wherever the frames
+    // are (pinned or pageable host memory, or device memory).
+    SX_CUDA(ctx, cudaMemcpyAsync(b.capture_stage + size_t(first_stream) * b.period * 8, i2s,
+                                 size_t(nstreams) * b.period * 8, cudaMemcpyDefault, bank_stream(bank, stream)));
+    if (!classify_pointer(ctx, i2s).on_device)
+        ctx->h2d_bytes += uint64_t(nstreams) * b.period * 8;
+    bank->external_capture = true;
+    return SXGPU_OK;
+}
+
+int sxgpu_bank_drain(sxgpu_bank *bank, uint32_t first_stream, uint32_t nstreams, size_t nframes, void *i2s,
+                     sxgpu_stream stream)
+{
+    if (!bank)
+        return SXGPU_ERR_INVALID;
+    sxgpu_ctx *ctx = bank->ctx;
+    const BankState &b = bank->st;
+    if (nstreams == 0 || nframes == 0)
+        return SXGPU_OK;
+    if (!i2s || uint64_t(first_stream) + nstreams > b.nstreams || nframes > b.ring)
+        return ctx->invalid("drain range outside the bank or longer than a ring");
+    SX_CUDA(ctx, cudaSetDevice(ctx->device));
+    HostPtrInfo di = classify_pointer(ctx, i2s);
+    if (!di.device_alias || di.foreign_device || reinterpret_cast<uintptr_t>(di.device_alias) % 8)
+        return ctx->invalid("drain destination must be device memory or pinned host memory, 8-byte aligned");
+    bank_drain_kernel<<<per_warp_grid(ctx, nstreams, 256), 256, 0, bank_stream(bank, stream)>>>(
+        b, first_stream, nstreams, uint32_t(nframes), static_cast<char *>(di.device_alias));
+    SX_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+    if (!di.on_device)
+        ctx->d2h_bytes += uint64_t(nstreams) * nframes * 8;
+    return SXGPU_OK;
+}
+
+int sxgpu_bank_device_view(sxgpu_bank *bank, void *out, size_t out_bytes, int *external_capture)
+{
+    if (!bank || !out)
+        return SXGPU_ERR_INVALID;
+    if (out_bytes != sizeof(BankState))
+        return bank->ctx->invalid("sxgpu_bank_device_view: size mismatch (header and library disagree)");
+    std::memcpy(out, &bank->st, sizeof(BankState));
+    if (external_capture)
+        *external_capture = bank->external_capture ? 1 : 0;
     return SXGPU_OK;
 }
 

@@ -31,6 +31,8 @@ SIGNATURES = {
     "sxh_read": (C.c_int, [_P, _P, _P, _S, C.POINTER(C.c_int), C.POINTER(_LL), C.c_long]),
     "sxh_write": (C.c_int, [_P, _P, _P, _S, C.POINTER(C.c_int), _LL, C.c_long]),
     "sxh_set_sample_rate": (C.c_int, [_P, C.c_int, C.c_double]),
+    "sxh_read_setting": (C.c_char_p, [_P, C.c_char_p]),
+    "sxh_write_setting": (C.c_int, [_P, C.c_char_p, C.c_char_p]),
     "sxh_bench_pairs": (C.c_int, [_P, _P, _P, _P, _S, C.c_int, _LL, C.POINTER(C.c_double), _P]),
     "sxh_bench_reads": (C.c_int, [_P, _P, _P, _S, C.c_int, C.POINTER(C.c_double)]),
     "sxh_bench_writes": (C.c_int, [_P, _P, _P, _S, C.c_int, C.POINTER(C.c_double)]),
@@ -116,6 +118,17 @@ class Device:
     def write(self, stream, addr: int, n: int, flags: int = 0, time_ns: int = 0, timeout_us: int = 1000000):
         f = C.c_int(flags)
         return self._ck(self.lib.sxh_write(self.p, stream, addr, n, C.byref(f), time_ns, timeout_us), "writeStream")
+
+    def read_setting(self, key: str) -> str:
+        return (self.lib.sxh_read_setting(self.p, key.encode()) or b"").decode()
+
+    def write_setting(self, key: str, value: str):
+        self._ck(self.lib.sxh_write_setting(self.p, key.encode(), value.encode()), "writeSetting")
+
+    def counter(self, name: str) -> int:
+        """A counter of the sxgpu context behind a product device (0 for any other build)."""
+        v = self.read_setting("sxgpu." + name)
+        return int(v) if v.isdigit() else 0
 
     # ---- the ALSA stand-in behind the device -----------------------------------------------------
     def capture_table(self, addr: int, nframes: int):

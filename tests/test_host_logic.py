@@ -22,6 +22,8 @@ def host():
     lib.sxplan_place_tx_block.argtypes = [C.c_int64, C.c_long, C.c_int, C.c_int64, C.c_ulong, C.POINTER(C.c_int),
                                           C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.sxplan_place_tx_block.restype = None
+    lib.sxplan_clock_after_forward.argtypes = [C.c_int64] * 5
+    lib.sxplan_clock_after_forward.restype = C.c_int64
     return lib
 
 
@@ -101,3 +103,100 @@ def test_parallel_bounce_copier(tmp_path, helpers):
     assert run.returncode == 0, run.stdout + run.stderr
     assert "ThreadSanitizer" not in run.stderr
     assert f"{helpers} helpers" in run.stdout
+
+
+@pytest.mark.parametrize("helpers", [0, 2])
+def test_host_pipeline_pieces(tmp_path, helpers):
+    """csrc/host/par_copy.hpp: the chunk schedule, and the owner/sidekick handshake of the *_host
+    pipeline (including an aborted run) -- under ThreadSanitizer when the toolchain links it."""
+    import os
+    import subprocess
+    from sxxcvr_b200 import _build
+    src = _build.ROOT / "tests" / "native" / "pipeline_test.cpp"
+    exe = tmp_path / "pipeline_test"
+    base = [os.environ.get("CXX", "g++"), "-std=c++17", "-g", "-Wall", "-Wextra", "-pthread",
+            "-I", str(_build.CSRC), str(src), "-o", str(exe)]
+    tsan = subprocess.run(base + ["-O1", "-fsanitize=thread"], capture_output=True, text=True)
+    if tsan.returncode != 0:
+        subprocess.run(base + ["-O2"], check=True, capture_output=True, text=True)
+    run = subprocess.run([str(exe), str(helpers)], capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0, run.stdout + run.stderr
+    assert "ThreadSanitizer" not in run.stderr
+    assert "pipeline ok" in run.stdout
+
+
+def forward_loop(clock, pos, target, ring, period):
+    """The reference's forward-and-wait loop (SoapySX.cpp:1043-1073) over the virtual-clock model
+    of the stream bank, one turn at a time: what sxplan::clock_after_forward states in closed form."""
+    gap = target - pos
+    while gap > 0:
+        fits = max(clock + ring - pos, 0)
+        if gap < fits:
+            moved = gap
+        else:
+            moved = fits
+            room_after = clock + ring - (pos + moved)
+            if room_after < period:
+                clock += period - room_after
+        pos += moved
+        gap -= moved
+    return clock
+
+
+@settings(max_examples=2000, deadline=None)
+@given(st.integers(0, 10**7), st.integers(-70000, 200000), st.integers(0, 600000),
+       st.sampled_from([1, 3, 256, 1000, 4096, 65536]))
+def test_forward_clock_closed_form_matches_the_loop(host, clock, lead, gap, period):
+    ring = 65536 // period * period
+    pos = clock + lead                      # the write pointer leads (or trails) the clock
+    target = pos + gap
+    assert host.sxplan_clock_after_forward(clock, pos, target, ring, period) == forward_loop(clock, pos, target, ring, period)
+
+
+def test_forward_clock_takes_a_garbage_timestamp_in_constant_time(host):
+    import time
+    t0 = time.perf_counter()
+    c = host.sxplan_clock_after_forward(0, 0, 10**15, 65536, 256)
+    assert time.perf_counter() - t0 < 0.01
+    assert c == 10**15 - 65536 + 256 - (10**15 - 65536) % 256 or c > 0      # lands within a period of target - ring
+    assert 0 <= (10**15 - 65536 + 256) - c < 256
+
+
+def test_stub_devices_on_separate_threads_do_not_share_a_lock():
+    """The ALSA stand-in locks per clock group: two devices driven from two threads make progress
+    independently, and a device's RX and TX threads (one clock group) still see a consistent clock."""
+    import threading
+    import numpy as np
+    from sxxcvr_b200 import _build
+    if not sxstream.REF_LIB.exists():
+        pytest.skip("needs oracle/_ref (the only driver=sx device that runs without a GPU)")
+    h = sxstream.Harness(sxstream.REF_LIB)
+    results = {}
+
+    def run(k):
+        with h.device() as d:
+            d.set_rate(75000.0)
+            h.lib.sx_alsa_set_capture_seed(d.cap, 100 + k)
+            rx, tx = d.setup(sxstream.RX), d.setup(sxstream.TX, args="threshold=0")
+            d.activate(rx), d.activate(tx)
+            crcs = []
+            for _ in range(300):
+                r, fl, t, buf = d.read(rx, 256)
+                w = d.write(tx, buf, 256, sxstream.HAS_TIME, t + 10_240_000)
+                crcs.append((r, t, sxstream.crc(buf), w))
+            results[k] = (crcs, d.pointers())
+
+    ts = [threading.Thread(target=run, args=(k,)) for k in range(4)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    serial = {}
+    for k in range(4):
+        saved = dict(results)
+        run(k)
+        serial[k] = results[k]
+        results.update(saved)
+    for k in range(4):
+        assert results[k] == serial[k], k
+        assert results[k][1] == [300 * 256, 300 * 256, results[k][1][2], 299 * 256 + 768 + 256]
