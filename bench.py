@@ -480,15 +480,22 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
     sustained = None
     if args.min_seconds > 0:
         per_step = max(step_ms, 1e-3) * 1e-3
-        nsus = max(args.steps, int(args.min_seconds / per_step) + 1)
+        batch = max(args.steps, int(0.25 * args.min_seconds / per_step) + 1)
         sampler2 = ClockSampler(local_rank, bus)
         barrier()
         sampler2.start()
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record(side)
-        for _ in range(nsus):
-            rx()
-            tx()
+        nsus, t_start = 0, time.perf_counter()
+        while True:                      # whole batches until the wall clock says enough
+            for _ in range(batch):
+                rx()
+                tx()
+            nsus += batch
+            side.synchronize()
+            enough = max_over_ranks(1.0 if time.perf_counter() - t_start >= args.min_seconds else 0.0)
+            if enough > 0:               # every rank runs the same number of batches
+                break
         s1.record(side)
         barrier()
         sus_ms = max_over_ranks(s0.elapsed_time(s1) / nsus)
@@ -569,7 +576,8 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
             row["product_pin1_us"] = pair_us(product, "pin", one)
             row["product_library_pinned_us"] = pair_us(product, "pinned", one)
             if n <= 4096:
-                row["product_lowlatency_us"] = pair_us(product, "pageable", one + ", lowlatency=1")
+                row["product_lowlatency1_us"] = pair_us(product, "pageable", one + ", lowlatency=1")
+                row["product_lowlatency0_us"] = pair_us(product, "pageable", one + ", lowlatency=0")
             if ref is not None:
                 row["reference_us"] = pair_us(ref, "pageable")
             for k in list(row):

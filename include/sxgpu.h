@@ -174,6 +174,14 @@ int sxgpu_bank_write(sxgpu_bank *bank, const void *d_cf32, int flags, const long
  * each stream's three stages run back to back on one warp, so the intermediate reads are served
  * from L2 and only the writes reach HBM. */
 int sxgpu_bank_repeat(sxgpu_bank *bank, void *d_cf32, long long rx_time_offset_ns, sxgpu_stream stream);
+/* The same iteration split around DSP of the caller's own (the process(buf) of
+ * example/linear_repeater.py:62): begin = sxgpu_bank_read with the CF32 block marked persisting
+ * in L2 for `stream`; the caller then launches its kernel(s) on that stream, in place on d_cf32;
+ * end = sxgpu_bank_write(bank, d_cf32, SOAPY_SDR_HAS_TIME, NULL, rx_time_offset_ns) and the mark
+ * is lifted.  DSP that is memoryless per sample can instead be compiled INTO the one-launch
+ * iteration: include/sx_hook.cuh. */
+int sxgpu_bank_repeat_begin(sxgpu_bank *bank, void *d_cf32, sxgpu_stream stream);
+int sxgpu_bank_repeat_end(sxgpu_bank *bank, const void *d_cf32, long long rx_time_offset_ns, sxgpu_stream stream);
 /* Frames from outside instead of the synthetic capture: copy one period of I2S frames for each
  * of `nstreams` consecutive streams, i2s[stream - first_stream][period], into their capture
  * slots.  `i2s` may be pinned or pageable host memory or device memory; the copy is ordered on

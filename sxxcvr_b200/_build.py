@@ -24,7 +24,9 @@ SOAPY_LIB = LIB / "libsxsoapy.so"
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC,-Wall",
+    # -ffp-contract=off: the host side of sx_time.h must round exactly like the device side's
+    # explicit _rn intrinsics on any host (GCC contracts by default on aarch64)
+    "-Xcompiler", "-fPIC,-Wall,-ffp-contract=off",
     "-shared",
 ]
 
@@ -72,7 +74,7 @@ def build_soapy_module(force: bool = False) -> Path:
     deps = SOAPY_SOURCES + list((CSRC / "shim").rglob("*.h*")) + [GPU_LIB, CSRC / "host" / "SoapySXB200.hpp"]
     if force or _stale(SOAPY_LIB, deps):
         _run([
-            os.environ.get("CXX", "g++"), "-std=c++17", "-O2", "-Wall", "-Wextra", "-fPIC", "-shared",
+            os.environ.get("CXX", "g++"), "-std=c++17", "-O2", "-ffp-contract=off", "-Wall", "-Wextra", "-fPIC", "-shared",
             "-Wl,-Bsymbolic", "-pthread",
             "-I", CSRC / "shim", "-I", ROOT / "include", "-I", CSRC,
             "-o", SOAPY_LIB, *SOAPY_SOURCES,
@@ -82,6 +84,7 @@ def build_soapy_module(force: bool = False) -> Path:
 
 
 EXAMPLE_BIN = LIB / "sx_repeater"
+HOOK_EXAMPLE_LIB = LIB / "libsxhook_example.so"
 
 
 def build_examples(force: bool = False) -> Path:
@@ -95,7 +98,19 @@ def build_examples(force: bool = False) -> Path:
     return EXAMPLE_BIN
 
 
+def build_hook_example(force: bool = False) -> Path:
+    """examples/repeater_hook.cu: user DSP compiled into the fused bank iteration (include/sx_hook.cuh)."""
+    build_gpu_library(force)
+    src = ROOT / "examples" / "repeater_hook.cu"
+    deps = [src, ROOT / "include" / "sx_hook.cuh", CSRC / "sx_bank.cuh", CSRC / "sx_kernels.cuh", GPU_LIB]
+    if force or _stale(HOOK_EXAMPLE_LIB, deps):
+        _run([_find_nvcc(), *NVCC_FLAGS, "-o", HOOK_EXAMPLE_LIB, src, "-L", LIB, "-lsxgpu",
+              "-Xlinker", "-rpath,$ORIGIN"])
+    return HOOK_EXAMPLE_LIB
+
+
 def build_all(force: bool = False) -> None:
     build_gpu_library(force)
     build_soapy_module(force)
     build_examples(force)
+    build_hook_example(force)

@@ -69,6 +69,8 @@ SIGNATURES = {
     "sxgpu_bank_read": (C.c_int, [_P, _P, _P]),
     "sxgpu_bank_write": (C.c_int, [_P, _P, C.c_int, _P, C.c_longlong, _P]),
     "sxgpu_bank_repeat": (C.c_int, [_P, _P, C.c_longlong, _P]),
+    "sxgpu_bank_repeat_begin": (C.c_int, [_P, _P, _P]),
+    "sxgpu_bank_repeat_end": (C.c_int, [_P, _P, C.c_longlong, _P]),
     "sxgpu_bank_ingest": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, _P]),
     "sxgpu_bank_drain": (C.c_int, [_P, C.c_uint32, C.c_uint32, _S, _P, _P]),
     "sxgpu_bank_device_view": (C.c_int, [_P, _P, _S, C.POINTER(C.c_int)]),
@@ -303,6 +305,13 @@ class Bank:
     def repeat(self, d_cf32, rx_time_offset_ns=0, stream=None):
         """read(d_cf32) then write(d_cf32, HAS_TIME, rx time + offset) in one launch."""
         self.ctx.check(self.lib.sxgpu_bank_repeat(self.handle, d_cf32, rx_time_offset_ns, stream), "sxgpu_bank_repeat")
+
+    def repeat_begin(self, d_cf32, stream=None):
+        self.ctx.check(self.lib.sxgpu_bank_repeat_begin(self.handle, d_cf32, stream), "sxgpu_bank_repeat_begin")
+
+    def repeat_end(self, d_cf32, rx_time_offset_ns=0, stream=None):
+        self.ctx.check(self.lib.sxgpu_bank_repeat_end(self.handle, d_cf32, rx_time_offset_ns, stream),
+                       "sxgpu_bank_repeat_end")
 
     def ingest(self, first_stream, nstreams, i2s, stream=None):
         """One period of I2S frames per stream from outside (host or device address)."""

@@ -184,10 +184,15 @@ SoapySXB200::SoapySXB200(const SoapySDR::Kwargs &args)
     // detection is inconclusive: 38.4 MHz (SoapySX.cpp:656-659).  clock=32e6 selects the
     // other board variant.  The initial rate is masterClock/256 (:662).
     cs16_enabled_ = kwarg(args, "cs16", "0") == "1";
-    // lowlatency=1: period-sized blocks (up to 4096 frames) are converted by a resident kernel
-    // that is rung through a doorbell in pinned memory -- no launch, no stream sync per call.
-    if (kwarg(args, "lowlatency", "0") == "1")
-        sxgpu_set_option(gpu_, "resident_max_frames", 4096);
+    // Period-sized blocks are converted by a resident kernel that is rung through a doorbell in
+    // pinned memory -- no launch, no stream sync per call (csrc/sx_resident.cuh).  By default for
+    // calls of up to 1024 frames, where it saves a third of the call (the reference's period is
+    // 256, SoapySX.cpp:451); lowlatency=1 extends it to 4096 frames, lowlatency=0 turns it off
+    // (e.g. when the GPU is time-sliced between processes: the kernel holds its slot for up to
+    // 20 ms at a time while a stream is calling in).
+    const std::string lowlatency = kwarg(args, "lowlatency", "");
+    if (lowlatency != "0")
+        sxgpu_set_option(gpu_, "resident_max_frames", lowlatency == "1" ? 4096 : 1024);
     // sxgpu.<option>=<integer>: any tuning option of the C ABI (include/sxgpu.h), e.g.
     // sxgpu.bounce_threads=2 when several devices share the host's cores.
     for (const auto &kv : args) {

@@ -149,7 +149,10 @@ private:
     double sample_rate_;
     mutable std::recursive_mutex settings_mutex_;
     uint32_t frequency_word_[2] = {0, 0}; // indexed by direction
-    double gain_[2][2] = {{0, 0}, {0, 0}};
+    // [0] = TX {DAC, MIXER}, [1] = RX {LNA, PGA}.  Start where the reference's register defaults
+    // read back (init_registers, SoapySX.cpp:146-176: 0x08 = 0x2E -> DAC 6 dB, MIXER 28 dB;
+    // 0x0C = 0x3F -> LNA 48 dB, PGA 30 dB), so getGain before any setGain agrees too.
+    double gain_[2][2] = {{6.0, 28.0}, {48.0, 30.0}};
     std::string antenna_[2];
     std::string pa_mode_ = "AUTO";
 

@@ -8,6 +8,11 @@
 // the CPU, under ThreadSanitizer where the toolchain has it.
 #pragma once
 
+#if defined(__x86_64__) || defined(_M_X64)
+#include <emmintrin.h>
+#define SXHOST_HAVE_NT_STORES 1
+#endif
+
 #include <condition_variable>
 #include <cstddef>
 #include <cstdint>
@@ -18,14 +23,52 @@
 
 namespace sxhost {
 
+// memcpy whose stores bypass the cache (x86: MOVNTDQ through the write-combining buffers).  A
+// bounce copy writes a destination nobody reads soon -- the pinned staging the copy engine will
+// fetch by DMA, or a caller buffer far larger than the caches -- so allocating its lines costs a
+// read of the destination from DRAM for nothing: 3 bytes of memory traffic per byte copied
+// instead of 2.  On a host whose memory bandwidth is what limits the pageable path, that is
+// the difference.  Falls back to memcpy for small or oddly aligned pieces and off x86.
+inline void stream_copy(void *dst, const void *src, size_t bytes)
+{
+#if defined(SXHOST_HAVE_NT_STORES)
+    if (bytes >= 4096) {
+        char *d = static_cast<char *>(dst);
+        const char *s = static_cast<const char *>(src);
+        const size_t head = (64 - (reinterpret_cast<uintptr_t>(d) & 63)) & 63;
+        if (head) {
+            std::memcpy(d, s, head);
+            d += head, s += head, bytes -= head;
+        }
+        const size_t lines = bytes / 64;
+        for (size_t i = 0; i < lines; i++) {
+            const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i *>(s));
+            const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i *>(s + 16));
+            const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i *>(s + 32));
+            const __m128i e = _mm_loadu_si128(reinterpret_cast<const __m128i *>(s + 48));
+            _mm_stream_si128(reinterpret_cast<__m128i *>(d), a);
+            _mm_stream_si128(reinterpret_cast<__m128i *>(d + 16), b);
+            _mm_stream_si128(reinterpret_cast<__m128i *>(d + 32), c);
+            _mm_stream_si128(reinterpret_cast<__m128i *>(d + 48), e);
+            d += 64, s += 64;
+        }
+        _mm_sfence(); // the streamed lines are globally visible before anyone is told the copy is done
+        std::memcpy(d, s, bytes - lines * 64);
+        return;
+    }
+#endif
+    std::memcpy(dst, src, bytes);
+}
+
 class ParallelCopier {
 public:
     // Copies below this size are done by the caller alone: waking helpers costs tens of
     // microseconds, a single thread moves 1 MiB in about a hundred.
     static constexpr size_t kMinParallelBytes = size_t(2) << 20;
 
-    // `helpers` threads are started on first use and parked between copies.
-    explicit ParallelCopier(unsigned helpers) : helpers_(helpers) {}
+    // `helpers` threads are started on first use and parked between copies.  `streaming`: use
+    // cache-bypassing stores (stream_copy) for every piece.
+    explicit ParallelCopier(unsigned helpers, bool streaming = false) : helpers_(helpers), streaming_(streaming) {}
 
     ~ParallelCopier()
     {
@@ -42,13 +85,14 @@ public:
     ParallelCopier &operator=(const ParallelCopier &) = delete;
 
     unsigned helpers() const { return helpers_; }
+    bool streaming() const { return streaming_; }
 
     // memcpy(dst, src, bytes); returns when every byte has been copied.  One copy at a time
     // (the caller serialises: the host pipeline holds the context's host mutex).
     void copy(void *dst, const void *src, size_t bytes)
     {
         if (helpers_ == 0 || bytes < kMinParallelBytes) {
-            std::memcpy(dst, src, bytes);
+            move(dst, src, bytes);
             return;
         }
         start_threads();
@@ -76,7 +120,15 @@ private:
         const size_t lo = size_t(part) * slice_;
         if (lo >= bytes_)
             return;
-        std::memcpy(dst_ + lo, src_ + lo, bytes_ - lo < slice_ ? bytes_ - lo : slice_);
+        move(dst_ + lo, src_ + lo, bytes_ - lo < slice_ ? bytes_ - lo : slice_);
+    }
+
+    void move(void *dst, const void *src, size_t bytes) const
+    {
+        if (streaming_)
+            stream_copy(dst, src, bytes);
+        else
+            std::memcpy(dst, src, bytes);
     }
 
     void start_threads()
@@ -106,6 +158,7 @@ private:
     }
 
     const unsigned helpers_;
+    const bool streaming_;
     std::vector<std::thread> threads_;
     std::mutex mutex_;
     std::condition_variable wake_, done_;

@@ -60,8 +60,21 @@ struct BankState {
     long long *tx_gap_length;
 
     char *capture_stage; // [nstreams][period] I2S frames
-    char *playback_ring; // [nstreams][ring]   I2S frames
+    char *playback_ring; // [ring / period][nstreams][period] I2S frames, see ring_frame()
 };
+
+// Where frame `pos` of stream s's playback ring lives.  Each stream has a ring of `ring` frames
+// (a whole number of periods), but the rings are stored time-major: period-long slice
+// (pos / period) mod (ring / period) of EVERY stream is contiguous.  Streams that run in
+// lock-step -- the normal case: one sample clock -- then write one dense region per iteration
+// (nstreams x period x 8 bytes) instead of nstreams regions ring x 8 bytes apart, which at
+// 65536 streams meant one 2 KiB write per 512 KiB of a 32 GiB arena: a TLB miss and a DRAM row
+// per write.  A block that does not start on a period boundary spans two slices.
+__device__ __forceinline__ char *ring_frame(const BankState &b, uint64_t s, uint64_t pos)
+{
+    const uint64_t slice = (pos / b.period) % (b.ring / b.period);
+    return b.playback_ring + ((slice * b.nstreams + s) * b.period + pos % b.period) * 8;
+}
 
 constexpr int SX_HAS_TIME = 1 << 2; // SOAPY_SDR_HAS_TIME
 
@@ -237,7 +250,6 @@ __device__ __forceinline__ void bank_play_block(const BankState &b, uint64_t s, 
 {
     if (at < 0)
         return;
-    char *ring = b.playback_ring + s * b.ring * 8;
 
     // ALSA plays zeros for regions the application skipped (silence_size = boundary, :493-496).
     if (gap > 0) {
@@ -248,24 +260,24 @@ __device__ __forceinline__ void bank_play_block(const BankState &b, uint64_t s, 
         Pack<2> zero;
         zero.w[0] = zero.w[1] = 0;
         for (long long i = lane; i < gap; i += 32)
-            st_stream<8>(ring + size_t(uint64_t(start + i) % b.ring) * 8, zero);
+            st_stream<8>(ring_frame(b, s, uint64_t(start + i)), zero);
         // A gap of a whole lap or more silences the slots the block is about to take.
         __syncwarp();
     }
 
-    // The block may straddle the end of the ring: at most two contiguous spans.
-    const uint64_t offset = uint64_t(at) % b.ring;
-    const uint64_t first_span = (b.ring - offset < b.period) ? b.ring - offset : b.period;
+    // The block may straddle a period boundary of the ring: at most two contiguous spans.
+    const uint64_t into = uint64_t(at) % b.period;
+    const uint64_t first_span = into ? b.period - into : b.period;
     BlockDesc d;
     d.thr2 = b.thr2;
     d.reserved = 0;
     d.src = cf32_in + s * b.period * 8;
-    d.dst = ring + offset * 8;
+    d.dst = ring_frame(b, s, uint64_t(at));
     d.length = first_span;
     convert_span<TxCf32>(d, 0, first_span, lane, 32);
     if (first_span < b.period) {
         d.src = cf32_in + (s * b.period + first_span) * 8;
-        d.dst = ring;
+        d.dst = ring_frame(b, s, uint64_t(at) + first_span);
         d.length = b.period - first_span;
         convert_span<TxCf32>(d, 0, d.length, lane, 32);
     }
@@ -342,8 +354,8 @@ __device__ __forceinline__ void bank_repeat_stream(const BankState &b, uint64_t 
 // back, so a stream costs its plan's one round trip (the three counters) and then only stores.
 // `capture_in_slot`: the capture slot was filled from outside (sxgpu_bank_ingest); it is read
 // (one round trip, all vectors in flight at once) instead of being produced here.
-// Needs an even period and 16-byte aligned CF32 blocks; a ring position that is odd or wraps
-// inside the block falls back to frame-wide stores for the ring side.
+// Needs an even period and 16-byte aligned CF32 blocks; a block that does not start on a period
+// boundary of the ring falls back to frame-wide stores for the ring side.
 template <class Hook>
 __device__ __forceinline__ void bank_repeat_stream_reg(const BankState &b, uint64_t s, char *cf32, uint64_t first,
                                                        long long at, long long gap, long long start, uint32_t lane,
@@ -351,7 +363,6 @@ __device__ __forceinline__ void bank_repeat_stream_reg(const BankState &b, uint6
 {
     char *slot = b.capture_stage + s * b.period * 8;
     char *cf = cf32 + s * b.period * 8;
-    char *ring = b.playback_ring + s * b.ring * 8;
     const uint32_t nvec = b.period / 2;
 
     if (at >= 0 && gap > 0) { // silence for a forwarded-over region (rare: late start, underrun)
@@ -363,11 +374,13 @@ __device__ __forceinline__ void bank_repeat_stream_reg(const BankState &b, uint6
         Pack<2> zero;
         zero.w[0] = zero.w[1] = 0;
         for (long long i = lane; i < g; i += 32)
-            st_stream<8>(ring + size_t(uint64_t(st0 + i) % b.ring) * 8, zero);
+            st_stream<8>(ring_frame(b, s, uint64_t(st0 + i)), zero);
         __syncwarp(); // a gap of a lap or more silences the slots the block is about to take
     }
-    const uint64_t offset = at >= 0 ? uint64_t(at) % b.ring : 0;
-    const bool ring_vec = at >= 0 && (offset & 1) == 0 && offset + b.period <= b.ring;
+    // Streams in lock-step write whole period slices of the ring: 16-byte stores.  A block that
+    // starts inside a slice goes frame by frame.
+    const bool ring_vec = at >= 0 && uint64_t(at) % b.period == 0;
+    char *ring = ring_vec ? ring_frame(b, s, uint64_t(at)) : nullptr;
 
     constexpr int U = 4;
     for (uint32_t base = 0; base < nvec; base += 32 * U) {
@@ -405,12 +418,12 @@ __device__ __forceinline__ void bank_repeat_stream_reg(const BankState &b, uint6
                 st_stream<16>(slot + size_t(v) * 16, cap[u]);
             st_stream<16>(cf + size_t(v) * 16, mid[u]);
             if (ring_vec) {
-                st_stream<16>(ring + (offset + 2 * size_t(v)) * 8, out[u]);
+                st_stream<16>(ring + size_t(v) * 16, out[u]);
             } else if (at >= 0) {
                 Pack<2> f0, f1;
                 f0.w[0] = out[u].w[0], f0.w[1] = out[u].w[1], f1.w[0] = out[u].w[2], f1.w[1] = out[u].w[3];
-                st_stream<8>(ring + size_t((offset + 2 * uint64_t(v)) % b.ring) * 8, f0);
-                st_stream<8>(ring + size_t((offset + 2 * uint64_t(v) + 1) % b.ring) * 8, f1);
+                st_stream<8>(ring_frame(b, s, uint64_t(at) + 2 * uint64_t(v)), f0);
+                st_stream<8>(ring_frame(b, s, uint64_t(at) + 2 * uint64_t(v) + 1), f1);
             }
         }
     }
@@ -541,17 +554,24 @@ __global__ void bank_drain_kernel(BankState b, uint32_t first_stream, uint32_t c
     for (uint64_t j = uint64_t(blockIdx.x) * warps_per_cta + (threadIdx.x >> 5); j < count; j += nwarps) {
         const uint64_t s = first_stream + j;
         const long long end = b.tx_position[s];
-        const char *ring = b.playback_ring + s * b.ring * 8;
         char *out = dst + j * uint64_t(nframes) * 8;
         for (uint32_t i = lane; i < nframes; i += 32) {
             const long long p = end - (long long)nframes + i;
             Pack<2> f;
             f.w[0] = f.w[1] = 0; // before the stream's first frame: silence
             if (p >= 0)
-                f = ld_stream<8>(ring + size_t(uint64_t(p) % b.ring) * 8);
+                f = ld_stream<8>(ring_frame(b, s, uint64_t(p)));
             st_stream<8>(out + size_t(i) * 8, f);
         }
     }
+}
+
+// nframes frames of ONE stream's ring starting at counter value `position`, gathered into a
+// contiguous buffer (sxgpu_bank_playback: tests and inspection, not a data path).
+__global__ void bank_gather_kernel(BankState b, uint32_t stream, long long position, uint64_t nframes, char *dst)
+{
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nframes; i += uint64_t(gridDim.x) * blockDim.x)
+        st_stream<8>(dst + i * 8, ld_stream<8>(ring_frame(b, stream, uint64_t(position) + i)));
 }
 
 __global__ void bank_advance_kernel(BankState b, long long frames)

@@ -669,12 +669,15 @@ __global__ void batch_slice_kernel(const BlockDesc *__restrict__ blocks, uint32_
 // end: 1 MiB - 64 MiB each) in ONE launch at the large-block kernel's throughput.
 //
 // Every block is cut into tiles of TILE frames; tile_start[b] = number of tiles in blocks
-// 0..b-1 (exclusive prefix sum, tile_start[nblocks] = total).  Persistent CTAs take global
-// tiles c, c + G, c + 2G, ... exactly like bulk_convert_kernel takes the tiles of one block,
+// 0..b-1 (exclusive prefix sum, tile_start[nblocks] = total).  Persistent CTAs walk the tiles
+// of all blocks the way bulk_convert_kernel walks the tiles of one block,
 // and run the same pipeline (bulk loads into a STAGES-deep shared-memory ring on mbarriers,
-// shared -> shared conversion by all threads, bulk stores gated by wait_group.read).  The
-// producer thread finds a tile's block by walking tile_start forward (binary search once, for
-// its first tile) and leaves a small record per stage for the consumers.
+// shared -> shared conversion by all threads, bulk stores gated by wait_group.read), except
+// that a CTA owns one contiguous range of tiles: the producer thread finds its first tile's block
+// by binary search, keeps that block's descriptor in registers, has the next block's already
+// requested, and so reads the descriptor list only when a block ends -- a per-tile lookup (two
+// dependent loads, ~1 us from L2) on the thread the whole CTA waits for cost 10-80 % of the
+// throughput (profiles/r02_summary.md).  It leaves a small record per stage for the consumers.
 //
 // A block whose buffers are not 16-byte aligned cannot be moved by bulk copies: its tiles are
 // converted with ordinary vector accesses by the same CTA ("direct" tiles), in the same pass.
@@ -696,22 +699,63 @@ struct TileRecord {
     uint32_t pad;
 };
 
-template <int TILE>
-__device__ __forceinline__ void batch_tile_record(const BatchBulkArgs &a, uint64_t t, uint32_t &b, TileRecord &rec,
-                                                  int src_frame_bytes, int dst_frame_bytes)
+// Producer-side cursor over the blocks of a batch: the block the current tile belongs to, held
+// in registers, and the NEXT non-trivial facts (next block's descriptor and end) already
+// requested, so that crossing a block boundary costs no round trip to memory at that moment.
+struct BatchCursor {
+    uint32_t blk;                 // current block
+    unsigned long long first, end; // its tiles are [first, end)
+    BlockDesc desc;
+    BlockDesc next_desc;          // blocks[blk + 1] (prefetched; junk past the last block)
+    unsigned long long next_end;  // tile_start[blk + 2]
+};
+
+__device__ __forceinline__ void batch_cursor_prefetch(const BatchBulkArgs &a, BatchCursor &c)
 {
-    while (b + 1 < a.nblocks && a.tile_start[b + 1] <= t) // also steps over empty blocks
-        b++;
-    const BlockDesc d = a.blocks[b];
-    const uint64_t lo = (t - a.tile_start[b]) * uint64_t(TILE);
-    const uint64_t left = d.length - lo;
+    if (c.blk + 1 < a.nblocks) {
+        c.next_desc = a.blocks[c.blk + 1];
+        c.next_end = a.tile_start[c.blk + 2];
+    }
+}
+
+__device__ __forceinline__ void batch_cursor_seek(const BatchBulkArgs &a, BatchCursor &c, unsigned long long t)
+{
+    // binary search: the last block whose first tile is <= t (steps over empty blocks)
+    uint32_t lo = 0, hi = a.nblocks - 1;
+    while (lo < hi) {
+        const uint32_t mid = lo + (hi - lo + 1) / 2;
+        if (a.tile_start[mid] <= t)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    c.blk = lo;
+    c.first = a.tile_start[lo];
+    c.end = a.tile_start[lo + 1];
+    c.desc = a.blocks[lo];
+    batch_cursor_prefetch(a, c);
+}
+
+template <int TILE>
+__device__ __forceinline__ void batch_tile_record(const BatchBulkArgs &a, unsigned long long t, BatchCursor &c,
+                                                  TileRecord &rec, int src_frame_bytes, int dst_frame_bytes)
+{
+    while (t >= c.end) { // next block (tiles arrive in increasing order); empty blocks fall through
+        c.blk++;
+        c.first = c.end;
+        c.end = c.next_end;
+        c.desc = c.next_desc;
+        batch_cursor_prefetch(a, c);
+    }
+    const uint64_t lo = (t - c.first) * uint64_t(TILE);
+    const uint64_t left = c.desc.length - lo;
     const uint32_t n = uint32_t(left < uint64_t(TILE) ? left : uint64_t(TILE));
-    rec.src = d.src + lo * src_frame_bytes;
-    rec.dst = d.dst + lo * dst_frame_bytes;
+    rec.src = c.desc.src + lo * src_frame_bytes;
+    rec.dst = c.desc.dst + lo * dst_frame_bytes;
     rec.frames = n;
-    rec.thr2 = d.thr2;
+    rec.thr2 = c.desc.thr2;
     rec.pad = 0;
-    const bool aligned = ((reinterpret_cast<uintptr_t>(d.src) | reinterpret_cast<uintptr_t>(d.dst)) & 15) == 0;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(c.desc.src) | reinterpret_cast<uintptr_t>(c.desc.dst)) & 15) == 0;
     // whole 16-byte units on both sides: groups of 4 frames when one side has 4-byte frames
     const uint32_t unit = (src_frame_bytes == 4 || dst_frame_bytes == 4) ? 4u : 2u;
     rec.bulk_frames = aligned ? (n / unit) * unit : 0u;
@@ -728,11 +772,14 @@ __global__ void __launch_bounds__(256) bulk_batch_kernel(const BatchBulkArgs a)
     uint64_t *full = reinterpret_cast<uint64_t *>(out_buf + size_t(STAGES) * OUT_STAGE);
     TileRecord *recs = reinterpret_cast<TileRecord *>(full + STAGES);
 
+    // Each CTA owns one contiguous range of tiles: consecutive tiles mostly belong to the same
+    // block, so the producer touches the descriptor list only at block boundaries.
     const uint64_t ntiles = a.tile_start[a.nblocks];
-    const uint64_t first = blockIdx.x, stride = gridDim.x;
+    const uint64_t per = (ntiles + gridDim.x - 1) / gridDim.x;
+    const uint64_t first = uint64_t(blockIdx.x) * per;
     if (first >= ntiles)
         return;
-    const uint64_t mine = (ntiles - first + stride - 1) / stride;
+    const uint64_t mine = ntiles - first < per ? ntiles - first : per;
     const uint64_t pol = bulk::make_policy(a.load_policy), pol_store = bulk::make_policy(a.store_policy);
 
     if (threadIdx.x == 0) {
@@ -742,12 +789,11 @@ __global__ void __launch_bounds__(256) bulk_batch_kernel(const BatchBulkArgs a)
     }
     __syncthreads();
 
-    // Producer state (thread 0): the block the next tile to be loaded belongs to.
-    uint32_t blk = 0;
+    BatchCursor cur; // producer state, thread 0 only
     auto produce = [&](uint64_t i) { // fills recs[i % STAGES] and, for a bulk tile, starts its load
         const int s = int(i % STAGES);
         TileRecord rec;
-        batch_tile_record<TILE>(a, first + i * stride, blk, rec, SFB, DFB);
+        batch_tile_record<TILE>(a, first + i, cur, rec, SFB, DFB);
         recs[s] = rec;
         if (rec.bulk_frames) {
             bulk::mbar_expect_tx(&full[s], rec.bulk_frames * SFB);
@@ -755,16 +801,7 @@ __global__ void __launch_bounds__(256) bulk_batch_kernel(const BatchBulkArgs a)
         }
     };
     if (threadIdx.x == 0) {
-        // binary search: the last block whose first tile is <= this CTA's first tile
-        uint32_t lo = 0, hi = a.nblocks - 1;
-        while (lo < hi) {
-            const uint32_t mid = lo + (hi - lo + 1) / 2;
-            if (a.tile_start[mid] <= first)
-                lo = mid;
-            else
-                hi = mid - 1;
-        }
-        blk = lo;
+        batch_cursor_seek(a, cur, first);
         for (uint64_t i = 0; i < uint64_t(STAGES) && i < mine; i++)
             produce(i);
     }

@@ -27,17 +27,21 @@
 namespace sx {
 
 struct alignas(64) Mailbox {
-    // Written by the host: one 32-byte record, fetched by the device with a single load so a
-    // request costs one PCIe read, not five.  The host stores `request` last; a read that sees
-    // the new sequence number therefore sees the rest of the record too (same cache line,
-    // stores in program order).
-    unsigned long long request; // sequence number of the latest request
-    const char *src;            // device-visible addresses of pinned host (or device) buffers
-    char *dst;
-    unsigned int nframes;       // bits 0..30: frames; bit 31: op (0 = RX S32->CF32, 1 = TX CF32->S32)
-    unsigned int thr2_bits_op;  // tx_threshold2 as float bits (unused for RX)
-    unsigned long long quit;    // non-zero: leave now (set by the host around device-wide syncs)
-    unsigned long long pad0[3];
+    // Written by the host: three 16-byte pieces of one cache line, fetched by the device with
+    // three independent loads (one PCIe round trip, not three in a row).  The loads may be
+    // served at different moments, so every piece carries the request's sequence number (or its
+    // low 15 bits) in the word the host stores LAST within that piece: a piece whose tag is the
+    // new number holds the new request's fields (x86 stores become visible in program order), and
+    // a request is taken only when all three tags agree.  No second look is needed.
+    unsigned long long request; // [piece A] sequence number of the latest request (stored last of all)
+    const char *src;            // [piece A] device-visible address of the source (stored before `request`)
+    char *dst;                  // [piece B]
+    unsigned long long packed;  // [piece B] bits 0..15: frames; bit 16: op (0 = RX S32->CF32, 1 = TX CF32->S32);
+                                //           bits 17..31: low 15 bits of the sequence number;
+                                //           bits 32..63: tx_threshold2 as float bits (stored after dst)
+    unsigned long long quit;    // [piece C] non-zero: leave now (set by the host around device-wide syncs)
+    unsigned long long request2; // [piece C] the sequence number again
+    unsigned long long pad0[2];
     // written by the device (own cache line)
     unsigned long long done; // sequence number of the last request served
     unsigned long long served;
@@ -77,24 +81,29 @@ struct Request {
     int op;
     unsigned long long quit;
 };
-// The 32-byte record as two 16-byte loads.
-__device__ __forceinline__ Request ld_request(const Mailbox *box)
+// The record as three 16-byte loads.  r.seq is the new sequence number only if every piece
+// belongs to it; otherwise it is reported as `last_seen` (nothing new yet, look again).
+__device__ __forceinline__ Request ld_request(const Mailbox *box, unsigned long long last_seen)
 {
-    unsigned long long a, b, c, d, q;
+    unsigned long long a, b, c, d, q, a2;
     asm volatile("ld.global.cv.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(box) : "memory");
     asm volatile("ld.global.cv.v2.u64 {%0,%1}, [%2];"
                  : "=l"(c), "=l"(d)
                  : "l"(reinterpret_cast<const char *>(box) + 16)
                  : "memory");
-    asm volatile("ld.global.cv.u64 %0, [%1];" : "=l"(q) : "l"(reinterpret_cast<const char *>(box) + 32) : "memory");
+    asm volatile("ld.global.cv.v2.u64 {%0,%1}, [%2];"
+                 : "=l"(q), "=l"(a2)
+                 : "l"(reinterpret_cast<const char *>(box) + 32)
+                 : "memory");
     Request r;
     r.quit = q;
-    r.seq = a;
     r.src = reinterpret_cast<const char *>(b);
     r.dst = reinterpret_cast<char *>(c);
-    r.nframes = unsigned(d) & 0x7FFFFFFFu;
-    r.op = int(unsigned(d) >> 31);
+    r.nframes = unsigned(d) & 0xFFFFu;
+    r.op = int((unsigned(d) >> 16) & 1u);
     r.thr2_bits = unsigned(d >> 32);
+    const bool whole = a == a2 && ((unsigned(d) >> 17) & 0x7FFFu) == unsigned(a & 0x7FFFu);
+    r.seq = whole ? a : last_seen;
     return r;
 }
 
@@ -151,11 +160,8 @@ __global__ void __launch_bounds__(256) resident_kernel(Mailbox *box, unsigned lo
             bool leaving = false, found = false;
             Request req;
             for (;;) {
-                req = ld_request(box);
+                req = ld_request(box, last_seen);
                 if (req.seq != last_seen) {
-                    // The two 16-byte halves are separate loads: take the record again once so
-                    // that both halves are at least as new as the sequence number just seen.
-                    req = ld_request(box);
                     found = true;
                     break;
                 }

@@ -94,9 +94,12 @@ struct sxgpu_ctx {
     int64_t bulk_load_policy = 0, bulk_store_policy = 0; // L2 eviction: 0 first, 1 normal, 2 last, 3 unchanged
     int64_t bulk_contiguous = 0;            // 0 round-robin tiles, 1 one contiguous range per CTA
     int64_t host_chunk_frames = 0;          // 0 auto (see pick_chunk_frames)
-    int64_t host_chunk_min_frames = 1 << 16; // first and last chunk of the ramped schedule; 0 = no ramp
+    int64_t host_chunk_min_frames = 0;      // > 0: chunk sizes ramp up from here and mirror at the end (measured: no gain, r02)
     int64_t host_mode = 0;                  // 0 auto, 1 copy engines, 2 zero-copy
-    int64_t small_mode = 0;                 // completion of small calls: 0 auto (= 2), 1 stream sync, 2 host flag
+    int64_t small_mode = 0;                 // completion of small calls: 0 auto (= 1), 1 stream sync, 2 host flag
+    int64_t host_in_mode = 0;               // pipeline input side: 0 auto (= 1), 1 copy engine, 2 read by the kernel across PCIe
+    int64_t host_out_mode = 0;              // pipeline output side: 0 auto (= 1), 1 copy engine, 2 written by the kernel across PCIe
+    int64_t bounce_nt = 1;                  // bounce copies use cache-bypassing stores
     int64_t zero_copy_max_frames = 1 << 18; // measured crossover, profiles/r01_sweep_host_path.json
     int64_t resident_max_frames = 0;        // > 0: blocks up to this size go to the resident converter
     int64_t zero_copy_variant = 1;          // schedule of the zero-copy kernel (1 vec128, 2 vec256, 3 bulk)
@@ -113,6 +116,7 @@ struct sxgpu_ctx {
 
     std::atomic<uint64_t> resident_launches{0}, resident_calls{0}, flagged_calls{0};
     std::atomic<int> live_banks{0}; // banks keep a pointer to their context
+    bool l2_carveout_set = false;   // sxgpu_bank_repeat_begin sets the persisting-L2 limit once
 
     // host pipeline: lane 0 serves the RX conversions, lane 1 the TX conversions
     HostLane lanes[2];
@@ -667,10 +671,13 @@ int resident_convert_call(sxgpu_ctx *ctx, HostLane &lane, int op, const void *sr
     const unsigned long long seq = ++lane.resident_seq;
     unsigned thr2_bits;
     std::memcpy(&thr2_bits, &thr2, sizeof thr2_bits);
+    // Fields first, each piece's tag after its fields, `request` last (see Mailbox).
     box->src = static_cast<const char *>(src);
     box->dst = static_cast<char *>(dst);
-    box->nframes = unsigned(length) | (unsigned(op) << 31);
-    box->thr2_bits_op = thr2_bits;
+    std::atomic_thread_fence(std::memory_order_release);
+    box->packed = (unsigned long long)(unsigned(length) | (unsigned(op) << 16) | (unsigned(seq & 0x7FFFu) << 17)) |
+                  ((unsigned long long)thr2_bits << 32);
+    box->request2 = seq;
     std::atomic_thread_fence(std::memory_order_release);
     box->request = seq;
 
@@ -771,8 +778,9 @@ void bounce_copy(sxgpu_ctx *ctx, std::unique_ptr<sxhost::ParallelCopier> &copier
                  size_t bytes)
 {
     const unsigned threads = bounce_thread_count(ctx);
-    if (!copier || copier->helpers() != threads - 1)
-        copier.reset(new sxhost::ParallelCopier(threads - 1));
+    const bool streaming = ctx->bounce_nt != 0;
+    if (!copier || copier->helpers() != threads - 1 || copier->streaming() != streaming)
+        copier.reset(new sxhost::ParallelCopier(threads - 1, streaming));
     copier->copy(dst, src, bytes);
 }
 
@@ -830,9 +838,9 @@ int convert_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset, void *h_d
         const bool frame_aligned = reinterpret_cast<uintptr_t>(kernel_in) % SFB == 0 &&
                                    reinterpret_cast<uintptr_t>(kernel_out) % DFB == 0;
         if (resident_op<Op>() >= 0 && !both_on_device && length <= size_t(ctx->resident_max_frames) &&
-            length < (size_t(1) << 31) && frame_aligned && kernel_in != kernel_out) {
+            length < (size_t(1) << 16) && frame_aligned && kernel_in != kernel_out) {
             SX_TRY(resident_convert_call(ctx, lane, resident_op<Op>(), kernel_in, kernel_out, length, thr2));
-        } else if (!both_on_device && ctx->small_mode != 1 && frame_aligned && ctx->host_mode != 2) {
+        } else if (!both_on_device && ctx->small_mode == 2 && frame_aligned && ctx->host_mode != 2) {
             SX_TRY(flagged_convert_call<Op>(ctx, lane, kernel_in, kernel_out, length, thr2));
         } else {
             SX_TRY(launch_convert<Op>(ctx, kernel_in, kernel_out, length, thr2,
@@ -853,6 +861,7 @@ int convert_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset, void *h_d
     // sidekick thread (and its helpers) as each chunk's device-to-host copy completes -- so the
     // two directions' CPU copies, the DMA and the kernels of different chunks all overlap.
     const bool bounce_in = !si.pinned && !si.on_device, bounce_out = !di.pinned && !di.on_device;
+    const bool in_zero_copy = ctx->host_in_mode == 2, out_zero_copy = ctx->host_out_mode == 2;
     const size_t c_max = std::min<size_t>(length, pick_chunk_frames(ctx, length));
     // + 128: the cap is rounded up to 64 frames and the last chunk carries the ragged end (< 64)
     SX_TRY(ensure_ring(ctx, lane, c_max + 128, bounce_in, bounce_out));
@@ -917,31 +926,44 @@ int convert_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset, void *h_d
             SX_TRY(wait_slot_free(i));
             const size_t first = chunks[i].first, n = chunks[i].frames;
 
+            // Input side: the caller's device buffer as it is; or pinned host memory (the caller's,
+            // or the bounce slot) either copied in by the copy engine or read by the kernel itself.
             const void *kernel_in = r.d_in[slot];
             if (si.on_device) {
                 kernel_in = static_cast<const char *>(si.device_alias) + first * SFB;
             } else {
-                const void *from = src + first * SFB;
+                const void *from = src + first * SFB; // host address, for the copy engine
+                const void *from_gpu = si.device_alias ? static_cast<const char *>(si.device_alias) + first * SFB : nullptr;
                 if (bounce_in) {
-                    bounce_copy(ctx, lane.copier_in, r.h_in[slot], from, n * SFB);
-                    from = r.h_in[slot];
+                    bounce_copy(ctx, lane.copier_in, r.h_in[slot], src + first * SFB, n * SFB);
+                    from = from_gpu = r.h_in[slot]; // cudaHostAlloc memory: one address for both
                 }
-                SX_CUDA(ctx, cudaMemcpyAsync(r.d_in[slot], from, n * SFB, cudaMemcpyHostToDevice, lane.s_h2d));
-                SX_CUDA(ctx, cudaEventRecord(r.copied_in[slot], lane.s_h2d));
-                SX_CUDA(ctx, cudaStreamWaitEvent(lane.s_comp, r.copied_in[slot], 0));
+                if (in_zero_copy && from_gpu) {
+                    kernel_in = from_gpu;
+                } else {
+                    SX_CUDA(ctx, cudaMemcpyAsync(r.d_in[slot], from, n * SFB, cudaMemcpyHostToDevice, lane.s_h2d));
+                    SX_CUDA(ctx, cudaEventRecord(r.copied_in[slot], lane.s_h2d));
+                    SX_CUDA(ctx, cudaStreamWaitEvent(lane.s_comp, r.copied_in[slot], 0));
+                }
             }
 
+            // Output side, likewise.
+            void *host_to = bounce_out ? r.h_out[slot] : static_cast<void *>(dst + first * DFB);
+            void *host_to_gpu = bounce_out          ? r.h_out[slot]
+                                : di.device_alias ? static_cast<void *>(static_cast<char *>(di.device_alias) + first * DFB)
+                                                  : nullptr;
+            const bool kernel_writes_host = !di.on_device && out_zero_copy && host_to_gpu;
             void *kernel_out = di.on_device ? static_cast<void *>(static_cast<char *>(di.device_alias) + first * DFB)
-                                            : r.d_out[slot];
+                               : kernel_writes_host ? host_to_gpu
+                                                    : r.d_out[slot];
             SX_TRY(launch_convert<Op>(ctx, kernel_in, kernel_out, n, thr2, variant, lane.s_comp));
 
-            if (di.on_device) {
+            if (di.on_device || kernel_writes_host) {
                 SX_CUDA(ctx, cudaEventRecord(r.done[slot], lane.s_comp));
             } else {
                 SX_CUDA(ctx, cudaEventRecord(r.converted[slot], lane.s_comp));
                 SX_CUDA(ctx, cudaStreamWaitEvent(lane.s_d2h, r.converted[slot], 0));
-                void *to = bounce_out ? r.h_out[slot] : static_cast<void *>(dst + first * DFB);
-                SX_CUDA(ctx, cudaMemcpyAsync(to, r.d_out[slot], n * DFB, cudaMemcpyDeviceToHost, lane.s_d2h));
+                SX_CUDA(ctx, cudaMemcpyAsync(host_to, r.d_out[slot], n * DFB, cudaMemcpyDeviceToHost, lane.s_d2h));
                 SX_CUDA(ctx, cudaEventRecord(r.done[slot], lane.s_d2h));
             }
             lane.issued.publish(i + 1);
@@ -971,8 +993,24 @@ template <class Op> constexpr size_t batch_smem_bytes()
 {
     return size_t(kBatchStages) * (size_t(kBatchTile) * (Op::kSrcWords + Op::kDstWords) * 4 + 8 + sizeof(TileRecord));
 }
-constexpr int kLoopTile = 2048, kLoopStages = 4;
-constexpr size_t kLoopSmem = 3 * size_t(kLoopStages) * kLoopTile * 8 + size_t(kLoopStages) * 8;
+// Shapes of the bulk loopback kernel (three buffers per stage: 24 KiB per 1024 frames).
+typedef void (*LoopKernel)(const BulkLoopbackArgs);
+struct LoopShape {
+    int tile, stages;
+    LoopKernel kernel;
+};
+const LoopShape kLoopShapes[] = {
+    {2048, 4, bulk_loopback_kernel<2048, 4>}, // default
+    {2048, 3, bulk_loopback_kernel<2048, 3>},
+    {1024, 4, bulk_loopback_kernel<1024, 4>},
+    {1024, 6, bulk_loopback_kernel<1024, 6>},
+    {1024, 8, bulk_loopback_kernel<1024, 8>},
+    {512, 8, bulk_loopback_kernel<512, 8>},
+};
+size_t loop_smem_bytes(const LoopShape &s)
+{
+    return 3 * size_t(s.stages) * s.tile * 8 + size_t(s.stages) * 8;
+}
 
 template <class Op>
 int convert_batch(sxgpu_ctx *ctx, const sxgpu_block *blocks, uint32_t nblocks, int on_device,
@@ -1102,6 +1140,9 @@ int64_t *option_slot(sxgpu_ctx *ctx, const char *key)
         {"host_chunk_min_frames", &ctx->host_chunk_min_frames},
         {"host_mode", &ctx->host_mode},
         {"small_mode", &ctx->small_mode},
+        {"host_in_mode", &ctx->host_in_mode},
+        {"host_out_mode", &ctx->host_out_mode},
+        {"bounce_nt", &ctx->bounce_nt},
         {"zero_copy_max_frames", &ctx->zero_copy_max_frames},
         {"resident_max_frames", &ctx->resident_max_frames},
         {"zero_copy_variant", &ctx->zero_copy_variant},
@@ -1211,9 +1252,12 @@ int sxgpu_init(int device, sxgpu_ctx **out)
                              cudaFuncAttributeMaxDynamicSharedMemorySize, int(batch_smem_bytes<RxCf32>())) != cudaSuccess ||
         cudaFuncSetAttribute(bulk_batch_kernel<TxCf32, kBatchTile, kBatchStages>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, int(batch_smem_bytes<TxCf32>())) != cudaSuccess ||
-        cudaFuncSetAttribute(bulk_loopback_kernel<kLoopTile, kLoopStages>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, int(kLoopSmem)) != cudaSuccess)
+        false)
         return bail(SXGPU_ERR_CUDA);
+    for (const LoopShape &shape : kLoopShapes)
+        if (cudaFuncSetAttribute(shape.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 int(loop_smem_bytes(shape))) != cudaSuccess)
+            return bail(SXGPU_ERR_CUDA);
     *out = ctx;
     return SXGPU_OK;
 }
@@ -1369,9 +1413,18 @@ int sxgpu_convert_loopback(sxgpu_ctx *ctx, const void *d_i2s_in, void *d_cf32, v
         BulkLoopbackArgs b = {static_cast<const char *>(d_i2s_in), static_cast<char *>(d_cf32),
                               static_cast<char *>(d_i2s_out), even, tx_threshold2, int(ctx->bulk_load_policy),
                               int(ctx->bulk_store_policy)};
-        auto k = bulk_loopback_kernel<kLoopTile, kLoopStages>;
-        const uint64_t ntiles = (even + kLoopTile - 1) / kLoopTile;
-        k<<<persistent_grid(ctx, k, 256, kLoopSmem, ntiles), 256, kLoopSmem, st>>>(b);
+        const LoopShape *shape = &kLoopShapes[0];
+        if (ctx->bulk_tile || ctx->bulk_stages) { // tuning: option bulk_tile / bulk_stages select a shape
+            shape = nullptr;
+            for (const LoopShape &c : kLoopShapes)
+                if (c.tile == (ctx->bulk_tile ? ctx->bulk_tile : 2048) && c.stages == (ctx->bulk_stages ? ctx->bulk_stages : 4))
+                    shape = &c;
+            if (!shape)
+                return ctx->invalid("unsupported bulk_tile/bulk_stages combination for the loopback");
+        }
+        const uint64_t ntiles = (even + shape->tile - 1) / shape->tile;
+        const size_t smem = loop_smem_bytes(*shape);
+        shape->kernel<<<persistent_grid(ctx, shape->kernel, 256, smem, ntiles), 256, smem, st>>>(b);
         SX_CUDA(ctx, cudaGetLastError());
         ctx->launches++;
         if (length & 1) {
@@ -1657,6 +1710,51 @@ int sxgpu_bank_repeat(sxgpu_bank *bank, void *d_cf32, long long rx_time_offset_n
     return SXGPU_OK;
 }
 
+// The repeater iteration split around a kernel of the caller's: begin = the read, with the
+// CF32 block marked persisting in L2 for the stream; end = the timed write of that block, after
+// which the mark is lifted.  In between the caller launches whatever it likes on the same stream.
+int sxgpu_bank_repeat_begin(sxgpu_bank *bank, void *d_cf32, sxgpu_stream stream)
+{
+    if (!bank)
+        return SXGPU_ERR_INVALID;
+    sxgpu_ctx *ctx = bank->ctx;
+    if (!d_cf32)
+        return ctx->invalid("null CF32 buffer");
+    SX_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = bank_stream(bank, stream);
+    const size_t bytes = size_t(bank->st.nstreams) * bank->st.period * 8;
+    const size_t window = std::min<size_t>(bytes, size_t(ctx->prop.accessPolicyMaxWindowSize));
+    if (window > 0 && ctx->prop.persistingL2CacheMaxSize > 0) {
+        if (!ctx->l2_carveout_set) { // once: let up to three quarters of L2 hold persisting lines
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize,
+                               std::min<size_t>(size_t(ctx->prop.persistingL2CacheMaxSize), size_t(ctx->prop.l2CacheSize) / 4 * 3));
+            cudaGetLastError();
+            ctx->l2_carveout_set = true;
+        }
+        cudaStreamAttrValue attr = {};
+        attr.accessPolicyWindow.base_ptr = d_cf32;
+        attr.accessPolicyWindow.num_bytes = window;
+        attr.accessPolicyWindow.hitRatio = 1.0f;
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess)
+            cudaGetLastError(); // a hint only: the iteration is correct without it
+    }
+    return sxgpu_bank_read(bank, d_cf32, stream);
+}
+
+int sxgpu_bank_repeat_end(sxgpu_bank *bank, const void *d_cf32, long long rx_time_offset_ns, sxgpu_stream stream)
+{
+    if (!bank)
+        return SXGPU_ERR_INVALID;
+    int rc = sxgpu_bank_write(bank, d_cf32, SX_HAS_TIME, nullptr, rx_time_offset_ns, stream);
+    cudaStreamAttrValue attr = {};
+    attr.accessPolicyWindow.num_bytes = 0; // lift the window for whatever the stream does next
+    if (cudaStreamSetAttribute(bank_stream(bank, stream), cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess)
+        cudaGetLastError();
+    return rc;
+}
+
 int sxgpu_bank_ingest(sxgpu_bank *bank, uint32_t first_stream, uint32_t nstreams, const void *i2s,
                       sxgpu_stream stream)
 {
@@ -1770,13 +1868,21 @@ int sxgpu_bank_playback(sxgpu_bank *bank, uint32_t index, int64_t position, size
         return ctx->invalid("playback window outside the stream's ring");
     SX_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = bank_stream(bank, stream);
-    const char *ring = b.playback_ring + size_t(index) * b.ring * 8;
-    uint64_t offset = uint64_t(position) % b.ring;
-    size_t first = std::min<size_t>(nframes, b.ring - offset);
-    SX_CUDA(ctx, cudaMemcpyAsync(h_i2s, ring + offset * 8, first * 8, cudaMemcpyDeviceToHost, st));
-    if (first < nframes)
-        SX_CUDA(ctx, cudaMemcpyAsync(static_cast<char *>(h_i2s) + first * 8, ring, (nframes - first) * 8,
-                                     cudaMemcpyDeviceToHost, st));
+    if (nframes == 0)
+        return SXGPU_OK;
+    // The rings are stored time-major (sx_bank.cuh, ring_frame): gather the window on the device,
+    // then one copy out.
+    void *tmp = nullptr;
+    SX_CUDA(ctx, cudaMallocAsync(&tmp, nframes * 8, st));
+    const int grid = int(std::min<uint64_t>((nframes + 255) / 256, uint64_t(ctx->prop.multiProcessorCount) * 4));
+    bank_gather_kernel<<<grid, 256, 0, st>>>(b, index, position, nframes, static_cast<char *>(tmp));
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(h_i2s, tmp, nframes * 8, cudaMemcpyDeviceToHost, st);
+    cudaFreeAsync(tmp, st);
+    if (e != cudaSuccess)
+        return ctx->fail(e, "sxgpu_bank_playback");
+    ctx->launches++;
     SX_CUDA(ctx, cudaStreamSynchronize(st));
     return SXGPU_OK;
 }

@@ -35,7 +35,8 @@ def unhex(words, dtype):
 
 
 RESET = dict(batch_variant=0, loopback_variant=0, small_mode=0, host_mode=0, host_chunk_frames=0,
-             host_chunk_min_frames=1 << 16, bounce_threads=0, resident_max_frames=0)
+             host_chunk_min_frames=0, bounce_threads=0, resident_max_frames=0, host_in_mode=0, host_out_mode=0,
+             bounce_nt=1)
 
 
 @pytest.fixture(autouse=True)
@@ -267,11 +268,19 @@ def test_same_staging_buffer_new_contents_every_small_call(ctx, oracle):
         assert np.array_equal(bits(ho.numpy()), bits(sxtest.oracle_rx(oracle, words))), k
 
 
-@pytest.mark.parametrize("c_min", [0, 1 << 12, 1 << 16])
+@pytest.mark.parametrize("c_min,in_mode,out_mode,nt", [(0, 1, 1, 1), (1 << 12, 1, 1, 0), (1 << 16, 1, 1, 1),
+                                                       (0, 1, 2, 1), (0, 2, 1, 1), (1 << 12, 2, 2, 0)])
 @pytest.mark.parametrize("kinds", ["pinned", "pageable", "pageable_in", "pageable_out"])
 @pytest.mark.parametrize("nframes", [(1 << 18) + 1, (1 << 20) + 17, (1 << 23) - 5])
-def test_ramped_chunk_pipeline(ctx, oracle, c_min, kinds, nframes):
+def test_host_pipeline_schedules_and_modes(ctx, oracle, c_min, in_mode, out_mode, nt, kinds, nframes):
+    """The copy-engine pipeline with a ramped or uniform chunk schedule, either side moved by the
+    copy engine or read/written by the kernel across PCIe, bounce copies with or without
+    cache-bypassing stores: same bits whatever the plumbing."""
+    ctx.set_option("host_mode", 1)
     ctx.set_option("host_chunk_min_frames", c_min)
+    ctx.set_option("host_in_mode", in_mode)
+    ctx.set_option("host_out_mode", out_mode)
+    ctx.set_option("bounce_nt", nt)
     ctx.set_option("host_chunk_frames", 1 << 19)
     words = sxtest.rx_uniform(nframes, seed=nframes % 1000)
     f = sxtest.tx_uniform(nframes, seed=nframes % 1000 + 1)
