@@ -36,6 +36,7 @@ GPU_DEPS = GPU_SOURCES + [CSRC / "sx_kernels.cuh", CSRC / "sx_bank.cuh", CSRC / 
 
 SOAPY_SOURCES = [
     CSRC / "host" / "SoapySXB200.cpp",
+    CSRC / "host" / "SoapySXB200Group.cpp",
     CSRC / "host" / "harness_capi.cpp",
     CSRC / "shim" / "soapy_shim.cpp",
     CSRC / "shim" / "alsa_stub.cpp",
@@ -71,7 +72,7 @@ def build_gpu_library(force: bool = False) -> Path:
 
 def build_soapy_module(force: bool = False) -> Path:
     build_gpu_library(force)
-    deps = SOAPY_SOURCES + list((CSRC / "shim").rglob("*.h*")) + [GPU_LIB, CSRC / "host" / "SoapySXB200.hpp"]
+    deps = SOAPY_SOURCES + list((CSRC / "shim").rglob("*.h*")) + list((CSRC / "host").glob("*.hpp")) + [GPU_LIB]
     if force or _stale(SOAPY_LIB, deps):
         _run([
             os.environ.get("CXX", "g++"), "-std=c++17", "-O2", "-ffp-contract=off", "-Wall", "-Wextra", "-fPIC", "-shared",

@@ -8,6 +8,7 @@
 #include <SoapySDR/Time.hpp>
 
 #include "sxgpu.h"
+#include "stream_ops.hpp"
 
 #include <algorithm>
 #include <cerrno>
@@ -23,15 +24,6 @@ namespace {
 // SX1255 sample-rate dividers that work over I2S with 32-bit slots (reference table,
 // SoapySX.cpp:196-208; the 24- and 16-bit entries are commented out there as broken).
 const unsigned kRateDividers[] = {1536, 768, 512, 256, 128, 64};
-
-// ALSA error -> SoapySDR stream error (reference :339-360): -EPIPE is an xrun, named by
-// direction; anything else is a generic stream error.
-int stream_error_from_alsa(const Endpoint &ep, long alsa_error)
-{
-    if (alsa_error == -EPIPE)
-        return ep.is_tx() ? SOAPY_SDR_UNDERFLOW : SOAPY_SDR_OVERFLOW;
-    return SOAPY_SDR_STREAM_ERROR;
-}
 
 std::string kwarg(const SoapySDR::Kwargs &args, const char *key, const std::string &fallback)
 {
@@ -413,41 +405,19 @@ int SoapySXB200::readStream(SoapySDR::Stream *stream, void *const *buffs, const 
     flags = 0;
     if (ep.is_tx())
         throw std::runtime_error("Wrong direction");
-    if (!ep.active)
-        return 0; // an inactive capture PCM would block forever (reference :887-894)
 
-    snd_pcm_sframes_t pending = 0, delay = 0;
-    int ret = snd_pcm_avail_delay(ep.pcm, &pending, &delay);
-    if (ret < 0) {
-        SoapySDR_logf(SOAPY_SDR_ERROR, "rx snd_pcm_avail_delay: %d", ret);
-        return stream_error_from_alsa(ep, ret);
-    }
-
-    if (unsigned long skip = sxplan::overrun_skip(pending, ep.ring)) {
-        snd_pcm_sframes_t skipped = snd_pcm_forward(ep.pcm, skip);
-        if (skipped < 0) {
-            SoapySDR_logf(SOAPY_SDR_ERROR, "rx snd_pcm_forward: %ld", long(skipped));
-            return stream_error_from_alsa(ep, skipped);
-        }
-        ep.position += skipped;
-        pending -= skipped;
-        SoapySDR_logf(SOAPY_SDR_WARNING, "RX buffer overrun. Skipped %ld samples", long(skipped));
-    }
-
-    unsigned long length = (unsigned long)std::min(numElems, (size_t)ULONG_MAX);
-    length = sxplan::trim_nonblocking(length, pending, timeoutUs);
-    if (length == 0)
-        return 0;
-
-    stage_rx_->reserve(length);
-    snd_pcm_sframes_t got = snd_pcm_readi(ep.pcm, stage_rx_->data(), length);
-    if (got < 0)
-        return stream_error_from_alsa(ep, got);
-
-    // The block's timestamp is the counter value of its first frame.
-    timeNs = SoapySDR::ticksToTimeNs(ep.position, sample_rate_);
-    flags |= SOAPY_SDR_HAS_TIME;
-    ep.position += got;
+    // Everything up to the conversion (csrc/host/stream_ops.hpp): pending frames, overrun skip,
+    // non-blocking trim, snd_pcm_readi into pinned staging, timestamp, frame counter.
+    const RxOutcome rx = rx_before_convert(ep, sample_rate_, numElems, timeoutUs, [this](size_t frames) {
+        stage_rx_->reserve(frames);
+        return stage_rx_->data();
+    });
+    if (rx.time_valid)
+        timeNs = rx.time_ns;
+    flags |= rx.flags;
+    if (rx.ret <= 0)
+        return rx.ret;
+    const int got = rx.ret;
 
     // I2S words -> CF32 on the GPU, straight out of pinned staging into the caller's buffer.
     pin_if_asked(ep, buffs[0], numElems * (ep.cs16 ? 4 : 8));
@@ -474,61 +444,13 @@ int SoapySXB200::writeStream(SoapySDR::Stream *stream, const void *const *buffs,
 
     if (!ep.is_tx())
         throw std::runtime_error("Wrong direction");
-    if (!ep.active)
-        return 0;
 
-    snd_pcm_sframes_t room = 0, queued = 0;
-    int ret = snd_pcm_avail_delay(ep.pcm, &room, &queued);
-    if (ret < 0) {
-        SoapySDR_logf(SOAPY_SDR_ERROR, "tx snd_pcm_avail_delay: %d", ret);
-        return stream_error_from_alsa(ep, ret);
-    }
-
-    unsigned long length = (unsigned long)std::min(numElems, (size_t)ULONG_MAX);
-
-    const bool timed = (flags & SOAPY_SDR_HAS_TIME) != 0;
-    const int64_t time_ticks = timed ? SoapySDR::timeNsToTicks(timeNs, sample_rate_) : 0;
-    sxplan::TxPlacement where =
-        sxplan::place_tx_block(ep.position, queued, timed, time_ticks, ep.ring.period);
-    if (where.discard) {
-        // Late bursts are dropped whole and reported as sent, as most SDR drivers do
-        // (reference :1013-1023).
-        SoapySDR_logf(SOAPY_SDR_WARNING, "Discarding %lu TX samples timed in the past", length);
-        return int(length);
-    }
-    if (where.underrun_jump > 0)
-        SoapySDR_logf(SOAPY_SDR_WARNING, "TX buffer underrun. Forwarding TX stream by %lld samples",
-                      (long long)where.underrun_jump);
-
-    // Move the ring's write pointer up to the block's position; what is skipped plays as
-    // silence.  When the ring cannot take the whole gap yet, take what fits and wait.
-    int64_t gap = where.write_position - ep.position;
-    while (gap > 0) {
-        snd_pcm_sframes_t step = (snd_pcm_sframes_t)std::min(gap, (int64_t)LONG_MAX);
-        snd_pcm_sframes_t fits = snd_pcm_forwardable(ep.pcm);
-        if (fits < 0) {
-            SoapySDR_logf(SOAPY_SDR_ERROR, "tx snd_pcm_forwardable: %ld", long(fits));
-            return stream_error_from_alsa(ep, fits);
-        }
-        snd_pcm_sframes_t moved;
-        if (step < fits) {
-            moved = snd_pcm_forward(ep.pcm, step);
-        } else {
-            moved = snd_pcm_forward(ep.pcm, fits);
-            snd_pcm_wait(ep.pcm, -10001);
-        }
-        if (moved < 0) {
-            SoapySDR_logf(SOAPY_SDR_ERROR, "tx snd_pcm_forward: %ld", long(moved));
-            return stream_error_from_alsa(ep, moved);
-        }
-        ep.position += moved;
-        gap -= moved;
-        room -= moved;
-    }
-
-    length = sxplan::trim_nonblocking(length, room, timeoutUs);
-    if (length == 0)
-        return 0;
+    // Everything up to the conversion (csrc/host/stream_ops.hpp): where the block lands, late
+    // bursts, the forward over the gap, the non-blocking trim.
+    const TxOutcome tx = tx_before_convert(ep, sample_rate_, numElems, flags, timeNs, timeoutUs);
+    if (!tx.convert)
+        return tx.ret;
+    const unsigned long length = tx.length;
 
     // CF32 -> I2S words on the GPU, from the caller's buffer into pinned staging.
     pin_if_asked(ep, buffs[0], numElems * (ep.cs16 ? 4 : 8));
@@ -543,11 +465,7 @@ int SoapySXB200::writeStream(SoapySDR::Stream *stream, const void *const *buffs,
         return SOAPY_SDR_STREAM_ERROR;
     }
 
-    snd_pcm_sframes_t sent = snd_pcm_writei(ep.pcm, stage_tx_->data(), length);
-    if (sent < 0)
-        return stream_error_from_alsa(ep, sent);
-    ep.position += sent;
-    return int(sent);
+    return tx_after_convert(ep, stage_tx_->data(), length);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -13,6 +13,7 @@
 #define SXHOST_HAVE_NT_STORES 1
 #endif
 
+#include <atomic>
 #include <condition_variable>
 #include <cstddef>
 #include <cstdint>
@@ -62,9 +63,13 @@ inline void stream_copy(void *dst, const void *src, size_t bytes)
 
 class ParallelCopier {
 public:
-    // Copies below this size are done by the caller alone: waking helpers costs tens of
+    // Copies below this size are done by the caller alone: handing out pieces costs a few
     // microseconds, a single thread moves 1 MiB in about a hundred.
     static constexpr size_t kMinParallelBytes = size_t(2) << 20;
+    // A helper that has finished its piece keeps looking for the next copy for this long before
+    // it parks on the condition variable: the chunks of one *_host call follow each other within
+    // tens of microseconds, and waking a parked thread costs about as much as copying a chunk.
+    static constexpr unsigned kSpinsBeforeParking = 20000; // ~100 us of polling
 
     // `helpers` threads are started on first use and parked between copies.  `streaming`: use
     // cache-bypassing stores (stream_copy) for every piece.
@@ -74,7 +79,7 @@ public:
     {
         {
             std::lock_guard<std::mutex> lock(mutex_);
-            quit_ = true;
+            quit_.store(true, std::memory_order_release);
         }
         wake_.notify_all();
         for (std::thread &t : threads_)
@@ -88,7 +93,7 @@ public:
     bool streaming() const { return streaming_; }
 
     // memcpy(dst, src, bytes); returns when every byte has been copied.  One copy at a time
-    // (the caller serialises: the host pipeline holds the context's host mutex).
+    // (the caller serialises: each pipeline side owns its copier).
     void copy(void *dst, const void *src, size_t bytes)
     {
         if (helpers_ == 0 || bytes < kMinParallelBytes) {
@@ -99,19 +104,22 @@ public:
         const unsigned parts = helpers_ + 1;
         // slices are multiples of 4 KiB so that no two threads share a page of the destination
         const size_t slice = ((bytes + parts - 1) / parts + 4095) & ~size_t(4095); // parts * slice >= bytes
+        dst_ = static_cast<char *>(dst);
+        src_ = static_cast<const char *>(src);
+        bytes_ = bytes;
+        slice_ = slice;
+        pending_.store(helpers_, std::memory_order_relaxed);
         {
+            // Published under the lock so that a helper about to park cannot miss it.
             std::lock_guard<std::mutex> lock(mutex_);
-            dst_ = static_cast<char *>(dst);
-            src_ = static_cast<const char *>(src);
-            bytes_ = bytes;
-            slice_ = slice;
-            pending_ = helpers_;
-            generation_++;
+            generation_.fetch_add(1, std::memory_order_release);
         }
         wake_.notify_all();
         copy_slice(0); // the caller takes the first slice
-        std::unique_lock<std::mutex> lock(mutex_);
-        done_.wait(lock, [this] { return pending_ == 0; });
+        unsigned spins = 0;
+        while (pending_.load(std::memory_order_acquire) != 0)
+            if (++spins > 2000)
+                std::this_thread::yield();
     }
 
 private:
@@ -143,17 +151,22 @@ private:
     void helper_main(unsigned part)
     {
         uint64_t seen = 0;
-        std::unique_lock<std::mutex> lock(mutex_);
         for (;;) {
-            wake_.wait(lock, [&] { return quit_ || generation_ != seen; });
-            if (quit_)
+            // Look for the next copy: poll for a while, then park.
+            unsigned spins = 0;
+            while (generation_.load(std::memory_order_acquire) == seen && !quit_.load(std::memory_order_acquire)) {
+                if (++spins < kSpinsBeforeParking)
+                    continue;
+                std::unique_lock<std::mutex> lock(mutex_);
+                wake_.wait(lock, [&] {
+                    return quit_.load(std::memory_order_acquire) || generation_.load(std::memory_order_acquire) != seen;
+                });
+            }
+            if (quit_.load(std::memory_order_acquire))
                 return;
-            seen = generation_;
-            lock.unlock();
+            seen = generation_.load(std::memory_order_acquire);
             copy_slice(part);
-            lock.lock();
-            if (--pending_ == 0)
-                done_.notify_one();
+            pending_.fetch_sub(1, std::memory_order_release);
         }
     }
 
@@ -161,10 +174,10 @@ private:
     const bool streaming_;
     std::vector<std::thread> threads_;
     std::mutex mutex_;
-    std::condition_variable wake_, done_;
-    bool quit_ = false;
-    uint64_t generation_ = 0;
-    unsigned pending_ = 0;
+    std::condition_variable wake_;
+    std::atomic<bool> quit_{false};
+    std::atomic<uint64_t> generation_{0};
+    std::atomic<unsigned> pending_{0};
     char *dst_ = nullptr;
     const char *src_ = nullptr;
     size_t bytes_ = 0, slice_ = 0;
@@ -188,7 +201,7 @@ public:
     {
         {
             std::lock_guard<std::mutex> lock(mutex_);
-            quit_ = true;
+            quit_.store(true, std::memory_order_release);
         }
         wake_.notify_all();
         if (thread_.joinable())
@@ -199,42 +212,53 @@ public:
 
     void start(std::function<void()> job)
     {
-        std::lock_guard<std::mutex> lock(mutex_);
         if (!thread_.joinable())
             thread_ = std::thread([this] { main(); });
         job_ = std::move(job);
-        busy_ = true;
+        {
+            std::lock_guard<std::mutex> lock(mutex_); // so that a thread about to park cannot miss it
+            started_.fetch_add(1, std::memory_order_release);
+        }
         wake_.notify_all();
     }
 
     void finish()
     {
-        std::unique_lock<std::mutex> lock(mutex_);
-        done_.wait(lock, [this] { return !busy_; });
+        unsigned spins = 0;
+        while (finished_.load(std::memory_order_acquire) != started_.load(std::memory_order_relaxed))
+            if (++spins > 2000)
+                std::this_thread::yield();
     }
 
 private:
     void main()
     {
-        std::unique_lock<std::mutex> lock(mutex_);
+        uint64_t seen = 0;
         for (;;) {
-            wake_.wait(lock, [this] { return quit_ || busy_; });
-            if (quit_)
+            // Calls follow each other closely while a stream is running: poll a while, then park.
+            unsigned spins = 0;
+            while (started_.load(std::memory_order_acquire) == seen && !quit_.load(std::memory_order_acquire)) {
+                if (++spins < ParallelCopier::kSpinsBeforeParking)
+                    continue;
+                std::unique_lock<std::mutex> lock(mutex_);
+                wake_.wait(lock, [&] {
+                    return quit_.load(std::memory_order_acquire) || started_.load(std::memory_order_acquire) != seen;
+                });
+            }
+            if (quit_.load(std::memory_order_acquire))
                 return;
-            std::function<void()> job = std::move(job_);
-            lock.unlock();
-            job();
-            lock.lock();
-            busy_ = false;
-            done_.notify_all();
+            seen = started_.load(std::memory_order_acquire);
+            job_();
+            finished_.store(seen, std::memory_order_release);
         }
     }
 
     std::thread thread_;
     std::mutex mutex_;
-    std::condition_variable wake_, done_;
+    std::condition_variable wake_;
     std::function<void()> job_;
-    bool busy_ = false, quit_ = false;
+    std::atomic<bool> quit_{false};
+    std::atomic<uint64_t> started_{0}, finished_{0};
 };
 
 // Progress counter shared by two threads of a pipeline: one publishes "chunks 0..n-1 are done",

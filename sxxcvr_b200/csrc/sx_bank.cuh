@@ -467,6 +467,40 @@ __global__ void __launch_bounds__(256) bank_repeat_reg_kernel(BankState b, char 
     }
 }
 
+// CTA-per-32-streams schedule with the intermediates in registers: the first warp takes the 32
+// streams' decisions, one stream per lane (the timestamp arithmetic is double precision and runs
+// on one lane per stream: 32 lanes side by side cost what one does), hands them over in shared
+// memory, and each of the CTA's warps then produces, converts and stores its streams' blocks
+// without reading anything back.
+template <class Hook>
+__global__ void __launch_bounds__(256) bank_repeat_group_reg_kernel(BankState b, char *cf32, long long rx_time_offset_ns,
+                                                                    bool capture_in_slot, Hook hook)
+{
+    __shared__ long long s_first[2][32], s_at[2][32], s_gap[2][32], s_start[2][32];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps_per_cta = blockDim.x >> 5;
+    const uint64_t ngroups = (uint64_t(b.nstreams) + 31) / 32;
+    int buf = 0;
+    for (uint64_t g = blockIdx.x; g < ngroups; g += gridDim.x, buf ^= 1) {
+        const uint64_t base = g * 32;
+        const uint32_t count = uint32_t(b.nstreams - base < 32 ? b.nstreams - base : 32);
+        if (threadIdx.x < count) {
+            long long first;
+            BankWritePlan w;
+            bank_plan_repeat(b, base + threadIdx.x, cf32, rx_time_offset_ns, first, w);
+            s_first[buf][threadIdx.x] = first;
+            s_at[buf][threadIdx.x] = w.at;
+            s_gap[buf][threadIdx.x] = w.gap;
+            s_start[buf][threadIdx.x] = w.start;
+        }
+        // One barrier per group: the plans alternate between two buffers, so the first warp may
+        // plan the next group while the others are still moving this one's blocks.
+        __syncthreads();
+        for (uint32_t j = warp; j < count; j += warps_per_cta)
+            bank_repeat_stream_reg(b, base + j, cf32, uint64_t(s_first[buf][j]), s_at[buf][j], s_gap[buf][j],
+                                   s_start[buf][j], lane, capture_in_slot, hook);
+    }
+}
+
 // The repeater iteration in one launch: readStream(period) on every stream, then
 // writeStream(period, HAS_TIME, that read's timestamp + rx_time_offset_ns) of the block just
 // read (example/linear_repeater.py:50-71 without the filters).  State and results are exactly

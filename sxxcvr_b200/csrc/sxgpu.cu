@@ -61,6 +61,7 @@ struct alignas(64) SmallFlag {
 struct HostLane {
     std::mutex mutex;
     cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
+    cudaStream_t s_slot[kRingSlots] = {}; // one stream per ring slot (pipeline_mode 2)
     HostRing ring;
     std::unique_ptr<sxhost::ParallelCopier> copier_in, copier_out; // bounce copies of pageable callers
     sxhost::Sidekick retirer;                                      // runs the outbound half of the pipeline
@@ -100,6 +101,8 @@ struct sxgpu_ctx {
     int64_t host_in_mode = 0;               // pipeline input side: 0 auto (= 1), 1 copy engine, 2 read by the kernel across PCIe
     int64_t host_out_mode = 0;              // pipeline output side: 0 auto (= 1), 1 copy engine, 2 written by the kernel across PCIe
     int64_t bounce_nt = 1;                  // bounce copies use cache-bypassing stores
+    int64_t pipeline_mode = 0;              // 0 auto (= 2); 1 = copy-in / compute / copy-out streams chained by events;
+                                            // 2 = one stream per ring slot, each chunk's three operations in order on it
     int64_t zero_copy_max_frames = 1 << 18; // measured crossover, profiles/r01_sweep_host_path.json
     int64_t resident_max_frames = 0;        // > 0: blocks up to this size go to the resident converter
     int64_t zero_copy_variant = 1;          // schedule of the zero-copy kernel (1 vec128, 2 vec256, 3 bulk)
@@ -572,6 +575,8 @@ int ensure_lane(sxgpu_ctx *ctx, HostLane &lane)
         SX_CUDA(ctx, cudaStreamCreateWithFlags(&lane.s_h2d, cudaStreamDefault));
         SX_CUDA(ctx, cudaStreamCreateWithFlags(&lane.s_comp, cudaStreamDefault));
         SX_CUDA(ctx, cudaStreamCreateWithFlags(&lane.s_d2h, cudaStreamDefault));
+        for (int i = 0; i < kRingSlots; i++)
+            SX_CUDA(ctx, cudaStreamCreateWithFlags(&lane.s_slot[i], cudaStreamDefault));
     }
     HostRing &r = lane.ring;
     if (!r.events) {
@@ -906,10 +911,20 @@ int convert_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset, void *h_d
         }
         return rc;
     };
+    // Two ways to order a chunk's three operations (copy in, convert, copy out).  Chained: one
+    // stream per kind of operation, events between them -- eight runtime calls per chunk, which at
+    // ~1.5 us each is the whole transfer time of a 512 KiB chunk.  Per slot (default): one stream
+    // per ring slot, the chunk's operations in order on it and chunk i + K behind chunk i on the
+    // same stream, so that the device buffers of a slot need no event at all; different slots'
+    // streams overlap each other on the copy engines and the SMs.  Three or four calls per chunk.
+    const bool per_slot = ctx->pipeline_mode != 1;
     // Slot i % K is free again once chunk i - K has left it: its device-to-host copy is complete
-    // (and, for a pageable destination, bounced out).
+    // (and, for a pageable destination, bounced out).  With one stream per slot the device side
+    // orders itself; only a pinned bounce buffer about to be refilled by the CPU needs the wait.
     auto wait_slot_free = [&](size_t i) -> int {
         if (i < size_t(kRingSlots))
+            return SXGPU_OK;
+        if (per_slot && !bounce_in && !use_sidekick)
             return SXGPU_OK;
         if (use_sidekick) {
             if (!lane.retired.wait_for(i - kRingSlots + 1, lane.pipeline_error))
@@ -940,6 +955,8 @@ int convert_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset, void *h_d
                 }
                 if (in_zero_copy && from_gpu) {
                     kernel_in = from_gpu;
+                } else if (per_slot) {
+                    SX_CUDA(ctx, cudaMemcpyAsync(r.d_in[slot], from, n * SFB, cudaMemcpyHostToDevice, lane.s_slot[slot]));
                 } else {
                     SX_CUDA(ctx, cudaMemcpyAsync(r.d_in[slot], from, n * SFB, cudaMemcpyHostToDevice, lane.s_h2d));
                     SX_CUDA(ctx, cudaEventRecord(r.copied_in[slot], lane.s_h2d));
@@ -956,9 +973,17 @@ int convert_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset, void *h_d
             void *kernel_out = di.on_device ? static_cast<void *>(static_cast<char *>(di.device_alias) + first * DFB)
                                : kernel_writes_host ? host_to_gpu
                                                     : r.d_out[slot];
-            SX_TRY(launch_convert<Op>(ctx, kernel_in, kernel_out, n, thr2, variant, lane.s_comp));
+            cudaStream_t s_kernel = per_slot ? lane.s_slot[slot] : lane.s_comp;
+            SX_TRY(launch_convert<Op>(ctx, kernel_in, kernel_out, n, thr2, variant, s_kernel));
 
-            if (di.on_device || kernel_writes_host) {
+            if (per_slot) {
+                if (!di.on_device && !kernel_writes_host)
+                    SX_CUDA(ctx, cudaMemcpyAsync(host_to, r.d_out[slot], n * DFB, cudaMemcpyDeviceToHost, s_kernel));
+                // the event is only looked at by the CPU: before a bounce buffer is reused or
+                // bounced out, and for the last K chunks at the end of the call
+                if (bounce_in || use_sidekick || i + size_t(kRingSlots) >= nchunks)
+                    SX_CUDA(ctx, cudaEventRecord(r.done[slot], s_kernel));
+            } else if (di.on_device || kernel_writes_host) {
                 SX_CUDA(ctx, cudaEventRecord(r.done[slot], lane.s_comp));
             } else {
                 SX_CUDA(ctx, cudaEventRecord(r.converted[slot], lane.s_comp));
@@ -1000,8 +1025,8 @@ struct LoopShape {
     LoopKernel kernel;
 };
 const LoopShape kLoopShapes[] = {
-    {2048, 4, bulk_loopback_kernel<2048, 4>}, // default
-    {2048, 3, bulk_loopback_kernel<2048, 3>},
+    {2048, 3, bulk_loopback_kernel<2048, 3>}, // default: 6 543 GB/s of 24 B/frame at 2^27 frames, against 6 085 for 4 stages
+    {2048, 4, bulk_loopback_kernel<2048, 4>},
     {1024, 4, bulk_loopback_kernel<1024, 4>},
     {1024, 6, bulk_loopback_kernel<1024, 6>},
     {1024, 8, bulk_loopback_kernel<1024, 8>},
@@ -1143,6 +1168,7 @@ int64_t *option_slot(sxgpu_ctx *ctx, const char *key)
         {"host_in_mode", &ctx->host_in_mode},
         {"host_out_mode", &ctx->host_out_mode},
         {"bounce_nt", &ctx->bounce_nt},
+        {"pipeline_mode", &ctx->pipeline_mode},
         {"zero_copy_max_frames", &ctx->zero_copy_max_frames},
         {"resident_max_frames", &ctx->resident_max_frames},
         {"zero_copy_variant", &ctx->zero_copy_variant},
@@ -1290,6 +1316,8 @@ int sxgpu_destroy(sxgpu_ctx *ctx)
         if (lane.s_h2d) cudaStreamDestroy(lane.s_h2d);
         if (lane.s_comp) cudaStreamDestroy(lane.s_comp);
         if (lane.s_d2h) cudaStreamDestroy(lane.s_d2h);
+        for (int i = 0; i < kRingSlots; i++)
+            if (lane.s_slot[i]) cudaStreamDestroy(lane.s_slot[i]);
         if (lane.s_resident) cudaStreamDestroy(lane.s_resident); // its kernel has left: asked to, and the device was synchronised
         if (lane.mailbox) cudaFreeHost(lane.mailbox);
         if (lane.flag) cudaFreeHost(lane.flag);
@@ -1417,7 +1445,7 @@ int sxgpu_convert_loopback(sxgpu_ctx *ctx, const void *d_i2s_in, void *d_cf32, v
         if (ctx->bulk_tile || ctx->bulk_stages) { // tuning: option bulk_tile / bulk_stages select a shape
             shape = nullptr;
             for (const LoopShape &c : kLoopShapes)
-                if (c.tile == (ctx->bulk_tile ? ctx->bulk_tile : 2048) && c.stages == (ctx->bulk_stages ? ctx->bulk_stages : 4))
+                if (c.tile == (ctx->bulk_tile ? ctx->bulk_tile : 2048) && c.stages == (ctx->bulk_stages ? ctx->bulk_stages : 3))
                     shape = &c;
             if (!shape)
                 return ctx->invalid("unsupported bulk_tile/bulk_stages combination for the loopback");
@@ -1685,10 +1713,10 @@ int sxgpu_bank_repeat(sxgpu_bank *bank, void *d_cf32, long long rx_time_offset_n
     const bool reg_ok = (b.period % 2 == 0) && reinterpret_cast<uintptr_t>(d_cf32) % 16 == 0;
     int64_t k = ctx->bank_repeat_variant;
     if (k == 0) {
-        if (reg_ok)
-            k = b.nstreams <= 2048 ? 201 : b.nstreams <= 16384 ? 202 : 204;
+        if (b.nstreams <= 2048)
+            k = reg_ok ? 201 : 1;
         else
-            k = b.nstreams <= 2048 ? 1 : b.nstreams <= 8192 ? 2 : b.nstreams <= 32768 ? 4 : 100;
+            k = b.nstreams <= 8192 ? 2 : b.nstreams <= 32768 ? 4 : 100;
     }
     if (k >= 200 && !reg_ok)
         return ctx->invalid("the register schedules need an even period and a 16-byte aligned CF32 buffer");
@@ -1701,7 +1729,13 @@ int sxgpu_bank_repeat(sxgpu_bank *bank, void *d_cf32, long long rx_time_offset_n
     case 201: reg_variant(bank_repeat_reg_kernel<1, IdentityHook>, 1); break;
     case 202: reg_variant(bank_repeat_reg_kernel<2, IdentityHook>, 2); break;
     case 204: reg_variant(bank_repeat_reg_kernel<4, IdentityHook>, 4); break;
-    default: return ctx->invalid("bank_repeat_variant must be 0 (auto), 1, 2, 4, 8, 100, 201, 202 or 204");
+    case 300: { // a CTA takes 32 streams per round: first warp decides, every warp keeps its streams in registers
+        const uint64_t groups = (uint64_t(b.nstreams) + 31) / 32;
+        auto kernel = bank_repeat_group_reg_kernel<IdentityHook>;
+        kernel<<<persistent_grid(ctx, kernel, 256, 0, groups), 256, 0, st>>>(b, cf, rx_time_offset_ns, ext, IdentityHook());
+        break;
+    }
+    default: return ctx->invalid("bank_repeat_variant must be 0 (auto), 1, 2, 4, 8, 100, 201, 202, 204 or 300");
     }
     SX_CUDA(ctx, cudaGetLastError());
     ctx->launches += 1;

@@ -163,3 +163,95 @@ class Device:
         if rc != 0:
             raise PluginError(f"bench_writes: writeStream returned {rc}")
         return sec.value
+
+
+class Group:
+    """N front-ends served as one device: one conversion per period for all of them
+    (csrc/host/SoapySXB200Group.hpp, flat sxg_* view).  Product module only."""
+
+    SIGNATURES = {
+        "sxg_last_error": (C.c_char_p, []),
+        "sxg_create": (C.c_int, [_S, C.c_char_p, C.POINTER(_P)]),
+        "sxg_destroy": (C.c_int, [_P]),
+        "sxg_size": (_S, [_P]),
+        "sxg_period": (_S, [_P]),
+        "sxg_set_sample_rate": (C.c_int, [_P, C.c_double]),
+        "sxg_activate": (C.c_int, [_P]),
+        "sxg_deactivate": (C.c_int, [_P]),
+        "sxg_pcm": (_P, [_P, _S, C.c_int]),
+        "sxg_read_all": (C.c_int, [_P, _P, _S, _P, _P, _P, C.c_long]),
+        "sxg_write_all": (C.c_int, [_P, _P, _S, _P, _P, _P, C.c_long]),
+        "sxg_repeat_all": (C.c_int, [_P, _P, _S, _LL, _P, _P, _P, C.c_long]),
+        "sxg_bench_repeat": (C.c_int, [_P, _S, _LL, C.c_int, C.POINTER(C.c_double)]),
+    }
+
+    def __init__(self, harness: Harness, members: int, args: str = ""):
+        import numpy as np
+        self.np = np
+        self.h, self.lib, self.n = harness, harness.lib, members
+        for name, (res, argt) in self.SIGNATURES.items():
+            fn = getattr(self.lib, name)
+            fn.restype, fn.argtypes = res, argt
+        p = _P()
+        if self.lib.sxg_create(members, args.encode(), C.byref(p)) != 0:
+            raise PluginError(self.lib.sxg_last_error().decode())
+        self.p = p
+        self.period = self.lib.sxg_period(p)
+
+    def close(self):
+        if self.p:
+            self.lib.sxg_destroy(self.p)
+            self.p = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _ck(self, rc, what):
+        if rc == THREW:
+            raise PluginError(f"{what}: {self.lib.sxg_last_error().decode()}")
+        return rc
+
+    def set_rate(self, rate):
+        self._ck(self.lib.sxg_set_sample_rate(self.p, rate), "setSampleRate")
+
+    def activate(self):
+        return self._ck(self.lib.sxg_activate(self.p), "activate")
+
+    def deactivate(self):
+        return self._ck(self.lib.sxg_deactivate(self.p), "deactivate")
+
+    def pcm(self, member: int, capture: bool):
+        return self.lib.sxg_pcm(self.p, member, 1 if capture else 0)
+
+    def read_all(self, cf32_addr, n, timeout_us=1000000):
+        np = self.np
+        rets, flags, t = np.zeros(self.n, np.int32), np.zeros(self.n, np.int32), np.zeros(self.n, np.int64)
+        rc = self._ck(self.lib.sxg_read_all(self.p, cf32_addr, n, rets.ctypes.data, flags.ctypes.data, t.ctypes.data,
+                                            timeout_us), "readAll")
+        return rc, rets, flags, t
+
+    def write_all(self, cf32_addr, n, flags, time_ns, timeout_us=1000000):
+        np = self.np
+        rets = np.zeros(self.n, np.int32)
+        f = np.ascontiguousarray(flags, dtype=np.int32)
+        t = np.ascontiguousarray(time_ns, dtype=np.int64)
+        rc = self._ck(self.lib.sxg_write_all(self.p, cf32_addr, n, f.ctypes.data, t.ctypes.data, rets.ctypes.data,
+                                             timeout_us), "writeAll")
+        return rc, rets
+
+    def repeat_all(self, cf32_addr, n, offset_ns, timeout_us=1000000):
+        np = self.np
+        rx, tx, t = np.zeros(self.n, np.int32), np.zeros(self.n, np.int32), np.zeros(self.n, np.int64)
+        rc = self._ck(self.lib.sxg_repeat_all(self.p, cf32_addr, n, offset_ns, rx.ctypes.data, tx.ctypes.data,
+                                              t.ctypes.data, timeout_us), "repeatAll")
+        return rc, rx, tx, t
+
+    def bench_repeat(self, n, offset_ns, iters) -> float:
+        sec = C.c_double(0)
+        rc = self._ck(self.lib.sxg_bench_repeat(self.p, n, offset_ns, iters, C.byref(sec)), "bench_repeat")
+        if rc != 0:
+            raise PluginError(f"bench_repeat: a member returned {rc}")
+        return sec.value

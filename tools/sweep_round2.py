@@ -58,6 +58,13 @@ def sweep_batched(ctx, side, out):
     rows.append({"shape": "1 x 1 GiB (single-block kernel)", "rx_gbs": 16 * total / sec / 1e9})
     sec = timed(lambda: ctx.convert_tx_buffer(cf.data_ptr(), 0, dst.data_ptr(), 0, total, 1e-6, st), side, 20)
     rows[-1]["tx_gbs"] = 16 * total / sec / 1e9
+    ctx.set_option("bulk_contiguous", 1)     # what does one contiguous tile range per CTA cost by itself?
+    sec = timed(lambda: ctx.convert_rx_buffer(src.data_ptr(), 0, cf.data_ptr(), 0, total, st), side, 20)
+    rows[-1]["rx_contiguous_ranges_gbs"] = 16 * total / sec / 1e9
+    sec = timed(lambda: ctx.convert_tx_buffer(cf.data_ptr(), 0, dst.data_ptr(), 0, total, 1e-6, st), side, 20)
+    rows[-1]["tx_contiguous_ranges_gbs"] = 16 * total / sec / 1e9
+    ctx.set_option("bulk_contiguous", 0)
+    print(json.dumps(rows[-1]), flush=True)
     for log2n in (17, 19, 21, 23, 25):
         n = 1 << log2n
         nb = total // n
@@ -101,7 +108,7 @@ def sweep_loopback(ctx, side, out):
             sec = timed(lambda: ctx.convert_loopback(src.data_ptr(), None, dst.data_ptr(), n, 1e-6, st), side, 20)
             row[f"{name}_16B_gbs"] = 16 * n / sec / 1e9
         ctx.set_option("loopback_variant", 0)
-        for tile, stages in ((2048, 3), (1024, 4), (1024, 6), (1024, 8), (512, 8)):
+        for tile, stages in ((2048, 4), (1024, 6)):
             ctx.set_option("bulk_tile", tile)
             ctx.set_option("bulk_stages", stages)
             for cps in (0, 1):
@@ -124,7 +131,7 @@ def sweep_bank(ctx, side, out):
     for S in (64, 1024, 4096, 16384, 65536):
         cf = torch.empty(S * P * 2, dtype=torch.float32, device="cuda")
         row = {"streams": S}
-        for variant in (1, 2, 4, 100, 201, 202, 204):
+        for variant in (1, 2, 4, 100, 201, 204, 300):
             ctx.set_option("bank_repeat_variant", variant)
             with Bank(ctx, S, P, rate, 0.0, 7) as bank:
                 sec = timed(lambda: bank.repeat(cf.data_ptr(), lat, st), side, 200, warm=5)
@@ -171,34 +178,24 @@ def sweep_host(ctx, out):
     for log2n in (16, 18, 19, 20, 21, 22, 24, 26):
         n = 1 << log2n
         row = {"frames": n}
-        for c_min in (0, 1 << 16):
-            ctx.set_option("host_chunk_min_frames", c_min)
-            for mode in ((0, 1) if log2n <= 19 else (0,)):
-                ctx.set_option("host_mode", mode)
-                key = f"pinned_cmin{c_min}" + ("_pipeline" if mode == 1 else "")
-                row[key + "_gbs"] = round(rate(lambda: ctx.convert_rx_buffer_host(a_in, 0, a_out, 0, n), n), 2)
-            ctx.set_option("host_mode", 0)
+        row["pinned_auto_gbs"] = round(rate(lambda: ctx.convert_rx_buffer_host(a_in, 0, a_out, 0, n), n), 2)
+        ctx.set_option("host_mode", 1)
+        for pmode in (1, 2):
+            ctx.set_option("pipeline_mode", pmode)
+            for out_mode in (1, 2):
+                ctx.set_option("host_out_mode", out_mode)
+                for chunk in (1 << 15, 1 << 16, 1 << 17, 1 << 18, 1 << 19, 1 << 20, 1 << 22):
+                    if chunk * 2 <= n or chunk == 1 << 15:
+                        ctx.set_option("host_chunk_frames", chunk)
+                        row[f"pinned_p{pmode}_out{out_mode}_chunk{chunk}_gbs"] = round(
+                            rate(lambda: ctx.convert_rx_buffer_host(a_in, 0, a_out, 0, n), n), 2)
+        ctx.set_option("host_chunk_min_frames", 1 << 14)
+        ctx.set_option("host_chunk_frames", 1 << 18)
+        ctx.set_option("host_out_mode", 1)
+        row["pinned_p2_ramp16k_to_256k_gbs"] = round(rate(lambda: ctx.convert_rx_buffer_host(a_in, 0, a_out, 0, n), n), 2)
         ctx.set_option("host_chunk_min_frames", 0)
-        for in_mode, out_mode in ((1, 2), (2, 1), (2, 2)):
-            ctx.set_option("host_in_mode", in_mode)
-            ctx.set_option("host_out_mode", out_mode)
-            ctx.set_option("host_mode", 1)
-            row[f"pinned_in{in_mode}_out{out_mode}_gbs"] = round(rate(lambda: ctx.convert_rx_buffer_host(a_in, 0, a_out, 0, n), n), 2)
-            for chunk in (1 << 16, 1 << 18):
-                if chunk * 4 <= n:
-                    ctx.set_option("host_chunk_frames", chunk)
-                    row[f"pinned_in{in_mode}_out{out_mode}_chunk{chunk}_gbs"] = round(
-                        rate(lambda: ctx.convert_rx_buffer_host(a_in, 0, a_out, 0, n), n), 2)
-            ctx.set_option("host_chunk_frames", 0)
-        for chunk in (1 << 16, 1 << 17, 1 << 18, 1 << 19):
-            if chunk * 2 <= n:
-                ctx.set_option("host_in_mode", 1)
-                ctx.set_option("host_out_mode", 1)
-                ctx.set_option("host_chunk_frames", chunk)
-                row[f"pinned_ce_chunk{chunk}_gbs"] = round(rate(lambda: ctx.convert_rx_buffer_host(a_in, 0, a_out, 0, n), n), 2)
         ctx.set_option("host_chunk_frames", 0)
-        ctx.set_option("host_in_mode", 0)
-        ctx.set_option("host_out_mode", 0)
+        ctx.set_option("pipeline_mode", 0)
         ctx.set_option("host_mode", 0)
         for nt in (0, 1):
             ctx.set_option("bounce_nt", nt)
