@@ -239,6 +239,12 @@ int sxgpu_convert_tx_buffer_cs16_host(sxgpu_ctx *ctx, const void *h_src, size_t 
                                       void *h_dest, size_t dest_offset, size_t length,
                                       float tx_threshold2);
 
+/* EXTENSION (no reference behaviour): the 16-bit I2S slot conversions with host buffers. */
+int sxgpu_convert_rx_buffer_s16_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset, void *h_dest,
+                                     size_t dest_offset, size_t length);
+int sxgpu_convert_tx_buffer_s16_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset, void *h_dest,
+                                     size_t dest_offset, size_t length, float tx_threshold2);
+
 /* ---- statistics (off the hot path) ------------------------------------------------------- */
 
 /* Order-sensitive checksum and flag counts over 32-bit words; every field is a sum mod 2^64
@@ -276,6 +282,32 @@ int sxgpu_memcpy_d2h(sxgpu_ctx *ctx, void *h_dst, const void *d_src, size_t byte
 int sxgpu_stream_create(sxgpu_ctx *ctx, sxgpu_stream *out);
 int sxgpu_stream_destroy(sxgpu_ctx *ctx, sxgpu_stream stream);
 int sxgpu_stream_sync(sxgpu_ctx *ctx, sxgpu_stream stream); /* NULL = context stream */
+
+/* ---- several GPUs from one process ----------------------------------------------------------- */
+
+/* One context and one host thread per GPU of `devices` (each ordinal once).  The path shards
+ * trivially -- every output word depends on one input word or one I/Q pair (SoapySX.cpp:108-111,
+ * :121-136), streams have independent counters (:378) -- so nothing crosses between GPUs and
+ * there is no collective: a list of blocks is split, every GPU converts its share at once.
+ * One multi-GPU call at a time per object; the per-GPU contexts (sxgpu_multi_context) stay usable
+ * on their own, e.g. for sxgpu_stats_words on each GPU's output. */
+typedef struct sxgpu_multi sxgpu_multi;
+int sxgpu_multi_create(const int *devices, int ndevices, sxgpu_multi **out);
+int sxgpu_multi_destroy(sxgpu_multi *m);
+int sxgpu_multi_size(sxgpu_multi *m);
+sxgpu_ctx *sxgpu_multi_context(sxgpu_multi *m, int index);
+const char *sxgpu_multi_last_error(sxgpu_multi *m);
+/* HOST buffers (src / dest of every block are host pointers; tx_threshold2 per block): block b is
+ * converted by GPU b mod G through that GPU's host pipeline, all GPUs in parallel, each driven by
+ * its own thread.  Synchronous: returns when every block is done. */
+int sxgpu_multi_convert_rx_host(sxgpu_multi *m, const sxgpu_block *blocks, uint32_t nblocks);
+int sxgpu_multi_convert_tx_host(sxgpu_multi *m, const sxgpu_block *blocks, uint32_t nblocks);
+/* DEVICE buffers: every block is converted on the GPU its source buffer lives on (its destination
+ * must be on the same GPU), one batched launch per GPU on that GPU's context stream.
+ * Asynchronous; sxgpu_multi_sync waits for every GPU. */
+int sxgpu_multi_convert_rx_batch(sxgpu_multi *m, const sxgpu_block *blocks, uint32_t nblocks);
+int sxgpu_multi_convert_tx_batch(sxgpu_multi *m, const sxgpu_block *blocks, uint32_t nblocks);
+int sxgpu_multi_sync(sxgpu_multi *m);
 
 /* ---- tuning and accounting ---------------------------------------------------------------- */
 

@@ -83,6 +83,8 @@ SIGNATURES = {
     "sxgpu_convert_tx_buffer_host": (C.c_int, [_P, _P, _S, _P, _S, _S, _F]),
     "sxgpu_convert_rx_buffer_cs16_host": (C.c_int, [_P, _P, _S, _P, _S, _S]),
     "sxgpu_convert_tx_buffer_cs16_host": (C.c_int, [_P, _P, _S, _P, _S, _S, _F]),
+    "sxgpu_convert_rx_buffer_s16_host": (C.c_int, [_P, _P, _S, _P, _S, _S]),
+    "sxgpu_convert_tx_buffer_s16_host": (C.c_int, [_P, _P, _S, _P, _S, _S, _F]),
     "sxgpu_stats_words": (C.c_int, [_P, _P, _S, C.c_uint64, C.POINTER(Stats), _P]),
     "sxgpu_synth_frames": (C.c_int, [_P, _P, C.c_uint64, _S, C.c_uint64, _P]),
     "sxgpu_malloc": (C.c_int, [_P, C.POINTER(_P), _S]),
@@ -96,6 +98,16 @@ SIGNATURES = {
     "sxgpu_stream_create": (C.c_int, [_P, C.POINTER(_P)]),
     "sxgpu_stream_destroy": (C.c_int, [_P, _P]),
     "sxgpu_stream_sync": (C.c_int, [_P, _P]),
+    "sxgpu_multi_create": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(_P)]),
+    "sxgpu_multi_destroy": (C.c_int, [_P]),
+    "sxgpu_multi_size": (C.c_int, [_P]),
+    "sxgpu_multi_context": (_P, [_P, C.c_int]),
+    "sxgpu_multi_last_error": (C.c_char_p, [_P]),
+    "sxgpu_multi_convert_rx_host": (C.c_int, [_P, _P, C.c_uint32]),
+    "sxgpu_multi_convert_tx_host": (C.c_int, [_P, _P, C.c_uint32]),
+    "sxgpu_multi_convert_rx_batch": (C.c_int, [_P, _P, C.c_uint32]),
+    "sxgpu_multi_convert_tx_batch": (C.c_int, [_P, _P, C.c_uint32]),
+    "sxgpu_multi_sync": (C.c_int, [_P]),
     "sxgpu_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
     "sxgpu_get_option": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_int64)]),
     "sxgpu_get_counter": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_uint64)]),
@@ -207,6 +219,14 @@ class Context:
     def convert_tx_buffer_cs16_host(self, h_src, src_offset, h_dest, dest_offset, length, tx_threshold2):
         self.check(self.lib.sxgpu_convert_tx_buffer_cs16_host(self.handle, h_src, src_offset, h_dest, dest_offset,
                                                               length, tx_threshold2), "sxgpu_convert_tx_buffer_cs16_host")
+
+    def convert_rx_buffer_s16_host(self, h_src, src_offset, h_dest, dest_offset, length):
+        self.check(self.lib.sxgpu_convert_rx_buffer_s16_host(self.handle, h_src, src_offset, h_dest, dest_offset,
+                                                             length), "sxgpu_convert_rx_buffer_s16_host")
+
+    def convert_tx_buffer_s16_host(self, h_src, src_offset, h_dest, dest_offset, length, tx_threshold2):
+        self.check(self.lib.sxgpu_convert_tx_buffer_s16_host(self.handle, h_src, src_offset, h_dest, dest_offset,
+                                                             length, tx_threshold2), "sxgpu_convert_tx_buffer_s16_host")
 
     # -- statistics, synthetic source -----------------------------------------------------------
     def stats_words(self, d_words, nwords, base_index=0, stream=None):
@@ -346,3 +366,57 @@ class Bank:
         self.ctx.check(self.lib.sxgpu_bank_playback(self.handle, index, position, nframes, out.ctypes.data, stream),
                        "sxgpu_bank_playback")
         return out
+
+
+class Multi:
+    """Several GPUs from one process (sxgpu_multi_* in include/sxgpu.h): one context and one host
+    thread per GPU, block lists split between them, no collective."""
+
+    def __init__(self, devices):
+        self.lib = load_library()
+        arr = (C.c_int * len(devices))(*devices)
+        h = _P()
+        rc = self.lib.sxgpu_multi_create(arr, len(devices), C.byref(h))
+        if rc != SXGPU_OK:
+            raise SxGpuError(rc, "sxgpu_multi_create", self.lib.sxgpu_strerror(rc).decode())
+        self.handle, self.devices = h, list(devices)
+
+    def close(self):
+        if self.handle:
+            self.lib.sxgpu_multi_destroy(self.handle)
+            self.handle = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def check(self, rc, what):
+        if rc != SXGPU_OK:
+            raise SxGpuError(rc, what, self.lib.sxgpu_multi_last_error(self.handle).decode())
+
+    def context(self, index: int) -> "Context":
+        """The index-th GPU's own context (owned by the Multi: do not close it)."""
+        c = Context.__new__(Context)
+        c.lib, c.handle, c.device = self.lib, _P(self.lib.sxgpu_multi_context(self.handle, index)), self.devices[index]
+        return c
+
+    def _call(self, fn, blocks, what):
+        arr = (Block * len(blocks))(*blocks)
+        self.check(fn(self.handle, C.cast(arr, _P), len(blocks)), what)
+
+    def convert_rx_host(self, blocks):
+        self._call(self.lib.sxgpu_multi_convert_rx_host, blocks, "sxgpu_multi_convert_rx_host")
+
+    def convert_tx_host(self, blocks):
+        self._call(self.lib.sxgpu_multi_convert_tx_host, blocks, "sxgpu_multi_convert_tx_host")
+
+    def convert_rx_batch(self, blocks):
+        self._call(self.lib.sxgpu_multi_convert_rx_batch, blocks, "sxgpu_multi_convert_rx_batch")
+
+    def convert_tx_batch(self, blocks):
+        self._call(self.lib.sxgpu_multi_convert_tx_batch, blocks, "sxgpu_multi_convert_tx_batch")
+
+    def sync(self):
+        self.check(self.lib.sxgpu_multi_sync(self.handle), "sxgpu_multi_sync")

@@ -10,6 +10,7 @@
 #include "sx_bank.cuh"
 #include "sx_resident.cuh"
 #include "host/par_copy.hpp"
+#include "host/worker_pool.hpp"
 
 #include <algorithm>
 #include <atomic>
@@ -1985,6 +1986,26 @@ int sxgpu_convert_tx_buffer_cs16_host(sxgpu_ctx *ctx, const void *h_src, size_t 
     return r;
 }
 
+int sxgpu_convert_rx_buffer_s16_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset, void *h_dest,
+                                     size_t dest_offset, size_t length)
+{
+    int r = convert_host<RxS16Cf32>(ctx, h_src, src_offset, h_dest, dest_offset, length, 0.0f,
+                                    ctx ? ctx->rx_variant : 0);
+    if (r == SXGPU_OK)
+        ctx->frames_rx += length;
+    return r;
+}
+
+int sxgpu_convert_tx_buffer_s16_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset, void *h_dest,
+                                     size_t dest_offset, size_t length, float tx_threshold2)
+{
+    int r = convert_host<TxCf32S16>(ctx, h_src, src_offset, h_dest, dest_offset, length, tx_threshold2,
+                                    ctx ? ctx->tx_variant : 0);
+    if (r == SXGPU_OK)
+        ctx->frames_tx += length;
+    return r;
+}
+
 int sxgpu_stats_words(sxgpu_ctx *ctx, const void *d_words, size_t nwords, uint64_t base_index,
                       sxgpu_stats *h_out, sxgpu_stream stream)
 {
@@ -2174,6 +2195,189 @@ int sxgpu_get_counter(sxgpu_ctx *ctx, const char *key, uint64_t *value)
     else if (!std::strcmp(key, "resident_calls")) *value = ctx->resident_calls;
     else if (!std::strcmp(key, "flagged_calls")) *value = ctx->flagged_calls;
     else return ctx->invalid("unknown counter");
+    return SXGPU_OK;
+}
+
+} // extern "C"
+
+// ---------------------------------------------------------------------------------------
+// Several GPUs from one process: one context and one host thread per GPU (SURVEY.md section
+// 8(e)).  Blocks and streams are independent, so the only thing the GPUs share is the caller's
+// list of blocks: block b of a host-buffer list goes to GPU b mod G; a device-buffer block goes to
+// the GPU its memory is on.  No data crosses between GPUs and there is no collective.
+// ---------------------------------------------------------------------------------------
+struct sxgpu_multi {
+    std::vector<sxgpu_ctx *> ctx;
+    std::unique_ptr<sxhost::WorkerPool> pool; // G - 1 helpers: GPU g is always driven by thread g
+    std::mutex mutex;                         // one multi-GPU call at a time
+    std::string last_error;
+};
+
+namespace {
+
+template <class Op>
+int multi_convert_host(sxgpu_multi *m, const sxgpu_block *blocks, uint32_t nblocks)
+{
+    if (!m)
+        return SXGPU_ERR_INVALID;
+    if (nblocks == 0)
+        return SXGPU_OK;
+    if (!blocks)
+        return SXGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(m->mutex);
+    const size_t G = m->ctx.size();
+    std::vector<int> rc(G, SXGPU_OK);
+    m->pool->run(G, 1, [&](size_t lo, size_t hi) {
+        for (size_t g = lo; g < hi; g++) {
+            sxgpu_ctx *ctx = m->ctx[g];
+            for (uint32_t b = uint32_t(g); b < nblocks && rc[g] == SXGPU_OK; b += uint32_t(G)) {
+                rc[g] = convert_host<Op>(ctx, blocks[b].src, 0, blocks[b].dest, 0, size_t(blocks[b].length),
+                                         blocks[b].tx_threshold2, lane_of<Op>() ? ctx->tx_variant : ctx->rx_variant);
+                if (rc[g] == SXGPU_OK)
+                    (lane_of<Op>() ? ctx->frames_tx : ctx->frames_rx) += blocks[b].length;
+            }
+        }
+    });
+    for (size_t g = 0; g < G; g++)
+        if (rc[g] != SXGPU_OK) {
+            m->last_error = "GPU " + std::to_string(m->ctx[g]->device) + ": " + sxgpu_last_error(m->ctx[g]);
+            return rc[g];
+        }
+    return SXGPU_OK;
+}
+
+template <class Op>
+int multi_convert_batch(sxgpu_multi *m, const sxgpu_block *blocks, uint32_t nblocks)
+{
+    if (!m)
+        return SXGPU_ERR_INVALID;
+    if (nblocks == 0)
+        return SXGPU_OK;
+    if (!blocks)
+        return SXGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(m->mutex);
+    const size_t G = m->ctx.size();
+    // Sort the blocks by the GPU their source buffer lives on.
+    std::vector<std::vector<sxgpu_block>> mine(G);
+    for (uint32_t b = 0; b < nblocks; b++) {
+        if (blocks[b].length == 0)
+            continue;
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, blocks[b].src) != cudaSuccess || attr.type != cudaMemoryTypeDevice) {
+            cudaGetLastError();
+            m->last_error = "block " + std::to_string(b) + ": source is not device memory";
+            return SXGPU_ERR_INVALID;
+        }
+        size_t g = 0;
+        while (g < G && m->ctx[g]->device != attr.device)
+            g++;
+        if (g == G) {
+            m->last_error = "block " + std::to_string(b) + ": its GPU is not part of this group";
+            return SXGPU_ERR_INVALID;
+        }
+        mine[g].push_back(blocks[b]);
+    }
+    std::vector<int> rc(G, SXGPU_OK);
+    m->pool->run(G, 1, [&](size_t lo, size_t hi) {
+        for (size_t g = lo; g < hi; g++)
+            if (!mine[g].empty())
+                rc[g] = convert_batch<Op>(m->ctx[g], mine[g].data(), uint32_t(mine[g].size()), 0, 0, nullptr);
+    });
+    for (size_t g = 0; g < G; g++)
+        if (rc[g] != SXGPU_OK) {
+            m->last_error = "GPU " + std::to_string(m->ctx[g]->device) + ": " + sxgpu_last_error(m->ctx[g]);
+            return rc[g];
+        }
+    return SXGPU_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int sxgpu_multi_create(const int *devices, int ndevices, sxgpu_multi **out)
+{
+    if (!out)
+        return SXGPU_ERR_INVALID;
+    *out = nullptr;
+    if (!devices || ndevices <= 0)
+        return SXGPU_ERR_INVALID;
+    std::unique_ptr<sxgpu_multi> m(new sxgpu_multi());
+    for (int i = 0; i < ndevices; i++) {
+        for (int j = 0; j < i; j++)
+            if (devices[j] == devices[i]) {
+                for (sxgpu_ctx *c : m->ctx)
+                    sxgpu_destroy(c);
+                return SXGPU_ERR_INVALID; // each GPU once
+            }
+        sxgpu_ctx *c = nullptr;
+        int rc = sxgpu_init(devices[i], &c);
+        if (rc != SXGPU_OK) {
+            for (sxgpu_ctx *done : m->ctx)
+                sxgpu_destroy(done);
+            return rc;
+        }
+        m->ctx.push_back(c);
+    }
+    m->pool.reset(new sxhost::WorkerPool(unsigned(ndevices - 1)));
+    *out = m.release();
+    return SXGPU_OK;
+}
+
+int sxgpu_multi_destroy(sxgpu_multi *m)
+{
+    if (!m)
+        return SXGPU_ERR_INVALID;
+    int worst = SXGPU_OK;
+    for (sxgpu_ctx *c : m->ctx) {
+        int rc = sxgpu_destroy(c);
+        if (rc != SXGPU_OK)
+            worst = rc;
+    }
+    delete m;
+    return worst;
+}
+
+int sxgpu_multi_size(sxgpu_multi *m) { return m ? int(m->ctx.size()) : 0; }
+
+sxgpu_ctx *sxgpu_multi_context(sxgpu_multi *m, int index)
+{
+    return (m && index >= 0 && size_t(index) < m->ctx.size()) ? m->ctx[size_t(index)] : nullptr;
+}
+
+const char *sxgpu_multi_last_error(sxgpu_multi *m)
+{
+    static thread_local std::string mine;
+    if (!m)
+        return "";
+    std::lock_guard<std::mutex> lock(m->mutex);
+    mine = m->last_error;
+    return mine.c_str();
+}
+
+int sxgpu_multi_convert_rx_host(sxgpu_multi *m, const sxgpu_block *blocks, uint32_t nblocks)
+{
+    return multi_convert_host<RxCf32>(m, blocks, nblocks);
+}
+int sxgpu_multi_convert_tx_host(sxgpu_multi *m, const sxgpu_block *blocks, uint32_t nblocks)
+{
+    return multi_convert_host<TxCf32>(m, blocks, nblocks);
+}
+int sxgpu_multi_convert_rx_batch(sxgpu_multi *m, const sxgpu_block *blocks, uint32_t nblocks)
+{
+    return multi_convert_batch<RxCf32>(m, blocks, nblocks);
+}
+int sxgpu_multi_convert_tx_batch(sxgpu_multi *m, const sxgpu_block *blocks, uint32_t nblocks)
+{
+    return multi_convert_batch<TxCf32>(m, blocks, nblocks);
+}
+
+int sxgpu_multi_sync(sxgpu_multi *m)
+{
+    if (!m)
+        return SXGPU_ERR_INVALID;
+    for (sxgpu_ctx *c : m->ctx)
+        SX_TRY(sxgpu_stream_sync(c, nullptr));
     return SXGPU_OK;
 }
 

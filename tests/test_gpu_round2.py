@@ -382,3 +382,22 @@ def test_resident_converter_leaves_when_the_device_is_synchronised(ctx, oracle):
         t.join()
     assert not bad
     assert ctx.counter("resident_launches") >= 2
+
+
+@pytest.mark.parametrize("pinned", [True, False])
+@pytest.mark.parametrize("nframes", [255, 4096, (1 << 21) + 5])
+def test_s16_extension_host_entry_points(ctx, oracle, pinned, nframes):
+    """EXTENSION (no reference: SoapySX.cpp:200-207, :474 run 32-bit slots only): the 16-bit I2S
+    slot conversions through the host-buffer entry points, against their specification in the oracle."""
+    rng = np.random.default_rng(nframes)
+    s16 = rng.integers(-32768, 32768, size=2 * nframes, dtype=np.int64).astype(np.int16)
+    f = sxtest.tx_gaussian_defined(nframes, seed=nframes)
+    hs, hf = torch.from_numpy(s16), torch.from_numpy(f)
+    ho = torch.zeros(2 * nframes, dtype=torch.float32)
+    hi = torch.zeros(2 * nframes, dtype=torch.int16)
+    if pinned:
+        hs, hf, ho, hi = hs.pin_memory(), hf.pin_memory(), ho.pin_memory(), hi.pin_memory()
+    ctx.convert_rx_buffer_s16_host(hs.data_ptr(), 0, ho.data_ptr(), 0, nframes)
+    assert np.array_equal(bits(ho.numpy()), bits(sxtest.oracle_rx_s16(oracle, s16)))
+    ctx.convert_tx_buffer_s16_host(hf.data_ptr(), 0, hi.data_ptr(), 0, nframes, sxtest.THR2_DEFAULT)
+    assert np.array_equal(hi.numpy(), sxtest.oracle_tx_s16(oracle, f, sxtest.THR2_DEFAULT))

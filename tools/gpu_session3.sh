@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_round2.py tests/test_gpu_hook.py tests/test_gpu_group.py tests/test_gpu_bank.py tests/test_gpu_convert.py tests/test_gpu_stream.py tests/test_gpu_stream_fuzz.py tests/test_gpu_compat.py tests/test_gpu_fuzz.py tests/test_bench_contract.py -m gpu -q --maxfail=25 -p no:cacheprovider > gpurun_out/s3_pytest.log 2>&1
+timeout 900 python -m pytest tests/test_gpu_round2.py tests/test_gpu_hook.py tests/test_gpu_group.py tests/test_gpu_bank.py tests/test_gpu_convert.py tests/test_gpu_stream.py tests/test_gpu_stream_fuzz.py tests/test_gpu_compat.py tests/test_gpu_multi_device.py tests/test_gpu_fuzz.py tests/test_bench_contract.py -m gpu -q --maxfail=25 -p no:cacheprovider > gpurun_out/s3_pytest.log 2>&1
 echo "pytest exit $?" >> gpurun_out/s3_pytest.log
 tail -30 gpurun_out/s3_pytest.log
 timeout 1200 python tools/sweep_round2.py --tag s3_sweep > gpurun_out/s3_sweep.log 2>&1
