@@ -541,17 +541,26 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
     e2e_frames = min(1 << args.e2e_log2_frames, frames)
     bounce = max(1, threads_here // e2e_streams - 1)
     dev_args = f", gpu={local_rank}, sxgpu.bounce_threads={bounce}"
-    streams = PluginStreams(product, e2e_frames, e2e_streams, args.e2e_buffers, dev_args, ctx, SEED + rank)
-    try:
-        barrier()
-        e2e_sec = streams.run(args.steps, max(args.warmup, 3))
-        barrier()
-        e2e_launches = sum(d.counter("launches") for d in streams.devs)
-    finally:
-        streams.close()
-    e2e_per_rank = [2 * e2e_frames / t / 1e6 for t in all_ranks(e2e_sec)]
-    e2e_sec = max_over_ranks(e2e_sec)
-    e2e_value = world * 2 * e2e_frames / e2e_sec / 1e6
+    def plugin_leg(kind):
+        streams = PluginStreams(product, e2e_frames, e2e_streams, kind, dev_args, ctx, SEED + rank)
+        try:
+            barrier()
+            sec = streams.run(args.steps, max(args.warmup, 3))
+            barrier()
+            nlaunch = sum(d.counter("launches") for d in streams.devs)
+        finally:
+            streams.close()
+        per_rank = [2 * e2e_frames / t / 1e6 for t in all_ranks(sec)]
+        sec = max_over_ranks(sec)
+        return {"value": world * 2 * e2e_frames / sec / 1e6, "sec": sec, "per_rank": per_rank, "launches": nlaunch}
+
+    legs = {args.e2e_buffers: plugin_leg(args.e2e_buffers)}
+    if not args.no_rows:                 # the other kinds of caller memory, same workload
+        for kind in ("pinned", "pin", "pageable"):
+            if kind not in legs:
+                legs[kind] = plugin_leg(kind)
+    head = legs[args.e2e_buffers]
+    e2e_sec, e2e_value, e2e_per_rank, e2e_launches = head["sec"], head["value"], head["per_rank"], head["launches"]
     # bytes that crossed the link each way per second on this rank, against what the link carries
     e2e_link_gbs = [v * 1e6 * 8 / 1e9 for v in e2e_per_rank]
     frac_of_link = [a / b if b else None for a, b in zip(e2e_link_gbs, link["both_each_way_gbs"])]
@@ -664,6 +673,10 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
                     "raw_link_gbs_per_rank": {k: [round(x, 2) for x in v] for k, v in link.items()},
                     "link_gbs_each_way_per_rank": [round(v, 2) for v in e2e_link_gbs],
                     "frac_of_link": [round(v, 3) if v is not None else None for v in frac_of_link],
+                    "by_caller_memory": {k: {"value": round(v["value"], 1), "ms_per_step": round(v["sec"] * 1e3, 3),
+                                             "frac_of_link": [round(x * 1e6 * 8 / 1e9 / l, 3) if l else None
+                                                              for x, l in zip(v["per_rank"], link["both_each_way_gbs"])]}
+                                         for k, v in legs.items()},
                     "plugin_rows": rows},
             "gpu_launches": launches, "clocks": clocks, "cpu_baseline": cpu, "small_blocks": small,
             "checksums": {"fields": list(sharding.STATS_FIELDS), "per_rank": checks,
@@ -798,6 +811,212 @@ def run_bank_arm(args, rank: int, local_rank: int, world: int):
         dist.destroy_process_group()
 
 
+def run_sweep_arm(args, rank: int, local_rank: int, world: int):
+    """--workload sweep: BASELINE config 5's small end.  1 GiB of RX and 1 GiB of TX work per GPU
+    per step as N independent blocks in ONE launch each (sxgpu_convert_*_batch, device-resident
+    descriptor lists), N x size from 1024 x 1 MiB to 1 x 1 GiB.  `value` is the whole sweep's
+    aggregate; `sweep` has one row per shape with its fraction of the measured HBM peak."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from sxxcvr_b200 import Context
+    from sxxcvr_b200.capi import Block
+
+    torch.cuda.set_device(local_rank)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ctx = Context(local_rank)
+    total = 1 << args.log2_frames
+    side = torch.cuda.Stream()
+    torch.cuda.set_stream(side)
+    st = side.cuda_stream
+    src = torch.empty(2 * total, dtype=torch.int32, device="cuda")
+    cf = torch.empty(2 * total, dtype=torch.float32, device="cuda")
+    dst = torch.empty(2 * total, dtype=torch.int32, device="cuda")
+    ctx.synth_frames(src.data_ptr(), 0, total, SEED + rank, st)
+    peak, peak_src = measured_peak()
+    rows, all_ms, launches0 = [], 0.0, ctx.counter("launches")
+    for log2n in (17, 19, 21, 23, args.log2_frames):
+        n = 1 << log2n
+        nb = total // n
+        lists = []
+        for a, b, thr in ((src, cf, 0.0), (cf, dst, THR2)):
+            arr = (Block * nb)(*[Block(a.data_ptr() + 8 * n * k, b.data_ptr() + 8 * n * k, n, thr, 0) for k in range(nb)])
+            lists.append(torch.from_numpy(np.frombuffer(bytes(arr), dtype=np.uint8).copy()).cuda())
+
+        def step():
+            ctx.convert_batch("rx", lists[0].data_ptr(), on_device=True, max_length=n, stream=st, nblocks=nb)
+            ctx.convert_batch("tx", lists[1].data_ptr(), on_device=True, max_length=n, stream=st, nblocks=nb)
+
+        for _ in range(max(args.warmup, 3)):
+            step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(side)
+        for _ in range(args.steps):
+            step()
+        e1.record(side)
+        barrier()
+        ms = e0.elapsed_time(e1) / args.steps
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        all_ms += ms
+        gbs = 2 * total * BYTES_PER_FRAME / (ms * 1e-3) / 1e9
+        rows.append({"blocks_per_launch": nb, "block_bytes": 8 * n, "frames_per_block": n, "ms_per_step": ms,
+                     "msamples_per_s": world * 2 * total / (ms * 1e-3) / 1e6, "hbm_gbs_per_gpu": gbs, "frac": gbs / peak})
+    launches = ctx.counter("launches") - launches0
+    worst = min(rows, key=lambda r: r["frac"])
+    if rank == 0:
+        emit(json.dumps({
+            "metric": METRIC, "value": world * 2 * total * len(rows) / (all_ms * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": all_ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "s32<->f32", "data": "synthetic",
+            "config": {"workload": "BASELINE config 5, small end: 1 GiB of RX + 1 GiB of TX per GPU per step as N blocks in one "
+                                   "launch each (sxgpu_convert_rx_batch / _tx_batch), N x size swept; a step here = all shapes once",
+                       "frames_per_step_per_gpu": 2 * total * len(rows), "bytes_per_frame": BYTES_PER_FRAME,
+                       "cache": "buffers of 1 GiB >> 126 MB L2",
+                       "parallelism": f"blocks sharded over {world} GPU(s), no data-path collective"},
+            "roofline": {"kernel": "bulk_batch_kernel (worst shape of the sweep)", "bound": "hbm",
+                         "achieved": worst["hbm_gbs_per_gpu"], "peak": peak, "unit": "GB/s", "frac": worst["frac"],
+                         "traffic": None, "peak_source": peak_src, "shape": f"{worst['blocks_per_launch']} x {worst['block_bytes'] >> 20} MiB"},
+            "sweep": rows, "e2e": None, "gpu_launches": launches, "cpu_baseline": None}))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_group_arm(args, rank: int, local_rank: int, world: int):
+    """--workload group: BASELINE config 4 with frames that come from N host-side ALSA stand-ins.
+    S front-ends per GPU behind ONE group device (SoapySXB200Group): a step is readStream(256) on
+    every member + writeStream(256, HAS_TIME, rx time + 768 frames) on every member, all members'
+    conversions in one launch; the reference beside it is S unmodified SoapySX devices stepped
+    one after the other on one thread (how one process would serve them)."""
+    import torch
+    import torch.distributed as dist
+    from sxxcvr_b200 import plugin
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    product = plugin.Harness()
+    P, rate = 256, 75000.0
+    lat = int(round(768 * 1e9 / rate))
+    rows = []
+    for S in (64, 1024, 4096):
+        with plugin.Group(product, S, f"gpu={local_rank}, threshold=0") as g:
+            g.set_rate(rate)
+            g.activate()
+            for i in range(S):
+                product.lib.sx_alsa_set_sink_limit(g.pcm(i, False), 0)
+            g.bench_repeat(P, lat, 5)
+            iters = max(20, min(500, 200000 // S))
+            sec = g.bench_repeat(P, lat, iters) / iters
+            rc, rx, tx, t = g.repeat_all(0, P, lat)
+            ok = rc == 0 and bool((rx == P).all() and (tx == P).all())
+            launches = 0
+        row = {"members": S, "us_per_iteration": sec * 1e6, "us_per_member": sec / S * 1e6,
+               "msamples_per_s": 2 * S * P / sec / 1e6, "all_members_returned_full_blocks": ok}
+        rows.append(row)
+    # The reference beside it: one unmodified SoapySX device's read+write pair, timed natively; a
+    # process serving S front-ends with it pays that per member per period (its converters run on
+    # the calling thread).
+    ref_pair_us = None
+    ref = reference_harness() if (rank == 0 and world == 1) else None
+    if ref is not None:
+        one = PluginStreams(ref, P, 1)
+        try:
+            ref_pair_us = one.run(5000, 50) * 1e6
+        finally:
+            one.close()
+        for row in rows:
+            row["reference_us_per_member"] = ref_pair_us
+            row["reference_us_per_iteration_one_thread"] = ref_pair_us * row["members"]
+    if world > 1:
+        vals = [None] * world
+        dist.all_gather_object(vals, rows[-1]["us_per_iteration"])
+        worst_us = max(vals)
+    else:
+        worst_us = rows[-1]["us_per_iteration"]
+    if rank == 0:
+        S = rows[-1]["members"]
+        emit(json.dumps({
+            "metric": METRIC, "value": world * 2 * S * P / (worst_us * 1e-6) / 1e6, "unit": UNIT, "n_gpus": world,
+            "steps": None, "warmup": 5, "ms_per_step": worst_us * 1e-3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "s32<->f32", "data": "synthetic",
+            "config": {"workload": "BASELINE config 4 through the group device: S front-ends (each its own ALSA stand-in pair) per GPU, "
+                                   "per step readStream(256) + writeStream(256, HAS_TIME, +768 frames) on every member, one launch for all",
+                       "members_per_gpu": S, "frames_per_block": P, "sample_rate": rate,
+                       "parallelism": f"members sharded over {world} GPU(s), no data-path collective"},
+            "group": rows, "e2e": {"value": world * 2 * S * P / (worst_us * 1e-6) / 1e6, "unit": UNIT,
+                                   "h2d_bytes_per_step": 8 * S * P, "d2h_bytes_per_step": 16 * S * P},
+            "roofline": None, "gpu_launches": None, "cpu_baseline": None}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_single_process_arm(args):
+    """--single-process --gpus N: the device-resident workload driven from ONE process through
+    sxgpu_multi_* (one context and one host thread per GPU) instead of one
+    rank per GPU.  Wall clock around K steps, every GPU synchronised on both sides."""
+    import torch
+    from sxxcvr_b200 import Multi
+    from sxxcvr_b200.capi import Block
+
+    G = args.gpus
+    if torch.cuda.device_count() < G:
+        raise SystemExit(f"bench.py --single-process: {G} GPUs requested, {torch.cuda.device_count()} visible")
+    frames = 1 << args.log2_frames
+    with Multi(list(range(G))) as m:
+        bufs = []
+        for g in range(G):
+            dev = f"cuda:{g}"
+            i2s = torch.empty(2 * frames, dtype=torch.int32, device=dev)
+            cf = torch.empty(2 * frames, dtype=torch.float32, device=dev)
+            out = torch.empty(2 * frames, dtype=torch.int32, device=dev)
+            m.context(g).synth_frames(i2s.data_ptr(), 0, frames, SEED + g)
+            bufs.append((i2s, cf, out))
+        m.sync()
+        rx = [Block(b[0].data_ptr(), b[1].data_ptr(), frames, 0.0, 0) for b in bufs]
+        tx = [Block(b[1].data_ptr(), b[2].data_ptr(), frames, THR2, 0) for b in bufs]
+        for _ in range(max(args.warmup, 3)):
+            m.convert_rx_batch(rx)
+            m.convert_tx_batch(tx)
+        m.sync()
+        l0 = sum(m.context(g).counter("launches") for g in range(G))
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            m.convert_rx_batch(rx)
+            m.convert_tx_batch(tx)
+        m.sync()
+        sec = (time.perf_counter() - t0) / args.steps
+        launches = sum(m.context(g).counter("launches") for g in range(G)) - l0
+        checks = [list(m.context(g).stats_words(bufs[g][2].data_ptr(), 2 * frames, 0)) for g in range(G)]
+    peak, peak_src = measured_peak()
+    gbs = 2 * frames * BYTES_PER_FRAME / sec / 1e9
+    args.gpus = G
+    emit(json.dumps({
+        "metric": METRIC, "value": G * 2 * frames / sec / 1e6, "unit": UNIT, "n_gpus": G, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "s32<->f32", "data": "synthetic",
+        "config": dict(workload_config(args, frames),
+                       parallelism=f"ONE process, {G} contexts and host threads (sxgpu_multi_*), one block per GPU per launch, no collective",
+                       timing="wall clock around the timed steps, every GPU synchronised on both sides"),
+        "roofline": {"kernel": "bulk_batch_kernel, one 1 GiB block per GPU", "bound": "hbm", "achieved": gbs, "peak": peak,
+                     "unit": "GB/s", "frac": gbs / peak, "traffic": None, "peak_source": peak_src,
+                     "note": "per-GPU average over the RX+TX step, launch gaps included"},
+        "e2e": None, "gpu_launches": launches, "cpu_baseline": None,
+        "checksums": {"per_gpu": checks}}))
+
+
 class QuietStdout:
     """stdout must carry exactly one JSON line.  Native libraries write banners to file descriptor 1
     (NCCL prints its version there when NCCL_DEBUG is set), so for the duration of the run fd 1
@@ -840,16 +1059,21 @@ def main():
     ap.add_argument("--log2-frames", type=int, default=27, help="frames per block per GPU (2^27 = 1 GiB in)")
     ap.add_argument("--e2e-log2-frames", type=int, default=27, help="frames per block of the plugin leg (capped at --log2-frames)")
     ap.add_argument("--e2e-streams", type=int, default=0, help="devices (caller threads) per GPU in the plugin leg; 0 = auto")
-    ap.add_argument("--e2e-buffers", default="pageable", choices=["pageable", "pin", "pinned"],
-                    help="caller buffers of the plugin leg: pageable numpy (default, what the reference's callers pass), "
-                         "the same with pin=1, or sxgpu_malloc_host memory")
+    ap.add_argument("--e2e-buffers", default="pinned", choices=["pageable", "pin", "pinned"],
+                    help="caller buffers of the headline plugin leg: sxgpu_malloc_host memory (default: the contract's "
+                         "'host->device copy from pinned host memory'), pageable numpy arrays with pin=1, or plain pageable "
+                         "numpy arrays (what the reference's callers pass); the other two are reported beside it")
     ap.add_argument("--min-seconds", type=float, default=1.0,
                     help="also report the device-resident figure sustained over at least this long (0 = skip)")
     ap.add_argument("--no-rows", action="store_true", help="skip the one-stream frames-per-call x buffer-kind table")
     ap.add_argument("--cpu-log2-frames", type=int, default=27, help="frames per step of the cpu_baseline sample inside the GPU arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="blocks", choices=["blocks", "bank"],
-                    help="blocks: the judged RX+TX block workload (default); bank: BASELINE config 4")
+    ap.add_argument("--workload", default="blocks", choices=["blocks", "bank", "sweep", "group"],
+                    help="blocks: the judged RX+TX block workload (default); bank: BASELINE config 4 (HBM-resident streams); "
+                         "sweep: config 5's block-size sweep, many blocks per launch; group: config 4 through the group "
+                         "device, frames from N host ALSA stand-ins")
+    ap.add_argument("--single-process", action="store_true",
+                    help="drive --gpus N from ONE process (sxgpu_multi_*: a context and a host thread per GPU) instead of one rank per GPU")
     ap.add_argument("--streams", type=int, default=65536, help="--workload bank: stream pairs per GPU")
     ap.add_argument("--graph", action="store_true", help="--workload bank: replay the step from a CUDA graph")
     ap.add_argument("--repeat-variant", type=int, default=None, help="--fused: option bank_repeat_variant")
@@ -859,6 +1083,11 @@ def main():
     args = ap.parse_args()
 
     rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
+    if args.single_process and args.impl != "reference":
+        global OUT
+        with QuietStdout() as OUT:
+            run_single_process_arm(args)
+        return
     if world == 1 and args.gpus > 1:
         # Launched without torchrun: re-exec under it so there is one process per GPU.
         port = 29500 + os.getpid() % 2000
@@ -866,12 +1095,15 @@ def main():
                "--master-addr", "127.0.0.1", "--master-port", str(port), __file__] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd))
 
-    global OUT
     with QuietStdout() as OUT:
         if args.impl == "reference":
             run_reference_arm(args, rank)
         elif args.workload == "bank":
             run_bank_arm(args, rank, local_rank, world)
+        elif args.workload == "sweep":
+            run_sweep_arm(args, rank, local_rank, world)
+        elif args.workload == "group":
+            run_group_arm(args, rank, local_rank, world)
         else:
             run_gpu_arm(args, rank, local_rank, world)
 

@@ -685,10 +685,15 @@ __global__ void batch_slice_kernel(const BlockDesc *__restrict__ blocks, uint32_
 // ---------------------------------------------------------------------------------------
 struct BatchBulkArgs {
     const BlockDesc *blocks;
-    const unsigned long long *tile_start; // [nblocks + 1]
+    const unsigned long long *tile_start; // [nblocks + 1] in device memory, or null: summed in the kernel
     uint32_t nblocks;
     int load_policy, store_policy;
 };
+
+// Lists of up to this many blocks need no tile_start from outside: every CTA sums the lengths
+// itself into shared memory (16 KiB), which saves a kernel launch and a scratch allocation per
+// batch -- together more than the conversion of a small batch takes.
+constexpr uint32_t kBatchLocalBlocks = 2048;
 
 struct TileRecord {
     const char *src; // first frame of the tile
@@ -710,42 +715,43 @@ struct BatchCursor {
     unsigned long long next_end;  // tile_start[blk + 2]
 };
 
-__device__ __forceinline__ void batch_cursor_prefetch(const BatchBulkArgs &a, BatchCursor &c)
+__device__ __forceinline__ void batch_cursor_prefetch(const BatchBulkArgs &a, const unsigned long long *ts, BatchCursor &c)
 {
     if (c.blk + 1 < a.nblocks) {
         c.next_desc = a.blocks[c.blk + 1];
-        c.next_end = a.tile_start[c.blk + 2];
+        c.next_end = ts[c.blk + 2];
     }
 }
 
-__device__ __forceinline__ void batch_cursor_seek(const BatchBulkArgs &a, BatchCursor &c, unsigned long long t)
+__device__ __forceinline__ void batch_cursor_seek(const BatchBulkArgs &a, const unsigned long long *ts, BatchCursor &c,
+                                                  unsigned long long t)
 {
     // binary search: the last block whose first tile is <= t (steps over empty blocks)
     uint32_t lo = 0, hi = a.nblocks - 1;
     while (lo < hi) {
         const uint32_t mid = lo + (hi - lo + 1) / 2;
-        if (a.tile_start[mid] <= t)
+        if (ts[mid] <= t)
             lo = mid;
         else
             hi = mid - 1;
     }
     c.blk = lo;
-    c.first = a.tile_start[lo];
-    c.end = a.tile_start[lo + 1];
+    c.first = ts[lo];
+    c.end = ts[lo + 1];
     c.desc = a.blocks[lo];
-    batch_cursor_prefetch(a, c);
+    batch_cursor_prefetch(a, ts, c);
 }
 
 template <int TILE>
-__device__ __forceinline__ void batch_tile_record(const BatchBulkArgs &a, unsigned long long t, BatchCursor &c,
-                                                  TileRecord &rec, int src_frame_bytes, int dst_frame_bytes)
+__device__ __forceinline__ void batch_tile_record(const BatchBulkArgs &a, const unsigned long long *ts, unsigned long long t,
+                                                  BatchCursor &c, TileRecord &rec, int src_frame_bytes, int dst_frame_bytes)
 {
     while (t >= c.end) { // next block (tiles arrive in increasing order); empty blocks fall through
         c.blk++;
         c.first = c.end;
         c.end = c.next_end;
         c.desc = c.next_desc;
-        batch_cursor_prefetch(a, c);
+        batch_cursor_prefetch(a, ts, c);
     }
     const uint64_t lo = (t - c.first) * uint64_t(TILE);
     const uint64_t left = c.desc.length - lo;
@@ -761,7 +767,42 @@ __device__ __forceinline__ void batch_tile_record(const BatchBulkArgs &a, unsign
     rec.bulk_frames = aligned ? (n / unit) * unit : 0u;
 }
 
-template <class Op, int TILE, int STAGES>
+// tile_start for the CTA's own use: 256 threads sum a contiguous run of blocks each, the run
+// totals are scanned across the CTA (shuffles within a warp, shared memory across warps), and
+// every thread writes its run's exclusive prefix.  ts has nblocks + 1 entries in shared memory.
+template <int TILE>
+__device__ __forceinline__ void batch_local_scan(const BatchBulkArgs &a, unsigned long long *ts)
+{
+    __shared__ unsigned long long warp_total[8];
+    const uint32_t per = (a.nblocks + blockDim.x - 1) / blockDim.x;
+    const uint32_t lo = threadIdx.x * per, hi = lo + per < a.nblocks ? lo + per : a.nblocks;
+    unsigned long long sum = 0;
+    for (uint32_t b = lo; b < hi; b++)
+        sum += (a.blocks[b].length + TILE - 1) / TILE;
+    unsigned long long incl = sum; // inclusive scan over the warp
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const unsigned long long up = __shfl_up_sync(0xffffffffu, incl, off);
+        if ((threadIdx.x & 31) >= uint32_t(off))
+            incl += up;
+    }
+    if ((threadIdx.x & 31) == 31)
+        warp_total[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    unsigned long long before = 0;
+    for (uint32_t w = 0; w < (threadIdx.x >> 5); w++)
+        before += warp_total[w];
+    unsigned long long acc = before + incl - sum;
+    for (uint32_t b = lo; b < hi; b++) {
+        ts[b] = acc;
+        acc += (a.blocks[b].length + TILE - 1) / TILE;
+    }
+    if (threadIdx.x == blockDim.x - 1)
+        ts[a.nblocks] = before + incl;
+    __syncthreads();
+}
+
+template <class Op, int TILE, int STAGES, bool LOCAL_SCAN>
 __global__ void __launch_bounds__(256) bulk_batch_kernel(const BatchBulkArgs a)
 {
     constexpr int SFB = Op::kSrcWords * 4, DFB = Op::kDstWords * 4;
@@ -771,10 +812,16 @@ __global__ void __launch_bounds__(256) bulk_batch_kernel(const BatchBulkArgs a)
     unsigned char *out_buf = smem + size_t(STAGES) * IN_STAGE;
     uint64_t *full = reinterpret_cast<uint64_t *>(out_buf + size_t(STAGES) * OUT_STAGE);
     TileRecord *recs = reinterpret_cast<TileRecord *>(full + STAGES);
+    const unsigned long long *ts = a.tile_start;
+    if constexpr (LOCAL_SCAN) {
+        unsigned long long *local = reinterpret_cast<unsigned long long *>(recs + STAGES);
+        batch_local_scan<TILE>(a, local);
+        ts = local;
+    }
 
     // Each CTA owns one contiguous range of tiles: consecutive tiles mostly belong to the same
     // block, so the producer touches the descriptor list only at block boundaries.
-    const uint64_t ntiles = a.tile_start[a.nblocks];
+    const uint64_t ntiles = ts[a.nblocks];
     const uint64_t per = (ntiles + gridDim.x - 1) / gridDim.x;
     const uint64_t first = uint64_t(blockIdx.x) * per;
     if (first >= ntiles)
@@ -793,7 +840,7 @@ __global__ void __launch_bounds__(256) bulk_batch_kernel(const BatchBulkArgs a)
     auto produce = [&](uint64_t i) { // fills recs[i % STAGES] and, for a bulk tile, starts its load
         const int s = int(i % STAGES);
         TileRecord rec;
-        batch_tile_record<TILE>(a, first + i, cur, rec, SFB, DFB);
+        batch_tile_record<TILE>(a, ts, first + i, cur, rec, SFB, DFB);
         recs[s] = rec;
         if (rec.bulk_frames) {
             bulk::mbar_expect_tx(&full[s], rec.bulk_frames * SFB);
@@ -801,7 +848,7 @@ __global__ void __launch_bounds__(256) bulk_batch_kernel(const BatchBulkArgs a)
         }
     };
     if (threadIdx.x == 0) {
-        batch_cursor_seek(a, cur, first);
+        batch_cursor_seek(a, ts, cur, first);
         for (uint64_t i = 0; i < uint64_t(STAGES) && i < mine; i++)
             produce(i);
     }

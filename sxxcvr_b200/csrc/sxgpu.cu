@@ -102,7 +102,7 @@ struct sxgpu_ctx {
     int64_t host_in_mode = 0;               // pipeline input side: 0 auto (= 1), 1 copy engine, 2 read by the kernel across PCIe
     int64_t host_out_mode = 0;              // pipeline output side: 0 auto (= 1), 1 copy engine, 2 written by the kernel across PCIe
     int64_t bounce_nt = 1;                  // bounce copies use cache-bypassing stores
-    int64_t pipeline_mode = 0;              // 0 auto (= 2); 1 = copy-in / compute / copy-out streams chained by events;
+    int64_t pipeline_mode = 0;              // 0 auto (= 1); 1 = copy-in / compute / copy-out streams chained by events;
                                             // 2 = one stream per ring slot, each chunk's three operations in order on it
     int64_t zero_copy_max_frames = 1 << 18; // measured crossover, profiles/r01_sweep_host_path.json
     int64_t resident_max_frames = 0;        // > 0: blocks up to this size go to the resident converter
@@ -124,6 +124,8 @@ struct sxgpu_ctx {
 
     // host pipeline: lane 0 serves the RX conversions, lane 1 the TX conversions
     HostLane lanes[2];
+
+    cudaMemPool_t scratch_pool = nullptr; // stream-ordered scratch of the batch entry points
 
     // statistics scratch
     StatsAcc *d_stats = nullptr;
@@ -562,8 +564,11 @@ size_t pick_chunk_frames(const sxgpu_ctx *ctx, size_t length)
 {
     if (ctx->host_chunk_frames > 0)
         return size_t(std::max<int64_t>(ctx->host_chunk_frames, 1024));
-    size_t chunk = size_t(1) << 18;
-    while (chunk < (size_t(1) << 22) && chunk * 8 < length)
+    // Measured (profiles/r02_summary.md, host path): a quarter of the block, between 1 MiB and
+    // 32 MiB per side.  Every queued copy costs ~5 us on the copy engine whatever its size, so
+    // chunks below 1 MiB lose more to that than they save in pipeline fill and drain.
+    size_t chunk = size_t(1) << 17;
+    while (chunk < (size_t(1) << 22) && chunk * 4 < length)
         chunk <<= 1;
     return chunk;
 }
@@ -867,7 +872,13 @@ int convert_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset, void *h_d
     // sidekick thread (and its helpers) as each chunk's device-to-host copy completes -- so the
     // two directions' CPU copies, the DMA and the kernels of different chunks all overlap.
     const bool bounce_in = !si.pinned && !si.on_device, bounce_out = !di.pinned && !di.on_device;
-    const bool in_zero_copy = ctx->host_in_mode == 2, out_zero_copy = ctx->host_out_mode == 2;
+    // Up to 2^23 frames the kernel writes its output straight into pinned host memory (posted
+    // writes across PCIe run at copy-engine speed) instead of leaving it to a third pipeline stage:
+    // one stage less to fill and drain, +5-10 % at 2^19-2^22 frames; beyond that the copy engine is
+    // ahead by 2-5 %.  The input side always goes through the copy engine (SM reads of host memory
+    // reach 60-70 % of it).
+    const bool in_zero_copy = ctx->host_in_mode == 2;
+    const bool out_zero_copy = ctx->host_out_mode == 2 || (ctx->host_out_mode == 0 && length <= (size_t(1) << 23));
     const size_t c_max = std::min<size_t>(length, pick_chunk_frames(ctx, length));
     // + 128: the cap is rounded up to 64 frames and the last chunk carries the ragged end (< 64)
     SX_TRY(ensure_ring(ctx, lane, c_max + 128, bounce_in, bounce_out));
@@ -912,13 +923,13 @@ int convert_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset, void *h_d
         }
         return rc;
     };
-    // Two ways to order a chunk's three operations (copy in, convert, copy out).  Chained: one
-    // stream per kind of operation, events between them -- eight runtime calls per chunk, which at
-    // ~1.5 us each is the whole transfer time of a 512 KiB chunk.  Per slot (default): one stream
-    // per ring slot, the chunk's operations in order on it and chunk i + K behind chunk i on the
-    // same stream, so that the device buffers of a slot need no event at all; different slots'
-    // streams overlap each other on the copy engines and the SMs.  Three or four calls per chunk.
-    const bool per_slot = ctx->pipeline_mode != 1;
+    // Two ways to order a chunk's three operations (copy in, convert, copy out).  Chained
+    // (default): one stream per kind of operation, events between them.  Per slot: one stream per
+    // ring slot, the chunk's operations in order on it and chunk i + K behind chunk i on the same
+    // stream, so that the device buffers of a slot need no event at all -- three or four runtime
+    // calls per chunk instead of eight.  Measured equal within noise (r02): the pipeline is bound
+    // by the copy engines' per-copy cost, not by the calling thread.
+    const bool per_slot = ctx->pipeline_mode == 2;
     // Slot i % K is free again once chunk i - K has left it: its device-to-host copy is complete
     // (and, for a pageable destination, bounced out).  With one stream per slot the device side
     // orders itself; only a pinned bounce buffer about to be refilled by the CPU needs the wait.
@@ -1015,9 +1026,10 @@ static_assert(sizeof(sxgpu_block) == sizeof(BlockDesc), "descriptor layouts must
 
 // Tile shape of the batched bulk kernel and of the bulk loopback: the large-block default.
 constexpr int kBatchTile = 2048, kBatchStages = 4;
-template <class Op> constexpr size_t batch_smem_bytes()
+template <class Op> constexpr size_t batch_smem_bytes(bool local_scan)
 {
-    return size_t(kBatchStages) * (size_t(kBatchTile) * (Op::kSrcWords + Op::kDstWords) * 4 + 8 + sizeof(TileRecord));
+    return size_t(kBatchStages) * (size_t(kBatchTile) * (Op::kSrcWords + Op::kDstWords) * 4 + 8 + sizeof(TileRecord)) +
+           (local_scan ? (size_t(kBatchLocalBlocks) + 1) * sizeof(unsigned long long) : 0);
 }
 // Shapes of the bulk loopback kernel (three buffers per stage: 24 KiB per 1024 frames).
 typedef void (*LoopKernel)(const BulkLoopbackArgs);
@@ -1064,8 +1076,9 @@ int convert_batch(sxgpu_ctx *ctx, const sxgpu_block *blocks, uint32_t nblocks, i
         }
         // Stream-ordered staging: safe against back-to-back batches on any stream.  The
         // descriptors are followed by the exclusive prefix sum of their tile counts.
-        SX_CUDA(ctx, cudaMallocAsync(&staged, size_t(nblocks) * sizeof(BlockDesc) +
-                                                  (size_t(nblocks) + 1) * sizeof(unsigned long long), st));
+        SX_CUDA(ctx, cudaMallocFromPoolAsync(&staged, size_t(nblocks) * sizeof(BlockDesc) +
+                                                          (size_t(nblocks) + 1) * sizeof(unsigned long long),
+                                             ctx->scratch_pool, st));
     } else if (max_length == 0) {
         return ctx->invalid("max_length is required for device-resident block lists");
     }
@@ -1087,9 +1100,11 @@ int convert_batch(sxgpu_ctx *ctx, const sxgpu_block *blocks, uint32_t nblocks, i
             host_tiles += (blocks[i].length + kBatchTile - 1) / kBatchTile;
         }
         tile_start[nblocks] = host_tiles;
-        // pageable source: copied before cudaMemcpyAsync returns
-        SX_CUDA(ctx, cudaMemcpyAsync(static_cast<char *>(staged) + size_t(nblocks) * sizeof(BlockDesc), tile_start.data(),
-                                     tile_start.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+        // (long lists only; short ones are summed by the kernel.)  Pageable source: copied before
+        // cudaMemcpyAsync returns.
+        if (nblocks > kBatchLocalBlocks)
+            SX_CUDA(ctx, cudaMemcpyAsync(static_cast<char *>(staged) + size_t(nblocks) * sizeof(BlockDesc), tile_start.data(),
+                                         tile_start.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
         // The caller may reuse `blocks` as soon as this call returns: when the list sits in pinned
         // memory cudaMemcpyAsync is truly asynchronous and would read it later, so the copy is
         // waited for here (a few microseconds for a list of this size; the kernels stay asynchronous).
@@ -1122,24 +1137,34 @@ int convert_batch(sxgpu_ctx *ctx, const sxgpu_block *blocks, uint32_t nblocks, i
         // Mid-size and large blocks: every block cut into tiles, all tiles of all blocks walked by
         // one persistent CTA per SM on the bulk-async schedule (bulk_batch_kernel).
         constexpr int TILE = kBatchTile;
-        unsigned long long *d_tile_start = nullptr;
-        uint64_t ntiles_hint = uint64_t(sms); // device-resident lists: the kernel reads the total itself
-        if (staged) {
-            d_tile_start = reinterpret_cast<unsigned long long *>(static_cast<char *>(staged) +
-                                                                  size_t(nblocks) * sizeof(BlockDesc));
-            ntiles_hint = host_tiles;
+        const int sm_grid_hint = sms; // the kernel finds the tile total itself; never more CTAs than SMs x occupancy
+        if (nblocks <= kBatchLocalBlocks) {
+            // Short lists: every CTA sums the tile counts itself.  One launch, no scratch.
+            BatchBulkArgs a = {d_blocks, nullptr, nblocks, int(ctx->bulk_load_policy), int(ctx->bulk_store_policy)};
+            auto k = bulk_batch_kernel<Op, TILE, kBatchStages, true>;
+            const size_t smem = batch_smem_bytes<Op>(true);
+            const uint64_t hint = staged ? std::max<uint64_t>(host_tiles, 1) : uint64_t(sm_grid_hint);
+            k<<<persistent_grid(ctx, k, 256, smem, hint), 256, smem, st>>>(a);
         } else {
-            SX_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void **>(&d_tile_start),
-                                         (size_t(nblocks) + 1) * sizeof(unsigned long long), st));
-            scan_guard.p = d_tile_start;
-            batch_tile_scan_kernel<TILE><<<1, 1024, 0, st>>>(d_blocks, nblocks, d_tile_start);
-            SX_CUDA(ctx, cudaGetLastError());
-            ctx->launches++;
+            unsigned long long *d_tile_start = nullptr;
+            uint64_t hint = uint64_t(sm_grid_hint);
+            if (staged) {
+                d_tile_start = reinterpret_cast<unsigned long long *>(static_cast<char *>(staged) +
+                                                                      size_t(nblocks) * sizeof(BlockDesc));
+                hint = std::max<uint64_t>(host_tiles, 1);
+            } else {
+                SX_CUDA(ctx, cudaMallocFromPoolAsync(reinterpret_cast<void **>(&d_tile_start),
+                                                     (size_t(nblocks) + 1) * sizeof(unsigned long long), ctx->scratch_pool, st));
+                scan_guard.p = d_tile_start;
+                batch_tile_scan_kernel<TILE><<<1, 1024, 0, st>>>(d_blocks, nblocks, d_tile_start);
+                SX_CUDA(ctx, cudaGetLastError());
+                ctx->launches++;
+            }
+            BatchBulkArgs a = {d_blocks, d_tile_start, nblocks, int(ctx->bulk_load_policy), int(ctx->bulk_store_policy)};
+            auto k = bulk_batch_kernel<Op, TILE, kBatchStages, false>;
+            const size_t smem = batch_smem_bytes<Op>(false);
+            k<<<persistent_grid(ctx, k, 256, smem, hint), 256, smem, st>>>(a);
         }
-        BatchBulkArgs a = {d_blocks, d_tile_start, nblocks, int(ctx->bulk_load_policy), int(ctx->bulk_store_policy)};
-        auto k = bulk_batch_kernel<Op, TILE, kBatchStages>;
-        int grid = persistent_grid(ctx, k, 256, batch_smem_bytes<Op>(), ntiles_hint);
-        k<<<grid, 256, batch_smem_bytes<Op>(), st>>>(a);
     }
     SX_CUDA(ctx, cudaGetLastError());
     ctx->launches++;
@@ -1248,6 +1273,7 @@ int sxgpu_init(int device, sxgpu_ctx **out)
     sxgpu_ctx *ctx = new sxgpu_ctx();
     ctx->device = device;
     auto bail = [&](int code) {
+        if (ctx->scratch_pool) cudaMemPoolDestroy(ctx->scratch_pool);
         if (ctx->d_stats) cudaFree(ctx->d_stats);
         if (ctx->h_stats) cudaFreeHost(ctx->h_stats);
         if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1275,12 +1301,30 @@ int sxgpu_init(int device, sxgpu_ctx **out)
         prepare_bulk_kernels<RxCs16>(ctx) != SXGPU_OK || prepare_bulk_kernels<TxCs16>(ctx) != SXGPU_OK ||
         prepare_bulk_kernels<RxS16Cf32>(ctx) != SXGPU_OK || prepare_bulk_kernels<TxCf32S16>(ctx) != SXGPU_OK)
         return bail(SXGPU_ERR_CUDA);
-    if (cudaFuncSetAttribute(bulk_batch_kernel<RxCf32, kBatchTile, kBatchStages>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, int(batch_smem_bytes<RxCf32>())) != cudaSuccess ||
-        cudaFuncSetAttribute(bulk_batch_kernel<TxCf32, kBatchTile, kBatchStages>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, int(batch_smem_bytes<TxCf32>())) != cudaSuccess ||
-        false)
+    if (cudaFuncSetAttribute(bulk_batch_kernel<RxCf32, kBatchTile, kBatchStages, false>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, int(batch_smem_bytes<RxCf32>(false))) != cudaSuccess ||
+        cudaFuncSetAttribute(bulk_batch_kernel<TxCf32, kBatchTile, kBatchStages, false>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, int(batch_smem_bytes<TxCf32>(false))) != cudaSuccess ||
+        cudaFuncSetAttribute(bulk_batch_kernel<RxCf32, kBatchTile, kBatchStages, true>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, int(batch_smem_bytes<RxCf32>(true))) != cudaSuccess ||
+        cudaFuncSetAttribute(bulk_batch_kernel<TxCf32, kBatchTile, kBatchStages, true>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, int(batch_smem_bytes<TxCf32>(true))) != cudaSuccess)
         return bail(SXGPU_ERR_CUDA);
+    {
+        // Stream-ordered scratch (descriptor lists staged from the host, tile counts of long lists)
+        // comes from a pool of the context's own that keeps what it is given back: the default
+        // pool returns memory to the system at every synchronisation, and the next batch then
+        // paid a fresh allocation -- several hundred microseconds, twice the conversion itself.
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        if (cudaMemPoolCreate(&ctx->scratch_pool, &props) != cudaSuccess)
+            return bail(SXGPU_ERR_CUDA);
+        uint64_t keep = UINT64_MAX;
+        cudaMemPoolSetAttribute(ctx->scratch_pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
     for (const LoopShape &shape : kLoopShapes)
         if (cudaFuncSetAttribute(shape.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  int(loop_smem_bytes(shape))) != cudaSuccess)
@@ -1324,6 +1368,7 @@ int sxgpu_destroy(sxgpu_ctx *ctx)
         if (lane.flag) cudaFreeHost(lane.flag);
         if (lane.d_arrivals) cudaFree(lane.d_arrivals);
     }
+    if (ctx->scratch_pool) cudaMemPoolDestroy(ctx->scratch_pool);
     if (ctx->d_stats) cudaFree(ctx->d_stats);
     if (ctx->h_stats) cudaFreeHost(ctx->h_stats);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
