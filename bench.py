@@ -724,6 +724,12 @@ def run_bank_arm(args, rank: int, local_rank: int, world: int):
     if args.ctas_per_sm is not None:
         ctx.set_option("ctas_per_sm", args.ctas_per_sm)
     bank = Bank(ctx, S, P, rate, 0.0, SEED + rank * S)          # this rank's streams: ids rank*S .. rank*S+S-1
+    if args.external:
+        # frames from outside: one period per stream handed in through sxgpu_bank_ingest (here once,
+        # from device memory); every iteration then converts what the capture slots hold
+        ext = torch.empty(S * P * 2, dtype=torch.int32, device="cuda")
+        ctx.synth_frames(ext.data_ptr(), 0, S * P, SEED + rank, st)
+        bank.ingest(0, S, ext.data_ptr(), st)
     cf = torch.empty(S * P * 2, dtype=torch.float32, device="cuda")
 
     def step():
@@ -782,6 +788,8 @@ def run_bank_arm(args, rank: int, local_rank: int, world: int):
                                    "writeStream(256, HAS_TIME, rx time + 768 frames) on every stream",
                        "streams_per_gpu": S, "frames_per_block": P, "sample_rate": rate,
                        "cuda_graph_replay": bool(args.graph),
+                       "capture": "frames handed in through sxgpu_bank_ingest" if args.external else
+                                  "synthetic generator inside the kernel (stand-in for the I2S DMA)",
                        "bank_repeat_variant": ctx.get_option("bank_repeat_variant") if args.fused else None,
                        "ctas_per_sm": ctx.get_option("ctas_per_sm"),
                        "calls_per_step": "sxgpu_bank_repeat (one launch)" if args.fused
@@ -1078,6 +1086,8 @@ def main():
     ap.add_argument("--graph", action="store_true", help="--workload bank: replay the step from a CUDA graph")
     ap.add_argument("--repeat-variant", type=int, default=None, help="--fused: option bank_repeat_variant")
     ap.add_argument("--ctas-per-sm", type=int, default=None, help="option ctas_per_sm (persistent grids)")
+    ap.add_argument("--external", action="store_true",
+                    help="--workload bank: capture frames come from sxgpu_bank_ingest instead of the synthetic generator")
     ap.add_argument("--fused", action="store_true",
                     help="--workload bank: the iteration as one sxgpu_bank_repeat launch instead of read + write")
     args = ap.parse_args()

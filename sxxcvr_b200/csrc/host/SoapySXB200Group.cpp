@@ -25,6 +25,10 @@ std::string arg(const SoapySDR::Kwargs &args, const char *key, const std::string
 // A member's bookkeeping is ~1 us of ALSA calls: below this many members per thread a wake-up
 // costs more than it saves.
 constexpr size_t kMembersPerThread = 32;
+// Up to this many frames in all members' blocks together the fused kernel works straight on the
+// pinned staging buffers; above, the copy engines carry the blocks to device memory and back
+// (crossover of the *_host entry points, profiles/r01_sweep_host_path.json).
+constexpr size_t kZeroCopyFrames = size_t(1) << 17;
 } // namespace
 
 SoapySXB200Group::SoapySXB200Group(size_t members, const SoapySDR::Kwargs &args)
@@ -78,6 +82,9 @@ SoapySXB200Group::~SoapySXB200Group()
     for (void *p : {stage_rx_, stage_tx_, stage_cf_})
         if (p)
             sxgpu_free_host(gpu_, p);
+    for (void *p : {dev_in_, dev_cf_, dev_out_})
+        if (p)
+            sxgpu_free(gpu_, p);
     sxgpu_destroy(gpu_);
 }
 
@@ -141,11 +148,20 @@ void SoapySXB200Group::reserve(size_t numElems)
             sxgpu_free_host(gpu_, *p);
         *p = nullptr;
     }
+    for (void **p : {&dev_in_, &dev_cf_, &dev_out_}) {
+        if (*p)
+            sxgpu_free(gpu_, *p);
+        *p = nullptr;
+    }
     capacity_ = 0;
     const size_t bytes = members_.size() * numElems * 8;
     if (sxgpu_malloc_host(gpu_, &stage_rx_, bytes) != SXGPU_OK || sxgpu_malloc_host(gpu_, &stage_tx_, bytes) != SXGPU_OK ||
         sxgpu_malloc_host(gpu_, &stage_cf_, bytes) != SXGPU_OK)
         throw std::runtime_error(std::string("pinned staging allocation failed: ") + sxgpu_last_error(gpu_));
+    if (members_.size() * numElems > kZeroCopyFrames &&
+        (sxgpu_malloc(gpu_, &dev_in_, bytes) != SXGPU_OK || sxgpu_malloc(gpu_, &dev_cf_, bytes) != SXGPU_OK ||
+         sxgpu_malloc(gpu_, &dev_out_, bytes) != SXGPU_OK))
+        throw std::runtime_error(std::string("device staging allocation failed: ") + sxgpu_last_error(gpu_));
     capacity_ = numElems;
 }
 
@@ -206,39 +222,64 @@ int SoapySXB200Group::repeatAll(void *cf32, size_t numElems, long long offset_ns
 {
     reserve(numElems);
     char *in = static_cast<char *>(stage_rx_);
-    // Both halves of the bookkeeping before the one launch: the read, then the placement of the
-    // timed write at this read's timestamp + offset.  A member whose read did not deliver a whole
-    // block writes nothing (the application would skip its write, linear_repeater.py:59-61).
+    const size_t total = members_.size() * numElems;
+    std::vector<long long> &t_rx = rx_time_scratch_;
+    t_rx.assign(members_.size(), 0);
+
+    // 1. The read half of the bookkeeping: every member's frames land side by side in pinned staging.
     pool_->run(members_.size(), kMembersPerThread, [&](size_t lo, size_t hi) {
         for (size_t i = lo; i < hi; i++) {
-            Member &m = *members_[i];
-            long long t = 0;
-            {
-                std::scoped_lock lock(m.rx.mutex);
-                const RxOutcome rx = rx_before_convert(m.rx, sample_rate_, numElems, timeoutUs,
-                                                       [&](size_t) { return in + i * numElems * 8; });
-                rx_rets[i] = rx.ret;
-                t = rx.time_ns;
-                if (rx_timeNs && rx.time_valid)
-                    rx_timeNs[i] = rx.time_ns;
-            }
-            tx_plan_[i] = TxOutcome();
-            if (rx_rets[i] == int(numElems)) {
-                std::scoped_lock lock(m.tx.mutex);
-                tx_plan_[i] = tx_before_convert(m.tx, sample_rate_, numElems, SOAPY_SDR_HAS_TIME, t + offset_ns, timeoutUs);
-            }
+            Endpoint &ep = members_[i]->rx;
+            std::scoped_lock lock(ep.mutex);
+            const RxOutcome rx = rx_before_convert(ep, sample_rate_, numElems, timeoutUs,
+                                                   [&](size_t) { return in + i * numElems * 8; });
+            rx_rets[i] = rx.ret;
+            t_rx[i] = rx.time_ns;
+            if (rx_timeNs && rx.time_valid)
+                rx_timeNs[i] = rx.time_ns;
         }
     });
-    // RX and TX conversions of every member in one launch, straight between the pinned staging
-    // buffers (device-addressable); the CF32 blocks land in pinned memory too.
-    const size_t total = members_.size() * numElems;
-    if (sxgpu_convert_loopback(gpu_, stage_rx_, stage_cf_, stage_tx_, total, tx_threshold2_, nullptr) != SXGPU_OK ||
-        sxgpu_stream_sync(gpu_, nullptr) != SXGPU_OK) {
+
+    // 2. RX and TX conversions of every member in ONE launch, queued without waiting.  Small groups:
+    // the kernel reads and writes the pinned staging buffers across PCIe itself.  Large groups:
+    // one copy in, the fused kernel on device buffers, one copy out (the copy engines move 8 MiB in
+    // a fifth of the time the SMs need to fetch it across the link).
+    int rc;
+    if (total <= kZeroCopyFrames) {
+        rc = sxgpu_convert_loopback(gpu_, stage_rx_, stage_cf_, stage_tx_, total, tx_threshold2_, nullptr);
+    } else {
+        rc = sxgpu_memcpy_h2d(gpu_, dev_in_, stage_rx_, total * 8, nullptr);
+        if (rc == SXGPU_OK)
+            rc = sxgpu_convert_loopback(gpu_, dev_in_, cf32 ? dev_cf_ : nullptr, dev_out_, total, tx_threshold2_, nullptr);
+        if (rc == SXGPU_OK)
+            rc = sxgpu_memcpy_d2h(gpu_, stage_tx_, dev_out_, total * 8, nullptr);
+        if (rc == SXGPU_OK && cf32)
+            rc = sxgpu_memcpy_d2h(gpu_, stage_cf_, dev_cf_, total * 8, nullptr);
+    }
+
+    // 3. While the GPU works: where each member's timed write lands (this read's timestamp +
+    // offset), the forward over the gap, the trim -- none of which needs the samples.  A member
+    // whose read did not deliver a whole block writes nothing (the application would skip its
+    // write, linear_repeater.py:59-61).
+    pool_->run(members_.size(), kMembersPerThread, [&](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; i++) {
+            tx_plan_[i] = TxOutcome();
+            if (rx_rets[i] != int(numElems))
+                continue;
+            Endpoint &ep = members_[i]->tx;
+            std::scoped_lock lock(ep.mutex);
+            tx_plan_[i] = tx_before_convert(ep, sample_rate_, numElems, SOAPY_SDR_HAS_TIME, t_rx[i] + offset_ns, timeoutUs);
+        }
+    });
+
+    if (rc != SXGPU_OK || sxgpu_stream_sync(gpu_, nullptr) != SXGPU_OK) {
         SoapySDR_logf(SOAPY_SDR_ERROR, "group repeat GPU conversion failed: %s", sxgpu_last_error(gpu_));
         return SOAPY_SDR_STREAM_ERROR;
     }
     if (cf32)
         std::memcpy(cf32, stage_cf_, total * 8);
+
+    // 4. Hand every member's I2S frames to its PCM.
     const char *out = static_cast<const char *>(stage_tx_);
     pool_->run(members_.size(), kMembersPerThread, [&](size_t lo, size_t hi) {
         for (size_t i = lo; i < hi; i++) {

@@ -77,7 +77,9 @@ private:
     std::vector<std::unique_ptr<Member>> members_;
     std::unique_ptr<WorkerPool> pool_;
     void *stage_rx_ = nullptr, *stage_tx_ = nullptr, *stage_cf_ = nullptr; // pinned, [members][capacity_]
+    void *dev_in_ = nullptr, *dev_cf_ = nullptr, *dev_out_ = nullptr;       // device, large groups only
     size_t capacity_ = 0;
+    std::vector<long long> rx_time_scratch_;
     std::vector<TxOutcome> tx_plan_; // per member, between the two halves of a write
 };
 

@@ -7,6 +7,7 @@
 #include "../sx_synth.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cerrno>
 #include <climits>
 #include <cstring>
@@ -62,7 +63,8 @@ struct _snd_pcm {
     snd_pcm_state_t state = SND_PCM_STATE_OPEN;
     _snd_pcm_hw_params hw;
     _snd_pcm_sw_params sw;
-    std::shared_ptr<ClockGroup> group;
+    std::shared_ptr<ClockGroup> group;           // ownership
+    std::atomic<ClockGroup *> group_now{nullptr}; // what Guard reads: the same object, without a lock
 
     int64_t appl_ptr = 0; // frames the application has consumed / produced / forwarded
     int64_t hw_ptr = 0;   // frames the "hardware" has captured / played
@@ -96,28 +98,27 @@ struct _snd_pcm {
 
 namespace {
 
-std::mutex g_registry;   // guards g_open and every PCM's `group` pointer
+std::mutex g_registry;   // guards g_open
 std::mutex g_link_mutex; // one snd_pcm_link at a time (it needs two groups)
 std::vector<snd_pcm_t *> g_open;
+// Groups emptied by snd_pcm_link are parked here instead of being freed, so that a thread which
+// read a PCM's old group pointer just before the link can still lock it, notice, and retry.
+std::vector<std::shared_ptr<ClockGroup>> g_retired_groups; // guarded by g_link_mutex
 
-// Holds the lock of the clock group `pcm` belongs to.  The group pointer only changes inside
-// snd_pcm_link, which holds both groups' locks while it re-points the members; so a group that
-// is still the PCM's group after its lock was taken stays so until the lock is released.
+// Holds the lock of the clock group `pcm` belongs to.  No process-wide lock is touched on this
+// path (thousands of PCMs on a handful of threads would all meet there): the PCM's group is read
+// from an atomic pointer, locked, and checked again -- the pointer only changes inside
+// snd_pcm_link, which holds both groups' locks while it re-points the members, so a group that is
+// still the PCM's group after its lock was taken stays so until the lock is released.
 class Guard {
 public:
     explicit Guard(snd_pcm_t *pcm)
     {
         for (;;) {
-            {
-                std::lock_guard<std::mutex> r(g_registry);
-                group_ = pcm->group;
-            }
+            group_ = pcm->group_now.load(std::memory_order_acquire);
             group_->mutex.lock();
-            {
-                std::lock_guard<std::mutex> r(g_registry);
-                if (pcm->group == group_)
-                    return;
-            }
+            if (pcm->group_now.load(std::memory_order_acquire) == group_)
+                return;
             group_->mutex.unlock();
         }
     }
@@ -126,7 +127,7 @@ public:
     Guard &operator=(const Guard &) = delete;
 
 private:
-    std::shared_ptr<ClockGroup> group_;
+    ClockGroup *group_;
 };
 
 bool takeFault(snd_pcm_t *pcm, sx_alsa_op op, int *err)
@@ -236,6 +237,7 @@ int snd_pcm_open(snd_pcm_t **out, const char *name, snd_pcm_stream_t stream, int
     pcm->dir = stream;
     pcm->group = std::make_shared<ClockGroup>();
     pcm->group->members.push_back(pcm);
+    pcm->group_now.store(pcm->group.get(), std::memory_order_release);
     std::lock_guard<std::mutex> r(g_registry);
     g_open.push_back(pcm);
     *out = pcm;
@@ -244,8 +246,10 @@ int snd_pcm_open(snd_pcm_t **out, const char *name, snd_pcm_stream_t stream, int
 
 int snd_pcm_close(snd_pcm_t *pcm)
 {
+    std::shared_ptr<ClockGroup> keep; // the group may lose its last owner here: not while it is locked
     {
         Guard lock(pcm);
+        keep = pcm->group;
         std::lock_guard<std::mutex> r(g_registry);
         auto &members = pcm->group->members;
         members.erase(std::remove(members.begin(), members.end(), pcm), members.end());
@@ -323,13 +327,14 @@ int snd_pcm_link(snd_pcm_t *a, snd_pcm_t *b)
     if (a->group == b->group)
         return -EALREADY;
     Guard lock_b(b);
-    std::lock_guard<std::mutex> r(g_registry);
     std::shared_ptr<ClockGroup> old = b->group;
     for (snd_pcm_t *m : old->members) {
         m->group = a->group;
+        m->group_now.store(a->group.get(), std::memory_order_release);
         a->group->members.push_back(m);
     }
     old->members.clear();
+    g_retired_groups.push_back(old); // lock_b still holds its mutex: it must outlive this call
     return 0;
 }
 

@@ -108,6 +108,8 @@ r = d.getGainRange(SoapySDR.SOAPY_SDR_RX, 0, "LNA")
 out["lna_range"] = [r.minimum(), r.maximum(), r.step()]
 r = d.getGainRange(SoapySDR.SOAPY_SDR_RX, 0)
 out["rx_range"] = [r.minimum(), r.maximum()]
+out["gain_at_open"] = [d.getGain(SoapySDR.SOAPY_SDR_RX, 0, "LNA"), d.getGain(SoapySDR.SOAPY_SDR_RX, 0, "PGA"),
+                       d.getGain(SoapySDR.SOAPY_SDR_TX, 0, "DAC"), d.getGain(SoapySDR.SOAPY_SDR_TX, 0, "MIXER")]
 d.setGain(SoapySDR.SOAPY_SDR_RX, 0, "LNA", 36)
 d.setGain(SoapySDR.SOAPY_SDR_RX, 0, "PGA", 10)
 out["rx_gain"] = [d.getGain(SoapySDR.SOAPY_SDR_RX, 0, "LNA"), d.getGain(SoapySDR.SOAPY_SDR_RX, 0, "PGA"),
@@ -148,6 +150,9 @@ print(json.dumps(out))
     assert res["formats"] == ["CF32"]
     assert res["native"][0] == "CF32"
     assert res["gains_rx"] == ["LNA", "PGA"] and res["gains_tx"] == ["DAC", "MIXER"]
+    # the reference's register defaults as getGain reads them back before any setGain; the GPU
+    # driver starts from the same values (tests/test_gpu_compat.py)
+    assert res["gain_at_open"] == [48.0, 30.0, 6.0, 28.0]
     assert res["lna_range"][:2] == [0.0, 48.0]
     assert res["rx_gain"][2] == res["rx_gain"][0] + res["rx_gain"][1]
     assert res["rate"] == 300000.0 and res["rates"] == 6   # the rates of the detected crystal (SoapySX.cpp:193-220)

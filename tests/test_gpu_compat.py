@@ -45,6 +45,8 @@ from SoapySDR import *
 out = {}
 d = SoapySDR.Device({"driver": "sx"})
 out["info"] = d.getHardwareInfo()
+out["gain_at_open"] = [d.getGain(SOAPY_SDR_RX, 0, "LNA"), d.getGain(SOAPY_SDR_RX, 0, "PGA"),
+                       d.getGain(SOAPY_SDR_TX, 0, "DAC"), d.getGain(SOAPY_SDR_TX, 0, "MIXER")]
 out["formats"] = list(d.getStreamFormats(SOAPY_SDR_RX, 0))
 d.setSampleRate(SOAPY_SDR_RX, 0, 75000.0); d.setSampleRate(SOAPY_SDR_TX, 0, 75000.0)
 rx = d.setupStream(SOAPY_SDR_RX, SOAPY_SDR_CF32, [0], {"link": "1"})
@@ -71,6 +73,9 @@ print(json.dumps(out))
     res = json.loads(out.strip().splitlines()[-1])
     assert "gpu" in res["info"] and int(res["info"]["gpu_sm_count"]) > 0
     assert res["formats"] == ["CF32"] and res["formats_cs16"] == ["CF32", "CS16"]
+    # what the reference's register defaults read back before any setGain (init_registers,
+    # SoapySX.cpp:146-176: 0x0C = 0x3F -> LNA 48, PGA 30; 0x08 = 0x2E -> DAC 6, MIXER 28)
+    assert res["gain_at_open"] == [48.0, 30.0, 6.0, 28.0]
     rows = res["rows"]
     assert all(r[0] == 256 and r[1] & 4 and r[3] == 256 for r in rows)
     assert rows[0][2] == 0

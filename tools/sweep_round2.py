@@ -144,7 +144,17 @@ def sweep_bank(ctx, side, out):
                 assert ((txp - rxp) == 768).all()
             row[f"v{variant}_us"] = round(sec * 1e6, 2)
             row[f"v{variant}_graph_us"] = round(gsec * 1e6, 2)
+        # frames from outside (sxgpu_bank_ingest): the capture slots are read, not synthesised
+        for variant in (2, 4, 100, 202, 204, 300):
+            ctx.set_option("bank_repeat_variant", variant)
+            with Bank(ctx, S, P, rate, 0.0, 7) as bank:
+                bank.ingest(0, 0, None, st)
+                sec = timed(lambda: bank.repeat(cf.data_ptr(), lat, st), side, 200, warm=5)
+            row[f"external_v{variant}_us"] = round(sec * 1e6, 2)
         ctx.set_option("bank_repeat_variant", 0)
+        ext = min((row[k], k) for k in row if k.startswith("external_"))
+        row["external_best"] = ext[1]
+        row["external_best_hbm_gbs"] = 24 * S * P / (ext[0] * 1e-6) / 1e9
         best = min((row[k], k) for k in row if k.endswith("_graph_us"))
         row["best"] = best[1]
         row["best_write_gbs"] = 24 * S * P / (best[0] * 1e-6) / 1e9
