@@ -608,6 +608,187 @@ __global__ void bank_gather_kernel(BankState b, uint32_t stream, long long posit
         st_stream<8>(dst + i * 8, ld_stream<8>(ring_frame(b, stream, uint64_t(position) + i)));
 }
 
+// ---------------------------------------------------------------------------------------
+// The repeater iteration on the bulk-async schedule (two launches: decisions, then data).
+//
+// bank_plan_repeat_kernel: one thread per stream takes readStream's and the timed
+// writeStream's decisions (bank_plan_repeat: same stores, same order as every other schedule)
+// and writes the silence of a forwarded-over gap itself -- rare, and off the data kernel's path.
+//
+// bank_repeat_bulk_kernel: the samples.  The streams' periods lie side by side in the capture
+// slots and in the caller's CF32 buffer, so the bank is one flat array of nstreams x period
+// frames and the iteration is the fused loopback over it: persistent CTAs, tiles of whole
+// streams (2048 frames: 8 streams of 256), three shared-memory buffers per stage.  The capture
+// tile is either produced in shared memory by all threads (synthetic stand-in for the I2S DMA)
+// and bulk-stored to the capture slots, or bulk-loaded from them (frames from outside,
+// sxgpu_bank_ingest); RX and TX conversions run shared -> shared; the CF32 tile leaves as one
+// bulk store, and the I2S tile as one bulk store per stream, to wherever that stream's write
+// position puts it in the time-major ring (two when the block straddles a period boundary; by
+// frame-wide thread stores when it starts on an odd frame).  No stage reads back what another
+// wrote, no warp waits on a dependent round trip: what is left is the 24 B/frame of HBM traffic.
+// Needs: period even, 2048 % period == 0, 16-byte aligned CF32 buffer.
+// ---------------------------------------------------------------------------------------
+__global__ void bank_plan_repeat_kernel(BankState b, char *cf32, long long rx_time_offset_ns)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= b.nstreams)
+        return;
+    long long first;
+    BankWritePlan w;
+    bank_plan_repeat(b, s, cf32, rx_time_offset_ns, first, w);
+    if (w.at >= 0 && w.gap > 0) { // ALSA plays zeros for what the application skipped (:493-496)
+        long long gap = w.gap, start = w.start;
+        if (gap > (long long)b.ring) {
+            start += gap - (long long)b.ring;
+            gap = (long long)b.ring;
+        }
+        Pack<2> zero;
+        zero.w[0] = zero.w[1] = 0;
+        for (long long i = 0; i < gap; i++)
+            st_stream<8>(ring_frame(b, s, uint64_t(start + i)), zero);
+    }
+}
+
+constexpr int kBankTile = 2048; // frames per tile of the bulk schedule
+
+struct BankTileMeta {
+    long long first[32]; // counter value of each stream's first captured frame (synthetic capture)
+    long long at[32];    // counter value its block is written at; -1: discarded as late
+};
+
+template <int STAGES, class Hook>
+__global__ void __launch_bounds__(256) bank_repeat_bulk_kernel(BankState b, char *cf32, bool capture_in_slot, Hook hook,
+                                                              int load_policy, int store_policy)
+{
+    constexpr size_t STAGE = size_t(kBankTile) * 8;
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char *in_buf = smem;
+    unsigned char *mid_buf = smem + size_t(STAGES) * STAGE;
+    unsigned char *out_buf = smem + 2 * size_t(STAGES) * STAGE;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + 3 * size_t(STAGES) * STAGE);
+    BankTileMeta *meta = reinterpret_cast<BankTileMeta *>(full + STAGES); // [2], alternating by tile
+
+    const uint32_t P = b.period;
+    const uint32_t spt = kBankTile / P; // streams per tile (host guarantees P divides the tile, spt <= 32 for P >= 64)
+    const uint64_t ntiles = (uint64_t(b.nstreams) + spt - 1) / spt;
+    const uint64_t first_tile = blockIdx.x, stride = gridDim.x;
+    if (first_tile >= ntiles)
+        return;
+    const uint64_t mine = (ntiles - first_tile + stride - 1) / stride;
+    const uint64_t pol = bulk::make_policy(load_policy), pol_store = bulk::make_policy(store_policy);
+    auto tile_streams = [&](uint64_t i) -> uint32_t {
+        const uint64_t s0 = (first_tile + i * stride) * spt;
+        return uint32_t(b.nstreams - s0 < spt ? b.nstreams - s0 : spt);
+    };
+    auto load_meta = [&](uint64_t i) { // threads 0..spt-1: the decisions of tile i's streams
+        if (threadIdx.x < tile_streams(i)) {
+            const uint64_t s = (first_tile + i * stride) * spt + threadIdx.x;
+            meta[i & 1].first[threadIdx.x] = b.rx_first_frame[s];
+            meta[i & 1].at[threadIdx.x] = b.tx_write_position[s];
+        }
+    };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; s++)
+            bulk::mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    load_meta(0);
+    __syncthreads();
+    if (capture_in_slot && threadIdx.x == 0) {
+        for (uint64_t i = 0; i < uint64_t(STAGES) && i < mine; i++) {
+            const uint32_t bytes = tile_streams(i) * P * 8;
+            bulk::mbar_expect_tx(&full[i], bytes);
+            bulk::load_g2s(in_buf + i * STAGE, b.capture_stage + (first_tile + i * stride) * spt * P * 8, bytes, &full[i], pol);
+        }
+    }
+
+    for (uint64_t i = 0; i < mine; i++) {
+        const int s = int(i % STAGES);
+        const uint32_t ns = tile_streams(i), nf = ns * P;
+        const uint64_t s0 = (first_tile + i * stride) * spt;
+        // the three buffers of stage s were last read by the stores of tile i - STAGES (one group per tile)
+        if (threadIdx.x == 0)
+            bulk::wait_group_read<STAGES - 1>();
+        __syncthreads();
+        // The next tile's decisions go into the other half of `meta`: its last readers (tile i - 1,
+        // up to thread 0's store issue) are all behind the barrier above, its next readers two
+        // barriers ahead.
+        if (i + 1 < mine)
+            load_meta(i + 1);
+        const BankTileMeta &m = meta[i & 1];
+
+        uint4 *ip = reinterpret_cast<uint4 *>(in_buf + size_t(s) * STAGE);
+        uint4 *mp = reinterpret_cast<uint4 *>(mid_buf + size_t(s) * STAGE);
+        uint4 *op = reinterpret_cast<uint4 *>(out_buf + size_t(s) * STAGE);
+        if (capture_in_slot)
+            bulk::mbar_wait(&full[s], uint32_t(i / STAGES) & 1u);
+        for (uint32_t v = threadIdx.x; v * 2 < nf; v += blockDim.x) {
+            const uint32_t j = (2 * v) / P, k = (2 * v) % P; // stream within the tile, frame within its block
+            Pack<4> in, mid, out;
+            if (capture_in_slot) {
+                const uint4 t = ip[v];
+                in.w[0] = t.x, in.w[1] = t.y, in.w[2] = t.z, in.w[3] = t.w;
+            } else {
+                const uint64_t z0 = sx_synth_frame(b.seed + s0 + j, uint64_t(m.first[j]) + k);
+                const uint64_t z1 = sx_synth_frame(b.seed + s0 + j, uint64_t(m.first[j]) + k + 1);
+                in.w[0] = uint32_t(z0), in.w[1] = uint32_t(z0 >> 32), in.w[2] = uint32_t(z1), in.w[3] = uint32_t(z1 >> 32);
+                ip[v] = make_uint4(in.w[0], in.w[1], in.w[2], in.w[3]);
+            }
+            RxCf32::apply<2>(in, mid, 0.0f);
+            hook(mid, s0 + j, k);
+            TxCf32::apply<2>(mid, out, b.thr2);
+            mp[v] = make_uint4(mid.w[0], mid.w[1], mid.w[2], mid.w[3]);
+            op[v] = make_uint4(out.w[0], out.w[1], out.w[2], out.w[3]);
+        }
+        bulk::fence_async_smem();
+        __syncthreads();
+
+        // A block that starts on an odd frame of the ring cannot be moved by 16-byte bulk copies:
+        // its frames go out one by one (all threads), straight from the output buffer.
+        for (uint32_t j = 0; j < ns; j++) {
+            const long long at = m.at[j];
+            if (at >= 0 && (at & 1)) {
+                const unsigned char *src = out_buf + size_t(s) * STAGE + size_t(j) * P * 8;
+                for (uint32_t f = threadIdx.x; f < P; f += blockDim.x) {
+                    Pack<2> w;
+                    const uint2 t = *reinterpret_cast<const uint2 *>(src + size_t(f) * 8);
+                    w.w[0] = t.x, w.w[1] = t.y;
+                    st_stream<8>(ring_frame(b, s0 + j, uint64_t(at) + f), w);
+                }
+            }
+        }
+
+        if (threadIdx.x == 0) {
+            const size_t flat = s0 * P * 8;
+            if (!capture_in_slot)
+                bulk::store_s2g(b.capture_stage + flat, in_buf + size_t(s) * STAGE, nf * 8, pol_store);
+            bulk::store_s2g(cf32 + flat, mid_buf + size_t(s) * STAGE, nf * 8, pol_store);
+            for (uint32_t j = 0; j < ns; j++) {
+                const long long at = m.at[j];
+                if (at < 0 || (at & 1))
+                    continue;
+                const unsigned char *src = out_buf + size_t(s) * STAGE + size_t(j) * P * 8;
+                const uint32_t into = uint32_t(uint64_t(at) % P);
+                const uint32_t span = into ? P - into : P;
+                bulk::store_s2g(ring_frame(b, s0 + j, uint64_t(at)), src, span * 8, pol_store);
+                if (span < P)
+                    bulk::store_s2g(ring_frame(b, s0 + j, uint64_t(at) + span), src + size_t(span) * 8, (P - span) * 8, pol_store);
+            }
+            bulk::commit_group();
+            const uint64_t nxt = i + STAGES;
+            if (capture_in_slot && nxt < mine) {
+                const uint32_t bytes = tile_streams(nxt) * P * 8;
+                bulk::mbar_expect_tx(&full[s], bytes);
+                bulk::load_g2s(in_buf + size_t(s) * STAGE, b.capture_stage + (first_tile + nxt * stride) * spt * P * 8, bytes,
+                               &full[s], pol);
+            }
+        }
+    }
+    if (threadIdx.x == 0)
+        bulk::wait_group_all();
+}
+
 __global__ void bank_advance_kernel(BankState b, long long frames)
 {
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
