@@ -670,6 +670,13 @@ __global__ void __launch_bounds__(256) bank_repeat_bulk_kernel(BankState b, char
 
     const uint32_t P = b.period;
     const uint32_t spt = kBankTile / P; // streams per tile (host guarantees P divides the tile, spt <= 32 for P >= 64)
+    // P divides 2048, so it is a power of two, and so is the number of period slices in the ring
+    // (65536 / P): every division on this path is a shift or a mask.
+    const uint32_t log2p = 31 - __clz(P);
+    const uint64_t slice_mask = b.ring / P - 1;
+    auto ring_at = [&](uint64_t stream, uint64_t pos) -> char * {
+        return b.playback_ring + ((((pos >> log2p) & slice_mask) * b.nstreams + stream) * P + (pos & (P - 1))) * 8;
+    };
     const uint64_t ntiles = (uint64_t(b.nstreams) + spt - 1) / spt;
     const uint64_t first_tile = blockIdx.x, stride = gridDim.x;
     if (first_tile >= ntiles)
@@ -707,8 +714,9 @@ __global__ void __launch_bounds__(256) bank_repeat_bulk_kernel(BankState b, char
         const int s = int(i % STAGES);
         const uint32_t ns = tile_streams(i), nf = ns * P;
         const uint64_t s0 = (first_tile + i * stride) * spt;
-        // the three buffers of stage s were last read by the stores of tile i - STAGES (one group per tile)
-        if (threadIdx.x == 0)
+        // the three buffers of stage s were last read by the stores of tile i - STAGES (every lane
+        // of the first warp issues stores and commits one group per tile, see below)
+        if (threadIdx.x < 32)
             bulk::wait_group_read<STAGES - 1>();
         __syncthreads();
         // The next tile's decisions go into the other half of `meta`: its last readers (tile i - 1,
@@ -724,7 +732,7 @@ __global__ void __launch_bounds__(256) bank_repeat_bulk_kernel(BankState b, char
         if (capture_in_slot)
             bulk::mbar_wait(&full[s], uint32_t(i / STAGES) & 1u);
         for (uint32_t v = threadIdx.x; v * 2 < nf; v += blockDim.x) {
-            const uint32_t j = (2 * v) / P, k = (2 * v) % P; // stream within the tile, frame within its block
+            const uint32_t j = (2 * v) >> log2p, k = (2 * v) & (P - 1); // stream within the tile, frame within its block
             Pack<4> in, mid, out;
             if (capture_in_slot) {
                 const uint4 t = ip[v];
@@ -754,30 +762,37 @@ __global__ void __launch_bounds__(256) bank_repeat_bulk_kernel(BankState b, char
                     Pack<2> w;
                     const uint2 t = *reinterpret_cast<const uint2 *>(src + size_t(f) * 8);
                     w.w[0] = t.x, w.w[1] = t.y;
-                    st_stream<8>(ring_frame(b, s0 + j, uint64_t(at) + f), w);
+                    st_stream<8>(ring_at(s0 + j, uint64_t(at) + f), w);
                 }
             }
         }
 
-        if (threadIdx.x == 0) {
-            const size_t flat = s0 * P * 8;
-            if (!capture_in_slot)
-                bulk::store_s2g(b.capture_stage + flat, in_buf + size_t(s) * STAGE, nf * 8, pol_store);
-            bulk::store_s2g(cf32 + flat, mid_buf + size_t(s) * STAGE, nf * 8, pol_store);
-            for (uint32_t j = 0; j < ns; j++) {
+        // Stores: the first warp, one stream per lane for the ring (where a block lands takes a
+        // couple of 64-bit divisions per stream: side by side on the lanes they cost what one
+        // does; on one thread they were six times the tile's transfer time), lane 0 for the two
+        // flat tiles and the next load.  Bulk groups are per thread: every lane commits one.
+        if (threadIdx.x < 32) {
+            if (threadIdx.x == 0) {
+                const size_t flat = s0 * P * 8;
+                if (!capture_in_slot)
+                    bulk::store_s2g(b.capture_stage + flat, in_buf + size_t(s) * STAGE, nf * 8, pol_store);
+                bulk::store_s2g(cf32 + flat, mid_buf + size_t(s) * STAGE, nf * 8, pol_store);
+            }
+            const uint32_t j = threadIdx.x;
+            if (j < ns) {
                 const long long at = m.at[j];
-                if (at < 0 || (at & 1))
-                    continue;
-                const unsigned char *src = out_buf + size_t(s) * STAGE + size_t(j) * P * 8;
-                const uint32_t into = uint32_t(uint64_t(at) % P);
-                const uint32_t span = into ? P - into : P;
-                bulk::store_s2g(ring_frame(b, s0 + j, uint64_t(at)), src, span * 8, pol_store);
-                if (span < P)
-                    bulk::store_s2g(ring_frame(b, s0 + j, uint64_t(at) + span), src + size_t(span) * 8, (P - span) * 8, pol_store);
+                if (at >= 0 && !(at & 1)) {
+                    const unsigned char *src = out_buf + size_t(s) * STAGE + size_t(j) * P * 8;
+                    const uint32_t into = uint32_t(uint64_t(at) & (P - 1));
+                    const uint32_t span = into ? P - into : P;
+                    bulk::store_s2g(ring_at(s0 + j, uint64_t(at)), src, span * 8, pol_store);
+                    if (span < P)
+                        bulk::store_s2g(ring_at(s0 + j, uint64_t(at) + span), src + size_t(span) * 8, (P - span) * 8, pol_store);
+                }
             }
             bulk::commit_group();
             const uint64_t nxt = i + STAGES;
-            if (capture_in_slot && nxt < mine) {
+            if (threadIdx.x == 0 && capture_in_slot && nxt < mine) {
                 const uint32_t bytes = tile_streams(nxt) * P * 8;
                 bulk::mbar_expect_tx(&full[s], bytes);
                 bulk::load_g2s(in_buf + size_t(s) * STAGE, b.capture_stage + (first_tile + nxt * stride) * spt * P * 8, bytes,
@@ -785,7 +800,7 @@ __global__ void __launch_bounds__(256) bank_repeat_bulk_kernel(BankState b, char
             }
         }
     }
-    if (threadIdx.x == 0)
+    if (threadIdx.x < 32)
         bulk::wait_group_all();
 }
 

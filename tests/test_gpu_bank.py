@@ -376,5 +376,8 @@ def test_repeat_with_blocks_that_straddle_ring_slices(ctx, variant, latency_fram
             if i in (0, 1, 5, 255, 256, 257, 299):
                 assert_same(snapshot(two_calls, cf_a, S), snapshot(fused, cf_b, S), i)
         _, rxp, txp = fused.positions()
-        assert (txp - rxp == latency_frames).all()
+        if latency_frames >= P:
+            assert (txp - rxp == latency_frames).all()
+        else:                       # a block timed before the end of its own read is late: dropped whole, every time
+            assert (txp == 0).all() and (rxp == 300 * P).all()
     ctx.set_option("bank_repeat_variant", 0)
