@@ -656,9 +656,9 @@ struct BankTileMeta {
     long long at[32];    // counter value its block is written at; -1: discarded as late
 };
 
-template <int STAGES, class Hook>
-__global__ void __launch_bounds__(256) bank_repeat_bulk_kernel(BankState b, char *cf32, bool capture_in_slot, Hook hook,
-                                                              int load_policy, int store_policy)
+template <int STAGES, int BLOCK, class Hook>
+__global__ void __launch_bounds__(BLOCK) bank_repeat_bulk_kernel(BankState b, char *cf32, bool capture_in_slot, Hook hook,
+                                                                int load_policy, int store_policy)
 {
     constexpr size_t STAGE = size_t(kBankTile) * 8;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -778,9 +778,16 @@ __global__ void __launch_bounds__(256) bank_repeat_bulk_kernel(BankState b, char
                     bulk::store_s2g(b.capture_stage + flat, in_buf + size_t(s) * STAGE, nf * 8, pol_store);
                 bulk::store_s2g(cf32 + flat, mid_buf + size_t(s) * STAGE, nf * 8, pol_store);
             }
+            // Streams in lock-step (the normal case: one sample clock, period-aligned writes) land side
+            // by side in one slice of the time-major ring: one store for the whole tile.
             const uint32_t j = threadIdx.x;
-            if (j < ns) {
-                const long long at = m.at[j];
+            const long long my_at = j < ns ? m.at[j] : m.at[0];
+            const bool lockstep = __all_sync(0xffffffffu, my_at == m.at[0]) && m.at[0] >= 0 && (uint64_t(m.at[0]) & (P - 1)) == 0;
+            if (lockstep) {
+                if (threadIdx.x == 0)
+                    bulk::store_s2g(ring_at(s0, uint64_t(m.at[0])), out_buf + size_t(s) * STAGE, nf * 8, pol_store);
+            } else if (j < ns) {
+                const long long at = my_at;
                 if (at >= 0 && !(at & 1)) {
                     const unsigned char *src = out_buf + size_t(s) * STAGE + size_t(j) * P * 8;
                     const uint32_t into = uint32_t(uint64_t(at) & (P - 1));

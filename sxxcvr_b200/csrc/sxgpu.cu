@@ -1325,7 +1325,9 @@ int sxgpu_init(int device, sxgpu_ctx **out)
         uint64_t keep = UINT64_MAX;
         cudaMemPoolSetAttribute(ctx->scratch_pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
-    if (cudaFuncSetAttribute(bank_repeat_bulk_kernel<3, IdentityHook>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(bank_repeat_bulk_kernel<3, 256, IdentityHook>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             int(3 * size_t(3) * kBankTile * 8 + 3 * 8 + 2 * sizeof(BankTileMeta))) != cudaSuccess ||
+        cudaFuncSetAttribute(bank_repeat_bulk_kernel<3, 1024, IdentityHook>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              int(3 * size_t(3) * kBankTile * 8 + 3 * 8 + 2 * sizeof(BankTileMeta))) != cudaSuccess)
         return bail(SXGPU_ERR_CUDA);
     for (const LoopShape &shape : kLoopShapes)
@@ -1795,10 +1797,18 @@ int sxgpu_bank_repeat(sxgpu_bank *bank, void *d_cf32, long long rx_time_offset_n
         bank_plan_repeat_kernel<<<per_stream_grid(b.nstreams, 128), 128, 0, st>>>(b, cf, rx_time_offset_ns);
         SX_CUDA(ctx, cudaGetLastError());
         ctx->launches++;
-        auto kernel = bank_repeat_bulk_kernel<kBankStages, IdentityHook>;
         const uint64_t tiles = (uint64_t(b.nstreams) + kBankTile / b.period - 1) / (kBankTile / b.period);
-        kernel<<<persistent_grid(ctx, kernel, 256, kBankSmem, tiles), 256, kBankSmem, st>>>(
-            b, cf, ext, IdentityHook(), int(ctx->bulk_load_policy), int(ctx->bulk_store_policy));
+        // Synthetic capture is ~170 instructions per pair of frames: 32 warps per SM to get through
+        // them; ingested capture is a plain conversion: 8 warps, like the loopback kernel.
+        if (ext && ctx->block != 1024) {
+            auto kernel = bank_repeat_bulk_kernel<kBankStages, 256, IdentityHook>;
+            kernel<<<persistent_grid(ctx, kernel, 256, kBankSmem, tiles), 256, kBankSmem, st>>>(
+                b, cf, ext, IdentityHook(), int(ctx->bulk_load_policy), int(ctx->bulk_store_policy));
+        } else {
+            auto kernel = bank_repeat_bulk_kernel<kBankStages, 1024, IdentityHook>;
+            kernel<<<persistent_grid(ctx, kernel, 1024, kBankSmem, tiles), 1024, kBankSmem, st>>>(
+                b, cf, ext, IdentityHook(), int(ctx->bulk_load_policy), int(ctx->bulk_store_policy));
+        }
         break;
     }
     default: return ctx->invalid("bank_repeat_variant must be 0 (auto), 1, 2, 4, 8, 100, 201, 202, 204, 300 or 400");
