@@ -6,6 +6,7 @@
 //    must release both threads.
 // Built and run by tests/test_host_logic.py, under ThreadSanitizer when available.
 #include "host/par_copy.hpp"
+#include "host/worker_pool.hpp"
 
 #include <cstdio>
 #include <cstdlib>
@@ -113,6 +114,25 @@ int main(int argc, char **argv)
                 return 1;
             }
             runs++;
+        }
+    }
+    // WorkerPool: disjoint ranges covering [0, n), every item exactly once, many rounds, ranges
+    // below the grain run on the owner alone.
+    {
+        WorkerPool pool(helpers);
+        for (size_t n : {size_t(0), size_t(1), size_t(31), size_t(32), size_t(33), size_t(1000), size_t(4096)}) {
+            for (int round = 0; round < 20; round++) {
+                std::vector<int> hits(n, 0);
+                pool.run(n, 32, [&](size_t lo, size_t hi) {
+                    for (size_t i = lo; i < hi; i++)
+                        hits[i]++;
+                });
+                for (size_t i = 0; i < n; i++)
+                    if (hits[i] != 1) {
+                        std::fprintf(stderr, "pool: item %zu of %zu ran %d times\n", i, n, hits[i]);
+                        return 1;
+                    }
+            }
         }
     }
     std::printf("pipeline ok: %d plans, %d runs, %u helpers\n", plans, runs, helpers);

@@ -2,7 +2,7 @@
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_bank.py tests/test_gpu_hook.py -m gpu -q --maxfail=10 -p no:cacheprovider > gpurun_out/s8_pytest.log 2>&1
 echo "pytest exit $?" >> gpurun_out/s8_pytest.log; tail -15 gpurun_out/s8_pytest.log
-timeout 900 python tools/sweep_round2.py --only bank --tag s8_sweep_bank > gpurun_out/s8_sweep.log 2>&1; cat gpurun_out/s8_sweep.log | cut -c1-1000
+timeout 900 python tools/sweep_round2.py --only bank,ext --tag s8_sweep_bank > gpurun_out/s8_sweep.log 2>&1; cat gpurun_out/s8_sweep.log | cut -c1-1000
 for v in 100 400; do
 timeout 300 python bench.py --workload bank --fused --graph --steps 200 --repeat-variant $v > gpurun_out/s8_bench_bank_v$v.json 2> gpurun_out/s8_bench_bank.err
 timeout 300 python bench.py --workload bank --fused --graph --external --steps 200 --repeat-variant $v > gpurun_out/s8_bench_bank_ext_v$v.json 2>> gpurun_out/s8_bench_bank.err; done

@@ -163,6 +163,38 @@ def sweep_bank(ctx, side, out):
     out["bank_repeat"] = rows
 
 
+def sweep_extensions(ctx, side, out):
+    """CS16 stream format and S16 I2S frames (extensions, 12 B/frame): bulk shapes per conversion."""
+    st = side.cuda_stream
+    n = 1 << 27
+    wide = torch.empty(2 * n, dtype=torch.int32, device="cuda")      # 8 B/frame side
+    narrow = torch.empty(2 * n, dtype=torch.int16, device="cuda")    # 4 B/frame side
+    ctx.synth_frames(wide.data_ptr(), 0, n, 1, st)
+    ops = {
+        "rx_cs16": lambda: ctx.convert_rx_buffer_cs16(wide.data_ptr(), 0, narrow.data_ptr(), 0, n, st),
+        "tx_cs16": lambda: ctx.convert_tx_buffer_cs16(narrow.data_ptr(), 0, wide.data_ptr(), 0, n, 1e-6, st),
+        "rx_s16": lambda: ctx.convert_rx_buffer_s16(narrow.data_ptr(), 0, wide.data_ptr(), 0, n, st),
+        "tx_s16": lambda: ctx.convert_tx_buffer_s16(wide.data_ptr(), 0, narrow.data_ptr(), 0, n, 1e-6, st),
+    }
+    rows = []
+    for tile, stages in ((0, 0), (2048, 3), (2048, 5), (2048, 6), (3072, 4), (4096, 3), (1024, 6)):
+        ctx.set_option("bulk_tile", tile)
+        ctx.set_option("bulk_stages", stages)
+        for cps in (0, 1):
+            ctx.set_option("ctas_per_sm", cps)
+            row = {"tile": tile or "default", "stages": stages or "default", "ctas_per_sm": cps or "occupancy"}
+            for name, fn in ops.items():
+                sec = timed(fn, side, 10)
+                row[name + "_gbs"] = round(12 * n / sec / 1e9, 1)
+                row[name + "_frac"] = round(12 * n / sec / 1e9 / PEAK, 3)
+            rows.append(row)
+            print(json.dumps(row), flush=True)
+    ctx.set_option("bulk_tile", 0)
+    ctx.set_option("bulk_stages", 0)
+    ctx.set_option("ctas_per_sm", 0)
+    out["extensions_12B_per_frame"] = rows
+
+
 def pinned(ctx, nbytes, dtype):
     addr = ctx.malloc_host(nbytes)
     return addr, torch.frombuffer((ctypes.c_char * nbytes).from_address(addr), dtype=dtype)
@@ -330,6 +362,8 @@ def main():
         sweep_loopback(ctx, side, out)
     if "bank" in which:
         sweep_bank(ctx, side, out)
+    if "ext" in which:
+        sweep_extensions(ctx, side, out)
     if "host" in which:
         sweep_host(ctx, out)
     ctx.close()
