@@ -632,6 +632,26 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
         small[f"rx_host_{nf}_frames_us_per_call_resident"] = (time.perf_counter() - t0) / reps * 1e6
     ctx.set_option("resident_max_frames", 0)
 
+    # ---- the same workload from ONE process (sxgpu_multi_*): rank 0 alone drives every GPU of the
+    # job for a few steps while the other ranks wait, so that the scaling record also holds the
+    # one-process-G-contexts way of sharding ------------------------------
+    single = None
+    if world > 1 and not args.no_rows:
+        barrier()
+        if rank == 0 and torch.cuda.device_count() >= world:
+            try:
+                sp_steps = min(args.steps, 20)
+                sec_sp, launches_sp, checks_sp = measure_single_process(world, frames, sp_steps, 3)
+                single = {"value": world * 2 * frames / sec_sp / 1e6, "unit": UNIT, "ms_per_step": sec_sp * 1e3,
+                          "steps": sp_steps, "gpu_launches": launches_sp,
+                          "hbm_gbs_per_gpu": 2 * frames * BYTES_PER_FRAME / sec_sp / 1e9,
+                          "how": f"one process, {world} contexts and host threads (sxgpu_multi_*), wall clock with every GPU "
+                                 "synchronised on both sides; the other ranks idle meanwhile",
+                          "checksums_match_ranks": [c[:3] for c in checks_sp] == [list(c[:3]) for c in checks]}
+            except Exception as ex:          # evidence only: never take the judged line down with it
+                single = {"error": str(ex)[:200]}
+        barrier()
+
     # ---- CPU baseline beside it (rank 0, N=1 only): the reference driver on this box's cores ------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -658,6 +678,7 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
             "vs_baseline": None, "dtype": "s32<->f32", "data": "synthetic",
             "config": workload_config(args, frames),
             "roofline": dominant, "roofline_rx": roof_rx, "roofline_tx": roof_tx, "sustained": sustained,
+            "single_process": single,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * 8 * e2e_frames,
                     "d2h_bytes_per_step": 2 * 8 * e2e_frames, "frames_per_block": e2e_frames,
                     "ms_per_step": e2e_sec * 1e3, "gpu_launches": e2e_launches,
@@ -971,18 +992,14 @@ def run_group_arm(args, rank: int, local_rank: int, world: int):
         dist.destroy_process_group()
 
 
-def run_single_process_arm(args):
-    """--single-process --gpus N: the device-resident workload driven from ONE process through
-    sxgpu_multi_* (one context and one host thread per GPU, SURVEY.md section 8(e)) instead of one
-    rank per GPU.  Wall clock around K steps, every GPU synchronised on both sides."""
+def measure_single_process(G, frames, steps, warmup):
+    """K steps of one RX + one TX block per GPU driven from this ONE process through
+    sxgpu_multi_* (a context and a host thread per GPU).  Wall clock, every GPU synchronised on
+    both sides.  Returns (seconds per step, launches, per-GPU output checksums)."""
     import torch
     from sxxcvr_b200 import Multi
     from sxxcvr_b200.capi import Block
 
-    G = args.gpus
-    if torch.cuda.device_count() < G:
-        raise SystemExit(f"bench.py --single-process: {G} GPUs requested, {torch.cuda.device_count()} visible")
-    frames = 1 << args.log2_frames
     with Multi(list(range(G))) as m:
         bufs = []
         for g in range(G):
@@ -995,22 +1012,36 @@ def run_single_process_arm(args):
         m.sync()
         rx = [Block(b[0].data_ptr(), b[1].data_ptr(), frames, 0.0, 0) for b in bufs]
         tx = [Block(b[1].data_ptr(), b[2].data_ptr(), frames, THR2, 0) for b in bufs]
-        for _ in range(max(args.warmup, 3)):
+        for _ in range(max(warmup, 3)):
             m.convert_rx_batch(rx)
             m.convert_tx_batch(tx)
         m.sync()
         l0 = sum(m.context(g).counter("launches") for g in range(G))
         t0 = time.perf_counter()
-        for _ in range(args.steps):
+        for _ in range(steps):
             m.convert_rx_batch(rx)
             m.convert_tx_batch(tx)
         m.sync()
-        sec = (time.perf_counter() - t0) / args.steps
+        sec = (time.perf_counter() - t0) / steps
         launches = sum(m.context(g).counter("launches") for g in range(G)) - l0
         checks = [list(m.context(g).stats_words(bufs[g][2].data_ptr(), 2 * frames, 0)) for g in range(G)]
+        del bufs
+    return sec, launches, checks
+
+
+def run_single_process_arm(args):
+    """--single-process --gpus N: the device-resident workload driven from ONE process through
+    sxgpu_multi_* (one context and one host thread per GPU, SURVEY.md section 8(e)) instead of one
+    rank per GPU.  Wall clock around K steps, every GPU synchronised on both sides."""
+    import torch
+
+    G = args.gpus
+    if torch.cuda.device_count() < G:
+        raise SystemExit(f"bench.py --single-process: {G} GPUs requested, {torch.cuda.device_count()} visible")
+    frames = 1 << args.log2_frames
+    sec, launches, checks = measure_single_process(G, frames, args.steps, args.warmup)
     peak, peak_src = measured_peak()
     gbs = 2 * frames * BYTES_PER_FRAME / sec / 1e9
-    args.gpus = G
     emit(json.dumps({
         "metric": METRIC, "value": G * 2 * frames / sec / 1e6, "unit": UNIT, "n_gpus": G, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",

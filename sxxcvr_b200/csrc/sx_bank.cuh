@@ -356,7 +356,7 @@ __device__ __forceinline__ void bank_repeat_stream(const BankState &b, uint64_t 
 // (one round trip, all vectors in flight at once) instead of being produced here.
 // Needs an even period and 16-byte aligned CF32 blocks; a block that does not start on a period
 // boundary of the ring falls back to frame-wide stores for the ring side.
-template <class Hook>
+template <int U, class Hook>
 __device__ __forceinline__ void bank_repeat_stream_reg(const BankState &b, uint64_t s, char *cf32, uint64_t first,
                                                        long long at, long long gap, long long start, uint32_t lane,
                                                        bool capture_in_slot, const Hook &hook)
@@ -382,7 +382,6 @@ __device__ __forceinline__ void bank_repeat_stream_reg(const BankState &b, uint6
     const bool ring_vec = at >= 0 && uint64_t(at) % b.period == 0;
     char *ring = ring_vec ? ring_frame(b, s, uint64_t(at)) : nullptr;
 
-    constexpr int U = 4;
     for (uint32_t base = 0; base < nvec; base += 32 * U) {
         Pack<4> cap[U], mid[U], out[U];
         if (capture_in_slot) {
@@ -462,7 +461,7 @@ __global__ void __launch_bounds__(256) bank_repeat_reg_kernel(BankState b, char 
             const long long start = __shfl_sync(0xffffffffu, my_start, j);
             if (j >= count)
                 break;
-            bank_repeat_stream_reg(b, base + j, cf32, first, at, gap, start, lane, capture_in_slot, hook);
+            bank_repeat_stream_reg<4>(b, base + j, cf32, first, at, gap, start, lane, capture_in_slot, hook);
         }
     }
 }
@@ -472,9 +471,11 @@ __global__ void __launch_bounds__(256) bank_repeat_reg_kernel(BankState b, char 
 // on one lane per stream: 32 lanes side by side cost what one does), hands them over in shared
 // memory, and each of the CTA's warps then produces, converts and stores its streams' blocks
 // without reading anything back.
-template <class Hook>
-__global__ void __launch_bounds__(256) bank_repeat_group_reg_kernel(BankState b, char *cf32, long long rx_time_offset_ns,
-                                                                    bool capture_in_slot, Hook hook)
+// U = 16-byte vectors a lane has in flight (4: a 256-frame period in one go, ~98 registers, two
+// CTAs per SM; 2: two passes per period, fewer registers, MINB CTAs per SM).
+template <int U, int MINB, class Hook>
+__global__ void __launch_bounds__(256, MINB) bank_repeat_group_reg_kernel(BankState b, char *cf32, long long rx_time_offset_ns,
+                                                                          bool capture_in_slot, Hook hook)
 {
     __shared__ long long s_first[2][32], s_at[2][32], s_gap[2][32], s_start[2][32];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps_per_cta = blockDim.x >> 5;
@@ -496,8 +497,8 @@ __global__ void __launch_bounds__(256) bank_repeat_group_reg_kernel(BankState b,
         // plan the next group while the others are still moving this one's blocks.
         __syncthreads();
         for (uint32_t j = warp; j < count; j += warps_per_cta)
-            bank_repeat_stream_reg(b, base + j, cf32, uint64_t(s_first[buf][j]), s_at[buf][j], s_gap[buf][j],
-                                   s_start[buf][j], lane, capture_in_slot, hook);
+            bank_repeat_stream_reg<U>(b, base + j, cf32, uint64_t(s_first[buf][j]), s_at[buf][j], s_gap[buf][j],
+                                      s_start[buf][j], lane, capture_in_slot, hook);
     }
 }
 
@@ -719,11 +720,17 @@ __global__ void __launch_bounds__(BLOCK) bank_repeat_bulk_kernel(BankState b, ch
         if (threadIdx.x < 32)
             bulk::wait_group_read<STAGES - 1>();
         __syncthreads();
-        // The next tile's decisions go into the other half of `meta`: its last readers (tile i - 1,
-        // up to thread 0's store issue) are all behind the barrier above, its next readers two
-        // barriers ahead.
-        if (i + 1 < mine)
-            load_meta(i + 1);
+        // The next tile's decisions: requested now into registers, parked in the other half of
+        // `meta` after the conversion (its last readers -- tile i - 1, up to the first warp's store
+        // issue -- are all behind the barrier above, its next readers two barriers ahead), so the
+        // round trip to memory runs under the conversion instead of in front of it.
+        long long next_first = 0, next_at = -1;
+        const bool fetch_next = i + 1 < mine && threadIdx.x < tile_streams(i + 1);
+        if (fetch_next) {
+            const uint64_t sn = (first_tile + (i + 1) * stride) * spt + threadIdx.x;
+            next_first = b.rx_first_frame[sn];
+            next_at = b.tx_write_position[sn];
+        }
         const BankTileMeta &m = meta[i & 1];
 
         uint4 *ip = reinterpret_cast<uint4 *>(in_buf + size_t(s) * STAGE);
@@ -748,6 +755,10 @@ __global__ void __launch_bounds__(BLOCK) bank_repeat_bulk_kernel(BankState b, ch
             TxCf32::apply<2>(mid, out, b.thr2);
             mp[v] = make_uint4(mid.w[0], mid.w[1], mid.w[2], mid.w[3]);
             op[v] = make_uint4(out.w[0], out.w[1], out.w[2], out.w[3]);
+        }
+        if (fetch_next) {
+            meta[(i + 1) & 1].first[threadIdx.x] = next_first;
+            meta[(i + 1) & 1].at[threadIdx.x] = next_at;
         }
         bulk::fence_async_smem();
         __syncthreads();

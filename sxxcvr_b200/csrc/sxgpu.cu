@@ -400,7 +400,10 @@ int launch_bulk(sxgpu_ctx *ctx, const char *src, const char *dst_c, uint64_t tot
 
     // Measured (profiles/r01_summary.md): 2048-frame tiles x 4 stages for large blocks; below
     // 2^24 frames the 1024-frame tile spreads the fewer tiles over more SMs.
-    BulkShape shape = {int(ctx->bulk_tile ? ctx->bulk_tile : (total >= (uint64_t(1) << 24) ? 2048 : 1024)),
+    // Unequal frame widths (the CS16 / S16 extensions, 12 B/frame): 3072 x 4, measured 0.98-1.04 of
+    // the copy peak for all four conversions against 0.78-0.93 on the equal-width default (r02).
+    const int big_tile = (SFB == DFB) ? 2048 : 3072;
+    BulkShape shape = {int(ctx->bulk_tile ? ctx->bulk_tile : (total >= (uint64_t(1) << 24) ? big_tile : 1024)),
                        int(ctx->bulk_stages ? ctx->bulk_stages : 4)};
     BulkKernel k = nullptr;
     bool skew = false;
@@ -1785,10 +1788,19 @@ int sxgpu_bank_repeat(sxgpu_bank *bank, void *d_cf32, long long rx_time_offset_n
     case 201: reg_variant(bank_repeat_reg_kernel<1, IdentityHook>, 1); break;
     case 202: reg_variant(bank_repeat_reg_kernel<2, IdentityHook>, 2); break;
     case 204: reg_variant(bank_repeat_reg_kernel<4, IdentityHook>, 4); break;
-    case 300: { // a CTA takes 32 streams per round: first warp decides, every warp keeps its streams in registers
+    case 300:   // a CTA takes 32 streams per round: first warp decides, every warp keeps its streams in registers
+    case 302:   // ... two vectors per lane in flight instead of four: fewer registers, three CTAs per SM
+    case 303: { // ... four CTAs per SM
         const uint64_t groups = (uint64_t(b.nstreams) + 31) / 32;
-        auto kernel = bank_repeat_group_reg_kernel<IdentityHook>;
-        kernel<<<persistent_grid(ctx, kernel, 256, 0, groups), 256, 0, st>>>(b, cf, rx_time_offset_ns, ext, IdentityHook());
+        auto go = [&](auto kernel) {
+            kernel<<<persistent_grid(ctx, kernel, 256, 0, groups), 256, 0, st>>>(b, cf, rx_time_offset_ns, ext, IdentityHook());
+        };
+        if (k == 300)
+            go(bank_repeat_group_reg_kernel<4, 1, IdentityHook>);
+        else if (k == 302)
+            go(bank_repeat_group_reg_kernel<2, 3, IdentityHook>);
+        else
+            go(bank_repeat_group_reg_kernel<2, 4, IdentityHook>);
         break;
     }
     case 400: { // decisions by a thread-per-stream kernel, samples on the bulk-async schedule
@@ -1811,7 +1823,7 @@ int sxgpu_bank_repeat(sxgpu_bank *bank, void *d_cf32, long long rx_time_offset_n
         }
         break;
     }
-    default: return ctx->invalid("bank_repeat_variant must be 0 (auto), 1, 2, 4, 8, 100, 201, 202, 204, 300 or 400");
+    default: return ctx->invalid("bank_repeat_variant must be 0 (auto), 1, 2, 4, 8, 100, 201, 202, 204, 300, 302, 303 or 400");
     }
     SX_CUDA(ctx, cudaGetLastError());
     ctx->launches += 1;

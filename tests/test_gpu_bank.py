@@ -237,7 +237,7 @@ def assert_same(a, b, where):
     (70, 3, 600000.0, 0.0),          # odd ring, tiny blocks: frame-wide accesses only
     (2, 4096, 32.0e6 / 1536, 0.25),
 ])
-@pytest.mark.parametrize("variant", [0, 1, 2, 4, 8, 100, 201, 202, 204, 300, 400])
+@pytest.mark.parametrize("variant", [0, 1, 2, 4, 8, 100, 201, 202, 204, 300, 302, 303, 400])
 def test_repeat_is_read_then_write(ctx, nstreams, period, rate, thr2, variant):
     """sxgpu_bank_repeat against the two calls it fuses, through overruns, late (discarded)
     bursts, far-ahead bursts (forward-and-wait with silence) and interleaved separate calls."""
@@ -270,7 +270,7 @@ def test_repeat_is_read_then_write(ctx, nstreams, period, rate, thr2, variant):
     ctx.set_option("bank_repeat_variant", 0)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 4, 8, 100, 201, 202, 204, 300, 400])
+@pytest.mark.parametrize("variant", [0, 1, 2, 4, 8, 100, 201, 202, 204, 300, 302, 303, 400])
 def test_repeat_large_bank_against_oracle(ctx, oracle, variant):
     from sxxcvr_b200 import Bank
     S, P = 16384 + 5, 256
@@ -358,7 +358,7 @@ def test_ingested_frames_replace_the_synthetic_capture(ctx, oracle, variant):
 
 
 @pytest.mark.parametrize("latency_frames", [769, 770, 1023, 1])
-@pytest.mark.parametrize("variant", [2, 100, 202, 300, 400])
+@pytest.mark.parametrize("variant", [2, 100, 202, 300, 303, 400])
 def test_repeat_with_blocks_that_straddle_ring_slices(ctx, variant, latency_frames):
     """Write positions that are not multiples of the period (odd, and even but inside a slice of
     the time-major ring): every schedule against the two calls it fuses."""
