@@ -639,6 +639,11 @@ int ensure_ring(sxgpu_ctx *ctx, HostLane &lane, size_t frames, bool bounce_in, b
         }
         r.chunk_frames = frames;
     }
+    bool missing = false;
+    for (int i = 0; i < kRingSlots; i++)
+        missing = missing || (bounce_in && !r.h_in[i]) || (bounce_out && !r.h_out[i]);
+    if (!missing)
+        return SXGPU_OK; // the usual case; nothing below runs per call (NearGpu is two system calls)
     NearGpu near(ctx);
     for (int i = 0; i < kRingSlots; i++) {
         if (bounce_in && !r.h_in[i])
@@ -780,10 +785,15 @@ unsigned bounce_thread_count(const sxgpu_ctx *ctx)
 {
     unsigned threads = unsigned(std::min<int64_t>(ctx->bounce_threads, 64));
     if (threads == 0) {
-        unsigned ranks = 1;
-        if (const char *env = std::getenv("LOCAL_WORLD_SIZE"))
-            ranks = unsigned(std::max(1, std::atoi(env)));
-        threads = std::max(1u, std::min(8u, std::thread::hardware_concurrency() / (2 * ranks)));
+        // Asked once per process: hardware_concurrency() reads /sys on every call, which a
+        // period-sized block (a 2 KiB copy) would pay twice per read+write pair.
+        static const unsigned automatic = [] {
+            unsigned ranks = 1;
+            if (const char *env = std::getenv("LOCAL_WORLD_SIZE"))
+                ranks = unsigned(std::max(1, std::atoi(env)));
+            return std::max(1u, std::min(8u, std::thread::hardware_concurrency() / (2 * ranks)));
+        }();
+        threads = automatic;
     }
     return threads;
 }
@@ -791,6 +801,13 @@ unsigned bounce_thread_count(const sxgpu_ctx *ctx)
 void bounce_copy(sxgpu_ctx *ctx, std::unique_ptr<sxhost::ParallelCopier> &copier, void *dst, const void *src,
                  size_t bytes)
 {
+    if (bytes < sxhost::ParallelCopier::kMinParallelBytes) { // small: this thread alone, no pool to consult
+        if (ctx->bounce_nt)
+            sxhost::stream_copy(dst, src, bytes);
+        else
+            std::memcpy(dst, src, bytes);
+        return;
+    }
     const unsigned threads = bounce_thread_count(ctx);
     const bool streaming = ctx->bounce_nt != 0;
     if (!copier || copier->helpers() != threads - 1 || copier->streaming() != streaming)

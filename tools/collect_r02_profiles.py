@@ -11,18 +11,36 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 OUT, PROF = ROOT / "gpurun_out", ROOT / "profiles"
 
-COPIES = {  # gpurun_out name -> profiles name (first that exists wins when a list is given)
-    "r02_bench_n1.json": ["s9_bench.json", "s4_bench.json"],
-    "r02_bench_reference_arm.json": ["s9_bench_ref.json", "s4_bench_ref.json"],
-    "r02_bench_sweep.json": ["s9_bench_sweep.json", "s4_bench_sweep.json"],
-    "r02_bench_group.json": ["s9_bench_group.json", "s5_bench_group.json"],
-    "r02_bench_single_process.json": ["s9_bench_single.json", "s4_bench_single.json"],
-    "r02_launches.csv": ["s9_launches.csv", "s4_launches.csv"],
-    "r02_sweep_host_path_and_plugin_pairs.json": ["s3_sweep.json"],
+COPIES = {  # profiles name -> candidates under gpurun_out (first that exists wins)
+    "r02_bench_n1.json": ["f1_bench.json"],
+    "r02_bench_n1_steps20.json": ["f1_bench_steps20.json"],
+    "r02_bench_reference_arm.json": ["f1_bench_ref.json"],
+    "r02_bench_sweep.json": ["f1_bench_sweep.json"],
+    "r02_bench_group.json": ["f1_bench_group.json"],
+    "r02_bench_single_process.json": ["f1_bench_single.json"],
+    "r02_bench_bank_fused.json": ["f1_bench_bank_fused.json"],
+    "r02_bench_bank_fused_graph.json": ["f1_bench_bank_fused_graph.json"],
+    "r02_bench_bank_fused_graph_external.json": ["f1_bench_bank_fused_graph_external.json"],
+    "r02_bench_bank_two_calls.json": ["f1_bench_bank_two_calls.json"],
+    "r02_bench_n2.json": ["m2_bench.json"],
+    "r02_bench_n2_single_process.json": ["m2_bench_single.json"],
+    "r02_bench_n2_reference_arm.json": ["m2_bench_ref.json"],
+    "r02_bench_n4.json": ["m4_bench.json"],
+    "r02_bench_n8.json": ["m8_bench.json"],
+    "r02_bench_n8_single_process.json": ["m8_bench_single.json"],
+    "r02_bench_n8_reference_arm.json": ["m8_bench_ref.json"],
+    "r02_bench_n8_sweep.json": ["m8_bench_sweep.json"],
+    "r02_launches.csv": ["f1_launches.csv"],
+    "r02_sweep_host_path_and_plugin_pairs.json": ["f1_sweep_host_plugin.json", "s3_sweep.json"],
+    "r02_sweep_bank_and_extensions.json": ["f1_sweep_bank_ext.json"],
     "r02_sweep_batched_loopback.json": ["s4_sweep.json"],
+    "r02_sweep_pipeline_modes.json": ["s3_sweep.json"],
     "r02_probe_batch_per_call.log": ["s4_probe_batch.log"],
     "r02_probe_batch_with_default_mempool.log": ["probe_batch.log"],
     "r02_probe_batch_with_default_mempool_ncu.csv": ["probe_batch_ncu.csv"],
+    "r02_sanitizer_memcheck.log": ["f1_sanitizer_memcheck.log"],
+    "r02_sanitizer_racecheck.log": ["f1_sanitizer_racecheck.log"],
+    "r02_final_gpu_pytest.log": ["f1_pytest.log"],
 }
 
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__bytes.sum.per_second",
@@ -55,7 +73,7 @@ def main():
         else:
             print("missing:", srcs, file=sys.stderr)
     table, traffic = [], {}
-    for rep in sorted(OUT.glob("s*_ncu_*.ncu-rep")):
+    for rep in sorted(list(OUT.glob("f1_ncu_*.ncu-rep")) + list(OUT.glob("s9a_ncu_*.ncu-rep"))):
         rows, units = raw_rows(rep)
         seen = {}
         for d in rows:
