@@ -638,18 +638,29 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
     single = None
     if world > 1 and not args.no_rows:
         barrier()
-        if rank == 0 and torch.cuda.device_count() >= world:
-            try:
-                sp_steps = min(args.steps, 20)
-                sec_sp, launches_sp, checks_sp = measure_single_process(world, frames, sp_steps, 3)
-                single = {"value": world * 2 * frames / sec_sp / 1e6, "unit": UNIT, "ms_per_step": sec_sp * 1e3,
-                          "steps": sp_steps, "gpu_launches": launches_sp,
-                          "hbm_gbs_per_gpu": 2 * frames * BYTES_PER_FRAME / sec_sp / 1e9,
-                          "how": f"one process, {world} contexts and host threads (sxgpu_multi_*), wall clock with every GPU "
-                                 "synchronised on both sides; the other ranks idle meanwhile",
-                          "checksums_match_ranks": [c[:3] for c in checks_sp] == [list(c[:3]) for c in checks]}
-            except Exception as ex:          # evidence only: never take the judged line down with it
-                single = {"error": str(ex)[:200]}
+        # The other ranks must wait on the HOST: a rank parked in an NCCL barrier keeps a kernel
+        # spinning on its GPU, which is one of the GPUs being measured.
+        try:
+            store = dist.distributed_c10d._get_default_store()
+        except Exception:
+            store = None
+        if rank == 0:
+            if torch.cuda.device_count() >= world and store is not None:
+                try:
+                    sp_steps = min(args.steps, 20)
+                    sec_sp, launches_sp, checks_sp = measure_single_process(world, frames, sp_steps, 3)
+                    single = {"value": world * 2 * frames / sec_sp / 1e6, "unit": UNIT, "ms_per_step": sec_sp * 1e3,
+                              "steps": sp_steps, "gpu_launches": launches_sp,
+                              "hbm_gbs_per_gpu": 2 * frames * BYTES_PER_FRAME / sec_sp / 1e9,
+                              "how": f"one process, {world} contexts and host threads (sxgpu_multi_*), wall clock with every GPU "
+                                     "synchronised on both sides; the other ranks wait on the host meanwhile",
+                              "checksums_match_ranks": [c[:3] for c in checks_sp] == [list(c[:3]) for c in checks]}
+                except Exception as ex:          # evidence only: never take the judged line down with it
+                    single = {"error": str(ex)[:200]}
+            if store is not None:
+                store.set("sx_single_process_leg_done", "1")
+        elif store is not None:
+            store.wait(["sx_single_process_leg_done"])
         barrier()
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the reference driver on this box's cores ------
@@ -794,12 +805,15 @@ def run_bank_arm(args, rank: int, local_rank: int, world: int):
     value = world * 2 * S * P / (ms * 1e-3) / 1e6
     hbm_bytes = 24 if args.fused else 40
     traffic = None      # DRAM bytes per launch from the committed ncu capture, when it is of this shape
-    try:
-        t = json.loads((ROOT / "profiles" / "r01_traffic.json").read_text()).get("bank_repeat", {})
-        if args.fused and t.get("streams") == S and t.get("frames_per_block") == P:
-            traffic = t.get("bytes_per_launch")
-    except (OSError, ValueError):
-        pass
+    traffic_source = None
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            t = json.loads((ROOT / "profiles" / name).read_text()).get("bank_repeat", {})
+            if args.fused and not args.external and t.get("streams") == S and t.get("frames_per_block") == P:
+                traffic, traffic_source = t.get("bytes_per_launch"), f"profiles/{name} (ncu --set full, one launch)"
+                break
+        except (OSError, ValueError):
+            pass
     if rank == 0:
         emit(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -828,7 +842,9 @@ def run_bank_arm(args, rank: int, local_rank: int, world: int):
                          "frac": hbm_bytes * S * P / (ms * 1e-3) / 1e9 / peak,
                          "moved_gbs": 40 * S * P / (ms * 1e-3) / 1e9,
                          "algorithmic_bytes_per_launch": hbm_bytes * S * P,
-                         "traffic": traffic, "peak_source": peak_src},
+                         "traffic": traffic, "traffic_source": traffic_source, "peak_source": peak_src,
+                         "frac_of_write_only_ceiling": hbm_bytes * S * P / (ms * 1e-3) / 1e9 / 7139.0,
+                         "write_only_ceiling": "7 139 GB/s: cudaMemset of 1 GiB on this part (profiles/r01_hbm_limits.json)"},
             "e2e": None, "gpu_launches": launches if not args.graph else None, "cpu_baseline": None,
             "constant_latency_holds": ok, "last_block_nonzero": bool(ring.any()),
             "checksums": {"fields": list(sharding.STATS_FIELDS), "per_rank": checks,
