@@ -452,8 +452,8 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
                 "frac": achieved / peak, "traffic": None, "avg_launch_ms": avg, "best_launch_ms": min(ms_list),
                 "algorithmic_bytes_per_launch": frames * BYTES_PER_FRAME, "peak_source": peak_src}
 
-    roof_rx = roof(rx_ms, "bulk_convert_kernel<RxCf32>")
-    roof_tx = roof(tx_ms, "bulk_convert_kernel<TxCf32>")
+    roof_rx = roof(rx_ms, "stream_convert_kernel<RxCf32, 2, 2, 256>, one tile per CTA")
+    roof_tx = roof(tx_ms, "stream_convert_kernel<TxCf32, 2, 2, 256>, one tile per CTA")
     dominant = roof_tx if sum(tx_ms) >= sum(rx_ms) else roof_rx
     # DRAM bytes per launch come from an `ncu --set full` capture, which cannot run inside a timed
     # bench: the committed capture of this same launch (same kernel, same frames per launch) is
@@ -544,8 +544,9 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
     def plugin_leg(kind):
         streams = PluginStreams(product, e2e_frames, e2e_streams, kind, dev_args, ctx, SEED + rank)
         try:
+            streams.run(max(args.warmup, 3), 0)   # warm-up as a pass of its own: every rank enters the timed one together
             barrier()
-            sec = streams.run(args.steps, max(args.warmup, 3))
+            sec = streams.run(args.steps, 0)
             barrier()
             nlaunch = sum(d.counter("launches") for d in streams.devs)
         finally:
@@ -830,13 +831,15 @@ def run_bank_arm(args, rank: int, local_rank: int, world: int):
                        "calls_per_step": "sxgpu_bank_repeat (one launch)" if args.fused
                                          else "sxgpu_bank_read + sxgpu_bank_write",
                        "parallelism": f"streams sharded over {world} GPU(s) in contiguous ranges, no data-path collective"},
-            # One launch: each stage reads what the previous one has just written while it is in
-            # L2, so what must cross HBM is the three writes, 24 B/frame (ncu: 399 MB written,
-            # 2-3 MB read per launch at 65536 streams, profiles/r01_launches_bank_fused.csv); the
-            # roofline is taken against those.  Separate launches move all 40 B/frame through HBM.
-            "roofline": {"kernel": "bank iteration (stand-in DMA 8 W + RX 8 R + 8 W + TX 8 R + 8 W per frame"
-                                   + ("; one launch: the two reads are served from L2, the 24 B/frame of writes reach HBM)"
-                                      if args.fused else ")"),
+            # One call: nothing is read back (the capture frames, their CF32 and I2S forms stay in
+            # registers between the stages), so what must cross HBM is the three writes, 24 B/frame --
+            # or 8 read + 16 written when the capture frames come from outside; the roofline is taken
+            # against those.  Separate read and write calls move all 40 B/frame through HBM.
+            "roofline": {"kernel": ("bank_plan_repeat_kernel + bank_repeat_data_kernel (decisions by a thread per stream, then "
+                                    "capture -> RX -> TX in registers, three stores per vector; "
+                                    + ("8 R + 16 W" if args.external else "24 W") + " per frame reach HBM)")
+                                   if args.fused else
+                                   "bank iteration, separate calls (stand-in DMA 8 W + RX 8 R + 8 W + TX 8 R + 8 W per frame)",
                          "hbm_bytes_per_frame": hbm_bytes, "bytes_moved_per_frame": 40,
                          "bound": "hbm", "achieved": hbm_bytes * S * P / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": hbm_bytes * S * P / (ms * 1e-3) / 1e9 / peak,
@@ -930,7 +933,7 @@ def run_sweep_arm(args, rank: int, local_rank: int, world: int):
                        "frames_per_step_per_gpu": 2 * total * len(rows), "bytes_per_frame": BYTES_PER_FRAME,
                        "cache": "buffers of 1 GiB >> 126 MB L2",
                        "parallelism": f"blocks sharded over {world} GPU(s), no data-path collective"},
-            "roofline": {"kernel": "bulk_batch_kernel (worst shape of the sweep)", "bound": "hbm",
+            "roofline": {"kernel": "batch_direct_kernel (worst shape of the sweep)", "bound": "hbm",
                          "achieved": worst["hbm_gbs_per_gpu"], "peak": peak, "unit": "GB/s", "frac": worst["frac"],
                          "traffic": None, "peak_source": peak_src, "shape": f"{worst['blocks_per_launch']} x {worst['block_bytes'] >> 20} MiB"},
             "sweep": rows, "e2e": None, "gpu_launches": launches, "cpu_baseline": None}))
@@ -1065,7 +1068,7 @@ def run_single_process_arm(args):
         "config": dict(workload_config(args, frames),
                        parallelism=f"ONE process, {G} contexts and host threads (sxgpu_multi_*), one block per GPU per launch, no collective",
                        timing="wall clock around the timed steps, every GPU synchronised on both sides"),
-        "roofline": {"kernel": "bulk_batch_kernel, one 1 GiB block per GPU", "bound": "hbm", "achieved": gbs, "peak": peak,
+        "roofline": {"kernel": "batch_direct_kernel, one 1 GiB block per GPU", "bound": "hbm", "achieved": gbs, "peak": peak,
                      "unit": "GB/s", "frac": gbs / peak, "traffic": None, "peak_source": peak_src,
                      "note": "per-GPU average over the RX+TX step, launch gaps included"},
         "e2e": None, "gpu_launches": launches, "cpu_baseline": None,

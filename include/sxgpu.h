@@ -312,8 +312,10 @@ int sxgpu_multi_sync(sxgpu_multi *m);
 /* ---- tuning and accounting ---------------------------------------------------------------- */
 
 /* Options (all have measured defaults):
- *   "rx_variant", "tx_variant"  0 = auto, 1 = 128-bit vector, 2 = 256-bit vector,
- *                               3 = bulk-async (TMA) staged through shared memory
+ *   "rx_variant", "tx_variant"  0 = auto (= 4), 1 = 128-bit vector, 2 = 256-bit vector,
+ *                               3 = bulk-async (TMA) staged through shared memory -- those three
+ *                               on persistent grids -- 4 = vector accesses, one tile per CTA,
+ *                               CTAs handed out in order by the hardware
  *   "ctas_per_sm"               persistent grid = sm_count * ctas_per_sm (0 = auto)
  *   "host_chunk_frames"         chunk size of the *_host pipeline
  *   "host_mode"                 0 = auto, 1 = copy-engine pipeline, 2 = zero-copy kernel
@@ -327,11 +329,21 @@ int sxgpu_multi_sync(sxgpu_multi *m);
  *                               K in {1, 2, 4, 8} = a warp takes K streams per round, stage by
  *                               stage through memory; 100 = a CTA takes 32 streams per round;
  *                               200 + K, K in {1, 2, 4} = a warp takes K streams per round and
- *                               keeps every intermediate in registers (stores only)
+ *                               keeps every intermediate in registers (stores only); 300, 302,
+ *                               303 = the same with a CTA's first warp deciding for 32 streams;
+ *                               400 = decisions by a thread-per-stream kernel, samples on the
+ *                               bulk-async schedule; 500, 502 = one launch, one chunk of streams
+ *                               per CTA; 600, 604 = decisions by a thread-per-stream kernel, then
+ *                               the samples by CTAs that take one chunk each (2 or 4 vectors per
+ *                               thread), the second kernel a programmatic dependent of the first
+ *                               ("bank_pdl" = 0 turns that off)
  *   "batch_variant"             blocks above 4096 frames in sxgpu_convert_*_batch: 0 = auto
- *                               (tiles of all blocks on the bulk-async schedule), 1 = slices of
- *                               CTAs on vector accesses
- *   "loopback_variant"          sxgpu_convert_loopback: 0 = auto (bulk-async), 1 = vector accesses
+ *                               (2 when the blocks are of similar length, else 3), 1 = slices of
+ *                               CTAs on vector accesses, 2 = one chunk per CTA in block-then-chunk
+ *                               order, 3 = tiles of all blocks on the bulk-async schedule
+ *   "loopback_variant"          sxgpu_convert_loopback: 0 = auto (= 2), 1 = vector accesses on a
+ *                               persistent grid, 2 = vector accesses, one tile per CTA,
+ *                               3 = bulk-async
  *   "small_mode"                completion of synchronous calls of up to zero_copy_max_frames
  *                               frames on host buffers: 0 = auto (= 2), 1 = stream
  *                               synchronisation, 2 = the kernel raises a flag in pinned memory

@@ -34,6 +34,18 @@
 
 namespace sx {
 
+// Programmatic dependent launch (no-ops in a kernel that was launched the ordinary way): the
+// first lets the next kernel of the stream be set up on the SMs while this one is still running;
+// the second, in that next kernel, waits until this one has finished and its stores are visible.
+__device__ __forceinline__ void pdl_launch_dependents()
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait()
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 struct BankState {
     uint32_t nstreams;
     uint32_t period;
@@ -58,6 +70,10 @@ struct BankState {
     long long *tx_write_position;
     long long *tx_gap_start; // forwarded-over region to be silenced
     long long *tx_gap_length;
+    long long *tx_ring_offset; // byte offset in playback_ring of the block's first frame (a multiple of 8),
+                               // + 1 when the block does not start on a period boundary of the ring (it then
+                               // spans two slices); -1: discarded as late.  Written by
+                               // bank_plan_repeat_kernel for the data kernels.
 
     char *capture_stage; // [nstreams][period] I2S frames
     char *playback_ring; // [ring / period][nstreams][period] I2S frames, see ring_frame()
@@ -72,6 +88,12 @@ struct BankState {
 // per write.  A block that does not start on a period boundary spans two slices.
 __device__ __forceinline__ char *ring_frame(const BankState &b, uint64_t s, uint64_t pos)
 {
+    const uint32_t P = b.period;
+    if ((P & (P - 1)) == 0) { // a power of two (the default 256 is): so is the ring, 65536, and everything is a shift
+        const uint32_t lg = 31 - __clz(P);
+        const uint64_t slice = (pos >> lg) & ((b.ring >> lg) - 1);
+        return b.playback_ring + ((((slice * b.nstreams + s) << lg) + (pos & (P - 1))) << 3);
+    }
     const uint64_t slice = (pos / b.period) % (b.ring / b.period);
     return b.playback_ring + ((slice * b.nstreams + s) * b.period + pos % b.period) * 8;
 }
@@ -631,12 +653,16 @@ __global__ void bank_gather_kernel(BankState b, uint32_t stream, long long posit
 // ---------------------------------------------------------------------------------------
 __global__ void bank_plan_repeat_kernel(BankState b, char *cf32, long long rx_time_offset_ns)
 {
+    pdl_launch_dependents(); // the data kernel may take its place on the SMs now; it waits for us before it reads
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= b.nstreams)
         return;
     long long first;
     BankWritePlan w;
     bank_plan_repeat(b, s, cf32, rx_time_offset_ns, first, w);
+    b.tx_ring_offset[s] = w.at >= 0 ? (long long)(ring_frame(b, s, uint64_t(w.at)) - b.playback_ring) +
+                                          (uint64_t(w.at) % b.period != 0 ? 1 : 0)
+                                    : -1;
     if (w.at >= 0 && w.gap > 0) { // ALSA plays zeros for what the application skipped (:493-496)
         long long gap = w.gap, start = w.start;
         if (gap > (long long)b.ring) {
@@ -820,6 +846,272 @@ __global__ void __launch_bounds__(BLOCK) bank_repeat_bulk_kernel(BankState b, ch
     }
     if (threadIdx.x < 32)
         bulk::wait_group_all();
+}
+
+// ---------------------------------------------------------------------------------------
+// The repeater iteration, one launch, hardware-scheduled CTAs ("direct" schedule).
+//
+// Every schedule above runs a persistent grid, and every one of them -- memory-staged, register-
+// resident, bulk-async -- lands within a few percent of what *plain stores of the same bytes from
+// a persistent grid* reach (tools/experiments/bank_limits.cu: 65.6 us for the 402 MB of 65536
+// streams x 256 frames, exactly cudaMemset's time over the same three regions).  The same bytes
+// written by CTAs that each take one chunk and leave -- handed out in index order by the hardware,
+// so that the addresses in flight form one compact window moving through each region -- take
+// 56-58 us, arithmetic included.  Hence this kernel: CTA c owns streams [c * G, (c + 1) * G), G
+// chosen so that they make up 256 * U 16-byte vectors; its first G threads take those streams'
+// decisions side by side (bank_plan_repeat: same stores, same order as every other schedule) and
+// park what the data phase needs in shared memory; then all threads produce (or load) the
+// capture frames, convert RX, apply the hook, convert TX and issue the three stores, U vectors
+// per thread in flight, nothing read back.  The streams' periods lie side by side in the capture
+// slots and in the caller's CF32 buffer, so those two are flat arrays; the ring side is flat too
+// whenever a block starts on a period boundary of the ring (two spans, frame-wide stores,
+// otherwise).  Needs an even period and a 16-byte aligned CF32 buffer.
+// ---------------------------------------------------------------------------------------
+struct BankDirectPlan {
+    long long first; // counter value of the stream's first captured frame
+    char *span1;     // where its block starts in the ring; nullptr: discarded as late
+    char *span2;     // where frame span1_frames of the block goes (blocks that straddle a slice boundary)
+    uint32_t span1_frames;
+    uint32_t vector_ok; // the whole block is one 16-byte aligned span
+};
+
+constexpr int kBankDirectMaxGroup = 256;
+
+__host__ __device__ inline uint32_t bank_direct_group(uint32_t period, int U)
+{
+    const uint32_t nvec = period / 2;
+    uint32_t g = nvec ? uint32_t(256 * U) / nvec : 1;
+    return g < 1 ? 1 : (g > uint32_t(kBankDirectMaxGroup) ? uint32_t(kBankDirectMaxGroup) : g);
+}
+
+template <int U, class Hook>
+__global__ void __launch_bounds__(256) bank_repeat_direct_kernel(BankState b, char *cf32, long long rx_time_offset_ns,
+                                                                 bool capture_in_slot, Hook hook)
+{
+    __shared__ BankDirectPlan s_plan[kBankDirectMaxGroup];
+    __shared__ long long s_gap[kBankDirectMaxGroup], s_start[kBankDirectMaxGroup];
+
+    const uint32_t nvec = b.period / 2;
+    const uint32_t G = bank_direct_group(b.period, U);
+    const uint64_t s0 = uint64_t(blockIdx.x) * G;
+    if (s0 >= b.nstreams)
+        return;
+    const uint32_t count = uint32_t(b.nstreams - s0 < G ? b.nstreams - s0 : G);
+
+    bool my_gap = false;
+    if (threadIdx.x < count) {
+        const uint64_t s = s0 + threadIdx.x;
+        long long first;
+        BankWritePlan w;
+        bank_plan_repeat(b, s, cf32, rx_time_offset_ns, first, w);
+        BankDirectPlan p;
+        p.first = first;
+        p.span1 = p.span2 = nullptr;
+        p.span1_frames = b.period;
+        p.vector_ok = 0;
+        if (w.at >= 0) {
+            const uint32_t into = uint32_t(uint64_t(w.at) % b.period);
+            p.span1 = ring_frame(b, s, uint64_t(w.at));
+            p.span1_frames = b.period - into;
+            p.span2 = into ? ring_frame(b, s, uint64_t(w.at) + p.span1_frames) : nullptr;
+            p.vector_ok = into == 0;
+            my_gap = w.gap > 0;
+        }
+        s_plan[threadIdx.x] = p;
+        s_gap[threadIdx.x] = w.at >= 0 ? w.gap : 0;
+        s_start[threadIdx.x] = w.start;
+    }
+    // One barrier hands the plans over and tells every thread whether any stream of the CTA has
+    // a forwarded-over region to silence (rare: late start, underrun).
+    if (__syncthreads_or(my_gap)) {
+        for (uint32_t j = 0; j < count; j++) {
+            long long gap = s_gap[j], start = s_start[j];
+            if (gap <= 0)
+                continue;
+            if (gap > (long long)b.ring) { // older than one lap: only the last lap is still in the ring
+                start += gap - (long long)b.ring;
+                gap = (long long)b.ring;
+            }
+            Pack<2> zero;
+            zero.w[0] = zero.w[1] = 0;
+            for (long long i = threadIdx.x; i < gap; i += blockDim.x)
+                st_stream<8>(ring_frame(b, s0 + j, uint64_t(start + i)), zero);
+        }
+        __syncthreads(); // a gap of a lap or more silences the slots the blocks are about to take
+    }
+
+    const bool pow2 = (nvec & (nvec - 1)) == 0;
+    const uint32_t log2v = 31 - __clz(nvec);
+    const uint32_t total = count * nvec; // vectors of this CTA
+    char *slot = b.capture_stage + s0 * b.period * 8;
+    char *cf = cf32 + s0 * b.period * 8;
+
+    for (uint32_t base = 0; base < total; base += 256 * U) {
+        Pack<4> cap[U], mid[U], out[U];
+        uint32_t jj[U], kk[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint32_t idx = base + u * 256 + threadIdx.x;
+            jj[u] = pow2 ? idx >> log2v : idx / nvec;
+            kk[u] = pow2 ? idx & (nvec - 1) : idx - jj[u] * nvec;
+            if (capture_in_slot) {
+                if (idx < total)
+                    cap[u] = ld_stream<16>(slot + size_t(idx) * 16);
+            } else {
+                const uint32_t j = idx < total ? jj[u] : 0;
+                const uint64_t first = uint64_t(s_plan[j].first);
+                const uint64_t z0 = sx_synth_frame(b.seed + s0 + j, first + 2 * uint64_t(kk[u]));
+                const uint64_t z1 = sx_synth_frame(b.seed + s0 + j, first + 2 * uint64_t(kk[u]) + 1);
+                cap[u].w[0] = uint32_t(z0), cap[u].w[1] = uint32_t(z0 >> 32);
+                cap[u].w[2] = uint32_t(z1), cap[u].w[3] = uint32_t(z1 >> 32);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint32_t idx = base + u * 256 + threadIdx.x;
+            RxCf32::apply<2>(cap[u], mid[u], 0.0f);
+            if (idx < total)
+                hook(mid[u], s0 + jj[u], 2 * kk[u]); // user DSP between RX and TX, identity by default
+            TxCf32::apply<2>(mid[u], out[u], b.thr2);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint32_t idx = base + u * 256 + threadIdx.x;
+            if (idx >= total)
+                continue;
+            if (!capture_in_slot)
+                st_stream<16>(slot + size_t(idx) * 16, cap[u]);
+            st_stream<16>(cf + size_t(idx) * 16, mid[u]);
+            const BankDirectPlan &p = s_plan[jj[u]];
+            if (p.vector_ok) {
+                st_stream<16>(p.span1 + size_t(kk[u]) * 16, out[u]);
+            } else if (p.span1) {
+                Pack<2> f0, f1;
+                f0.w[0] = out[u].w[0], f0.w[1] = out[u].w[1], f1.w[0] = out[u].w[2], f1.w[1] = out[u].w[3];
+                const uint32_t fr = 2 * kk[u];
+                st_stream<8>(fr < p.span1_frames ? p.span1 + size_t(fr) * 8 : p.span2 + size_t(fr - p.span1_frames) * 8, f0);
+                st_stream<8>(fr + 1 < p.span1_frames ? p.span1 + size_t(fr + 1) * 8 : p.span2 + size_t(fr + 1 - p.span1_frames) * 8, f1);
+            }
+        }
+    }
+}
+
+// The data side of the same schedule with the decisions taken beforehand by
+// bank_plan_repeat_kernel (one thread per stream, every stream of the bank side by side: the
+// decisions are a chain of dependent 64-bit divisions and double-precision operations, a few
+// microseconds of latency per stream however few lanes run it, so inside the data CTAs -- as in
+// bank_repeat_direct_kernel above -- they hold a whole CTA's registers and threads idle for
+// longer than its stores take).  CTA c takes vectors [c * 256 * U, (c + 1) * 256 * U) of the flat
+// capture and CF32 arrays; its first threads fetch the streams' first-frame counters and ring
+// offsets into shared memory while the others already have the capture loads in flight.
+template <int U, class Hook>
+__global__ void __launch_bounds__(256) bank_repeat_data_kernel(BankState b, char *cf32, bool capture_in_slot, Hook hook)
+{
+    // streams a CTA can touch: 256 * U vectors of at least two vectors per stream (period >= 4,
+    // checked by the host), plus one for a chunk that starts inside a stream
+    constexpr int kMaxStreams = 256 * U / 2 + 1;
+    __shared__ long long s_first[kMaxStreams], s_off[kMaxStreams];
+
+    const uint32_t nvec = b.period / 2;
+    const uint64_t total = uint64_t(b.nstreams) * nvec;
+    const uint64_t v0 = uint64_t(blockIdx.x) * (256 * U);
+    if (v0 >= total)
+        return;
+    const bool pow2 = (nvec & (nvec - 1)) == 0;
+    const uint32_t log2v = 31 - __clz(nvec);
+    const uint64_t s0 = pow2 ? v0 >> log2v : v0 / nvec;                       // first stream this CTA touches
+    const uint64_t vlast = v0 + 256 * U - 1 < total - 1 ? v0 + 256 * U - 1 : total - 1;
+    const uint32_t count = uint32_t((pow2 ? vlast >> log2v : vlast / nvec) - s0) + 1; // <= 256 * U / nvec + 1
+    pdl_wait(); // the decisions (and, before them, the previous iteration's samples) are in memory
+    for (uint32_t j = threadIdx.x; j < count; j += 256) {
+        s_first[j] = b.rx_first_frame[s0 + j];
+        s_off[j] = b.tx_ring_offset[s0 + j];
+    }
+    Pack<4> cap[U], mid[U], out[U];
+    if (capture_in_slot) {
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint64_t v = v0 + u * 256 + threadIdx.x;
+            if (v < total)
+                cap[u] = ld_stream<16>(b.capture_stage + v * 16);
+        }
+    }
+    __syncthreads();
+
+    // Which stream (relative to s0) a vector belongs to and where in its period, in 32-bit
+    // arithmetic: the CTA's vectors start r0 vectors into stream s0.
+    const uint32_t r0 = uint32_t(v0 - s0 * nvec);
+    uint32_t jj[U], kk[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const uint32_t local = r0 + u * 256 + threadIdx.x;
+        const uint32_t j = pow2 ? local >> log2v : local / nvec;
+        jj[u] = v0 + u * 256 + threadIdx.x < total ? j : 0;
+        kk[u] = pow2 ? local & (nvec - 1) : local - j * nvec;
+        if (!capture_in_slot) {
+            const uint64_t first = uint64_t(s_first[jj[u]]);
+            const uint64_t z0 = sx_synth_frame(b.seed + s0 + jj[u], first + 2 * uint64_t(kk[u]));
+            const uint64_t z1 = sx_synth_frame(b.seed + s0 + jj[u], first + 2 * uint64_t(kk[u]) + 1);
+            cap[u].w[0] = uint32_t(z0), cap[u].w[1] = uint32_t(z0 >> 32);
+            cap[u].w[2] = uint32_t(z1), cap[u].w[3] = uint32_t(z1 >> 32);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const uint64_t v = v0 + u * 256 + threadIdx.x;
+        RxCf32::apply<2>(cap[u], mid[u], 0.0f);
+        if (v < total)
+            hook(mid[u], s0 + jj[u], 2 * kk[u]); // user DSP between RX and TX, identity by default
+        TxCf32::apply<2>(mid[u], out[u], b.thr2);
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const uint64_t v = v0 + u * 256 + threadIdx.x;
+        if (v >= total)
+            continue;
+        if (!capture_in_slot)
+            st_stream<16>(b.capture_stage + v * 16, cap[u]);
+        st_stream<16>(cf32 + v * 16, mid[u]);
+        const long long off = s_off[jj[u]];
+        if (off < 0)
+            continue; // discarded as late
+        if ((off & 1) == 0) {
+            // the block starts on a period boundary of the ring: one contiguous, 16-byte aligned span
+            st_stream<16>(b.playback_ring + off + size_t(kk[u]) * 16, out[u]);
+        } else {
+            // it straddles two slices of the time-major ring: frame by frame (rare: a stream out of step)
+            const uint64_t at = uint64_t(b.tx_write_position[s0 + jj[u]]);
+            Pack<2> f0, f1;
+            f0.w[0] = out[u].w[0], f0.w[1] = out[u].w[1], f1.w[0] = out[u].w[2], f1.w[1] = out[u].w[3];
+            st_stream<8>(ring_frame(b, s0 + jj[u], at + 2 * uint64_t(kk[u])), f0);
+            st_stream<8>(ring_frame(b, s0 + jj[u], at + 2 * uint64_t(kk[u]) + 1), f1);
+        }
+    }
+}
+
+// Launches the two kernels of the plan + data schedule on `st`: decisions by one thread per
+// stream, then the samples, the second as a programmatic dependent of the first so that its
+// launch and the first CTAs' set-up run under the decisions instead of after them.
+// U = 16-byte vectors per thread (2 or 4).  Returns the CUDA error of the launches.
+template <int U, class Hook>
+inline cudaError_t launch_bank_repeat_planned(const BankState &b, char *cf32, long long rx_time_offset_ns, bool capture_in_slot,
+                                              cudaStream_t st, const Hook &hook, bool programmatic = true)
+{
+    bank_plan_repeat_kernel<<<(b.nstreams + 63) / 64, 64, 0, st>>>(b, cf32, rx_time_offset_ns);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess)
+        return e;
+    const uint64_t vectors = uint64_t(b.nstreams) * (b.period / 2);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(unsigned((vectors + 256 * U - 1) / (256 * U)));
+    cfg.blockDim = dim3(256);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = programmatic ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, bank_repeat_data_kernel<U, Hook>, b, cf32, capture_in_slot, hook);
 }
 
 __global__ void bank_advance_kernel(BankState b, long long frames)

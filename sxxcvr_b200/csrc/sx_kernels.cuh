@@ -664,6 +664,36 @@ __global__ void batch_slice_kernel(const BlockDesc *__restrict__ blocks, uint32_
     }
 }
 
+// Mid-size and large blocks, one chunk per CTA: CTA i takes chunk (i mod chunks_per_block) of
+// block (i / chunks_per_block), so that the hardware hands the CTAs out block after block, chunk
+// after chunk -- the order the blocks usually lie in memory.  chunks_per_block is sized for the
+// longest block; CTAs past a shorter block's end leave at once, and the last CTA of a block takes
+// all that is left of it.  A chunk is four accesses per thread (all four loads in flight before
+// the first store, see convert_span).
+template <class Op> __host__ __device__ constexpr uint64_t batch_direct_chunk()
+{
+    constexpr int narrow = Op::kSrcWords < Op::kDstWords ? Op::kSrcWords : Op::kDstWords;
+    return uint64_t(256) * 4 * (16 / (narrow * 4));
+}
+template <class Op>
+__global__ void __launch_bounds__(256) batch_direct_kernel(const BlockDesc *__restrict__ blocks, uint32_t nblocks,
+                                                           uint32_t chunks_per_block)
+{
+    const uint32_t b = blockIdx.x / chunks_per_block;
+    if (b >= nblocks)
+        return;
+    const BlockDesc d = blocks[b];
+    const uint32_t c = blockIdx.x - b * chunks_per_block;
+    const uint64_t lo = uint64_t(c) * batch_direct_chunk<Op>();
+    if (lo >= d.length)
+        return;
+    // The last CTA of a block takes whatever is left, so that a block longer than the caller said
+    // (max_length) is still converted whole, only slowly.
+    const uint64_t hi = (c + 1 < chunks_per_block && lo + batch_direct_chunk<Op>() < d.length) ? lo + batch_direct_chunk<Op>()
+                                                                                              : d.length;
+    convert_span<Op>(d, lo, hi, threadIdx.x, 256);
+}
+
 // ---------------------------------------------------------------------------------------
 // Batched blocks on the bulk-async schedule: many mid-size blocks (BASELINE config 5's small
 // end: 1 MiB - 64 MiB each) in ONE launch at the large-block kernel's throughput.

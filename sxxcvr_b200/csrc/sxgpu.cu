@@ -88,7 +88,7 @@ struct sxgpu_ctx {
     cudaStream_t stream = nullptr;
 
     // options
-    int64_t rx_variant = 0, tx_variant = 0; // 0 auto, 1 vec128, 2 vec256, 3 bulk
+    int64_t rx_variant = 0, tx_variant = 0; // 0 auto (= 4), 1 vec128, 2 vec256, 3 bulk (persistent grids), 4 one tile per CTA
     int64_t unroll = 0;                     // 0 auto (4), else 2/4/8
     int64_t block = 0;                      // 0 auto, threads per CTA
     int64_t ctas_per_sm = 0;                // 0 auto
@@ -107,8 +107,9 @@ struct sxgpu_ctx {
     int64_t zero_copy_max_frames = 1 << 18; // measured crossover, profiles/r01_sweep_host_path.json
     int64_t resident_max_frames = 0;        // > 0: blocks up to this size go to the resident converter
     int64_t zero_copy_variant = 1;          // schedule of the zero-copy kernel (1 vec128, 2 vec256, 3 bulk)
-    int64_t batch_variant = 0;              // blocks above 4096 frames: 0 auto (= bulk-async tiles), 1 = slices of CTAs on vector accesses
-    int64_t loopback_variant = 0;           // 0 auto (= bulk-async), 1 = vector accesses
+    int64_t batch_variant = 0;              // blocks above 4096 frames: 0 auto, 1 = slices of CTAs on vector accesses, 2 = one chunk per CTA, 3 = bulk-async tiles
+    int64_t loopback_variant = 0;           // 0 auto (= 2), 1 = vector accesses on a persistent grid, 2 = one tile per CTA, 3 = bulk-async
+    int64_t bank_pdl = 1;                   // the plan + data schedule launches its data kernel as a programmatic dependent
     int64_t bank_repeat_variant = 0;        // 0 auto; 1, 2, 4, 8 = K streams per warp round; 100 = 32 per CTA round
     int64_t bounce_threads = 0;             // threads copying a pageable caller's buffer: 0 auto, 1 = the caller alone
     int64_t numa_local_alloc = 1;           // place pinned host memory on the GPU's NUMA node
@@ -471,8 +472,31 @@ int launch_convert(sxgpu_ctx *ctx, const void *src_v, void *dst_v, uint64_t tota
     if (reinterpret_cast<uintptr_t>(src) % 4 || reinterpret_cast<uintptr_t>(dst) % 4)
         return ctx->invalid("sample buffers must be at least 4-byte aligned");
 
+    // Default (measured, profiles/r02_summary.md section 2): one tile per CTA, CTAs handed out in
+    // index order by the hardware.  The addresses in flight then form one compact window that
+    // moves through the block, which is what HBM wants to see: 6.9 TB/s against 6.5-6.6 for every
+    // persistent schedule (grid-stride vector kernels and the bulk-async ring alike), whose CTAs
+    // drift apart as they go.
     if (variant == 0)
-        variant = 3; // measured default (profiles/r01_summary.md section 4): bulk-async staging wins
+        variant = 4;
+    if (variant == 4) {
+        constexpr bool narrow = Op::kSrcWords != Op::kDstWords; // 12 B/frame: 256 bits on the wide side
+        Plan p = plan_access<Op>(src, dst, total, narrow ? 4 : 2);
+        if (p.fr >= 2 && total >= p.head + uint64_t(p.fr)) {
+            // two accesses per thread in flight; four below 2^21 frames, where fewer, fatter CTAs
+            // ramp up faster than more, thinner ones (r02 sweep: 2.0 against 1.4 TB/s at 2^19 frames)
+            constexpr int block = 256;
+            const int unroll = total < (uint64_t(1) << 21) ? 4 : 2;
+            StreamArgs a = {src, dst, total, p.head, (total - p.head) / uint64_t(p.fr), thr2};
+            StreamKernel k = stream_kernel<Op>(p.fr, unroll, block);
+            uint64_t tiles = (a.nvec + uint64_t(block) * unroll - 1) / (uint64_t(block) * unroll);
+            k<<<unsigned(std::min<uint64_t>(tiles, 0x7fffffffu)), block, 0, st>>>(a);
+            SX_CUDA(ctx, cudaGetLastError());
+            ctx->launches++;
+            return SXGPU_OK;
+        }
+        variant = 3; // the two sides are out of step (or too short): the skewed bulk kernel, then the word kernel
+    }
     if (variant == 3) {
         bool handled = false;
         SX_TRY(launch_bulk<Op>(ctx, src, dst, total, thr2, st, &handled));
@@ -1140,12 +1164,34 @@ int convert_batch(sxgpu_ctx *ctx, const sxgpu_block *blocks, uint32_t nblocks, i
     }
 
     const int sms = ctx->prop.multiProcessorCount;
+    // One chunk per CTA, CTAs in block-then-chunk order (batch_direct_kernel): the schedule of the
+    // single-block default.  Every block gets the chunk count of the longest one and the CTAs past
+    // a shorter block's end leave at once, so it is taken when that padding is small: host lists
+    // are checked exactly; device-resident lists are taken at the caller's word (max_length) up to
+    // a grid that bounds what a ragged list could waste.
+    constexpr uint64_t kChunk = batch_direct_chunk<Op>();
+    const uint64_t chunks_per_block = (uint64_t(max_length) + kChunk - 1) / kChunk;
+    bool batch_direct = false;
+    if (max_length > 4096 && (ctx->batch_variant == 0 || ctx->batch_variant == 2)) {
+        const uint64_t grid = uint64_t(nblocks) * chunks_per_block;
+        if (staged) {
+            uint64_t used = 0;
+            for (uint32_t i = 0; i < nblocks; i++)
+                used += (blocks[i].length + kChunk - 1) / kChunk;
+            batch_direct = grid <= 0x7fffffffu && (ctx->batch_variant == 2 || used * 4 >= grid * 3);
+        } else {
+            batch_direct = grid <= (ctx->batch_variant == 2 ? 0x7fffffffu : (uint64_t(1) << 21));
+        }
+    }
     if (max_length <= 4096) {
         // One warp per block: a 256-frame period is 128 x 16 bytes = 4 accesses per lane.
         int block = 256, warps = block / 32;
         uint64_t ctas = (uint64_t(nblocks) + warps - 1) / warps;
         int grid = int(std::min<uint64_t>(ctas, uint64_t(sms) * 8));
         batch_warp_kernel<Op><<<grid, block, 0, st>>>(d_blocks, nblocks);
+    } else if (batch_direct) {
+        batch_direct_kernel<Op><<<unsigned(uint64_t(nblocks) * chunks_per_block), 256, 0, st>>>(d_blocks, nblocks,
+                                                                                            uint32_t(chunks_per_block));
     } else if (ctx->batch_variant == 1) {
         int block = 256;
         uint64_t slices = (max_length + 16383) / 16384; // ~128 KiB of frames per CTA pass
@@ -1219,6 +1265,7 @@ int64_t *option_slot(sxgpu_ctx *ctx, const char *key)
         {"resident_max_frames", &ctx->resident_max_frames},
         {"zero_copy_variant", &ctx->zero_copy_variant},
         {"bank_repeat_variant", &ctx->bank_repeat_variant},
+        {"bank_pdl", &ctx->bank_pdl},
         {"batch_variant", &ctx->batch_variant},
         {"loopback_variant", &ctx->loopback_variant},
         {"bounce_threads", &ctx->bounce_threads},
@@ -1506,7 +1553,17 @@ int sxgpu_convert_loopback(sxgpu_ctx *ctx, const void *d_i2s_in, void *d_cf32, v
         return ctx->invalid("loopback buffers must be 16-byte aligned");
     SX_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
-    if (ctx->loopback_variant != 1 && length >= 2) {
+    if (ctx->loopback_variant == 0 || ctx->loopback_variant == 2) {
+        // One tile per CTA, handed out in index order by the hardware (see launch_convert): two
+        // 16-byte vectors per thread in flight, 6.8 TB/s of 24 B/frame at 2^27 frames.
+        LoopbackArgs a = {static_cast<const char *>(d_i2s_in), static_cast<char *>(d_cf32),
+                          static_cast<char *>(d_i2s_out), length / 2, length, tx_threshold2};
+        constexpr int block = 256, U = 2;
+        uint64_t tiles = std::max<uint64_t>(1, (a.nvec + uint64_t(block) * U - 1) / (uint64_t(block) * U));
+        loopback_kernel<U><<<unsigned(std::min<uint64_t>(tiles, 0x7fffffffu)), block, 0, st>>>(a);
+        SX_CUDA(ctx, cudaGetLastError());
+        ctx->launches++;
+    } else if (ctx->loopback_variant == 3 && length >= 2) {
         // Bulk-async schedule over the even part; an odd last frame goes through the vector kernel.
         const uint64_t even = uint64_t(length) & ~uint64_t(1);
         BulkLoopbackArgs b = {static_cast<const char *>(d_i2s_in), static_cast<char *>(d_cf32),
@@ -1634,7 +1691,7 @@ int sxgpu_bank_create(sxgpu_ctx *ctx, const sxgpu_bank_config *config, sxgpu_ban
     size_t bytes = 0;
     bytes += 3 * (n * sizeof(long long) + 256);                       // clock, rx/tx position
     bytes += 3 * (n * sizeof(int) + 256) + (n * sizeof(long long) + 256); // results
-    bytes += 4 * (n * sizeof(long long) + 256) + (n * sizeof(BlockDesc) + 256); // plans
+    bytes += 5 * (n * sizeof(long long) + 256) + (n * sizeof(BlockDesc) + 256); // plans
     bytes += n * geo.period * 8 + 256;                                // capture staging
     bytes += n * geo.buffer * 8 + 256;                                // playback rings
     cudaError_t e = cudaMalloc(&bank->arena, bytes);
@@ -1663,6 +1720,7 @@ int sxgpu_bank_create(sxgpu_ctx *ctx, const sxgpu_bank_config *config, sxgpu_ban
     b.tx_write_position = carve<long long>(cur, n);
     b.tx_gap_start = carve<long long>(cur, n);
     b.tx_gap_length = carve<long long>(cur, n);
+    b.tx_ring_offset = carve<long long>(cur, n);
     b.rx_blocks = carve<BlockDesc>(cur, n);
     b.capture_stage = carve<char>(cur, n * geo.period * 8);
     b.playback_ring = carve<char>(cur, n * geo.buffer * 8);
@@ -1791,8 +1849,10 @@ int sxgpu_bank_repeat(sxgpu_bank *bank, void *d_cf32, long long rx_time_offset_n
     if (k == 0) {
         if (b.nstreams <= 2048)
             k = reg_ok ? 201 : 1;
-        else
+        else if (b.nstreams < 32768 || !reg_ok || b.period < 4)
             k = b.nstreams <= 8192 ? 2 : b.nstreams <= 32768 ? 4 : 100;
+        else
+            k = ext ? 604 : 600; // decisions first, then the samples by hardware-scheduled CTAs
     }
     if (k >= 200 && !reg_ok)
         return ctx->invalid("the register schedules need an even period and a 16-byte aligned CF32 buffer");
@@ -1820,6 +1880,28 @@ int sxgpu_bank_repeat(sxgpu_bank *bank, void *d_cf32, long long rx_time_offset_n
             go(bank_repeat_group_reg_kernel<2, 4, IdentityHook>);
         break;
     }
+    case 500:   // one launch, hardware-scheduled CTAs: a CTA plans its streams, then stores only (four vectors per thread)
+    case 502: { // ... two vectors per thread
+        if (k == 500) {
+            auto kernel = bank_repeat_direct_kernel<4, IdentityHook>;
+            const uint32_t g = bank_direct_group(b.period, 4);
+            kernel<<<(b.nstreams + g - 1) / g, 256, 0, st>>>(b, cf, rx_time_offset_ns, ext, IdentityHook());
+        } else {
+            auto kernel = bank_repeat_direct_kernel<2, IdentityHook>;
+            const uint32_t g = bank_direct_group(b.period, 2);
+            kernel<<<(b.nstreams + g - 1) / g, 256, 0, st>>>(b, cf, rx_time_offset_ns, ext, IdentityHook());
+        }
+        break;
+    }
+    case 600:   // decisions by a thread-per-stream kernel, then the samples by hardware-scheduled CTAs (two vectors per thread)
+    case 604: { // ... four vectors per thread
+        if (b.period < 4)
+            return ctx->invalid("the direct schedules need a period of at least four frames");
+        SX_CUDA(ctx, k == 600 ? launch_bank_repeat_planned<2>(b, cf, rx_time_offset_ns, ext, st, IdentityHook(), ctx->bank_pdl != 0)
+                              : launch_bank_repeat_planned<4>(b, cf, rx_time_offset_ns, ext, st, IdentityHook(), ctx->bank_pdl != 0));
+        ctx->launches++;
+        break;
+    }
     case 400: { // decisions by a thread-per-stream kernel, samples on the bulk-async schedule
         if (!bulk_ok)
             return ctx->invalid("the bulk schedule needs an even period that divides 2048, at least 64, and a 16-byte aligned CF32 buffer");
@@ -1840,7 +1922,7 @@ int sxgpu_bank_repeat(sxgpu_bank *bank, void *d_cf32, long long rx_time_offset_n
         }
         break;
     }
-    default: return ctx->invalid("bank_repeat_variant must be 0 (auto), 1, 2, 4, 8, 100, 201, 202, 204, 300, 302, 303 or 400");
+    default: return ctx->invalid("bank_repeat_variant must be 0 (auto), 1, 2, 4, 8, 100, 201, 202, 204, 300, 302, 303, 400, 500, 502, 600 or 604");
     }
     SX_CUDA(ctx, cudaGetLastError());
     ctx->launches += 1;

@@ -40,7 +40,7 @@ def gpu_tx(ctx, floats: np.ndarray, thr2: float, **opts) -> np.ndarray:
     return host(dst)
 
 
-VARIANTS = [dict(rx_variant=1, tx_variant=1), dict(rx_variant=2, tx_variant=2), dict(rx_variant=3, tx_variant=3),
+VARIANTS = [dict(rx_variant=4, tx_variant=4), dict(rx_variant=1, tx_variant=1), dict(rx_variant=2, tx_variant=2), dict(rx_variant=3, tx_variant=3),
             dict(rx_variant=3, tx_variant=3, bulk_tile=1024, bulk_stages=4),
             dict(rx_variant=2, tx_variant=2, unroll=8, block=512), dict(rx_variant=1, tx_variant=1, unroll=2)]
 RESET = dict(rx_variant=0, tx_variant=0, unroll=0, block=0, bulk_tile=0, bulk_stages=0, ctas_per_sm=0)
@@ -139,7 +139,7 @@ def test_tx_survey_kats(ctx):
 
 
 @pytest.mark.parametrize("src_off,dst_off", [(0, 0), (1, 1), (1, 0), (0, 1), (3, 3), (3, 2), (2, 1), (5, 7)])
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])
 def test_frame_offsets_and_misaligned_views(ctx, oracle, src_off, dst_off, variant):
     """Offsets are in frames, as in the reference (SoapySX.cpp:105-106, :118-119); an odd frame
     offset leaves only 8-byte alignment and different src/dest offsets defeat wide vectors."""
@@ -257,7 +257,7 @@ def test_cs16_extensions_match_their_specification(ctx, oracle):
     """EXTENSION: no reference implementation exists (SoapySX.cpp:752-753); parity is against
     our own scalar specification in oracle/sx_oracle.c."""
     for n in (1, 2, 3, 4, 5, 4096, 100003):
-        for variant in (1, 2, 3):
+        for variant in (1, 2, 3, 4):
             ctx.set_option("rx_variant", variant)
             ctx.set_option("tx_variant", variant)
             words = sxtest.rx_uniform(n, seed=n)
@@ -279,7 +279,7 @@ def test_cs16_extensions_match_their_specification(ctx, oracle):
 def test_s16_frame_extension_matches_its_specification(ctx, oracle):
     """EXTENSION: 16-bit I2S slots; no reference implementation (SoapySX.cpp:200-207, :474)."""
     for n in (1, 2, 3, 4, 7, 4096, 100003, (1 << 21) + 2):
-        for variant in (1, 2, 3):
+        for variant in (1, 2, 3, 4):
             ctx.set_option("rx_variant", variant)
             ctx.set_option("tx_variant", variant)
             rng = np.random.default_rng(n)

@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 
 torch = pytest.importorskip("torch")
 
-OPTIONS = dict(rx_variant=(0, 1, 2, 3), tx_variant=(0, 1, 2, 3), unroll=(0, 2, 4, 8), block=(0, 256, 512),
+OPTIONS = dict(rx_variant=(0, 1, 2, 3, 4), tx_variant=(0, 1, 2, 3, 4), unroll=(0, 2, 4, 8), block=(0, 256, 512),
                ctas_per_sm=(0, 1, 3), bulk_tile=(0, 512, 1024, 2048), bulk_stages=(0, 4))
 
 

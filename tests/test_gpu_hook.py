@@ -59,7 +59,7 @@ def ulp_distance(a, b):
     return np.abs(a.view(np.int32).astype(np.int64) - b.view(np.int32).astype(np.int64))
 
 
-@pytest.mark.parametrize("S,P", [(5, 256), (2100, 256), (17000, 64)])
+@pytest.mark.parametrize("S,P", [(5, 256), (2100, 256), (17000, 64), (32768 + 3, 64)])
 @pytest.mark.parametrize("split", [False, True])
 def test_clip_gain_hook_inside_the_fused_iteration(ctx, oracle, hooklib, S, P, split):
     from sxxcvr_b200 import Bank

@@ -125,7 +125,7 @@ def make_blocks(src_ptr, dst_ptr, lengths, offsets, thr):
     return [Block(src_ptr + 8 * o, dst_ptr + 8 * o, n, t, 0) for n, o, t in zip(lengths, offsets, thr)]
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 @pytest.mark.parametrize("shape", ["64x1MiB", "16x4MiB", "4x16MiB", "ragged", "misaligned", "device_list"])
 def test_batched_mid_size_blocks(ctx, oracle, variant, shape):
     rng = np.random.default_rng(11)
@@ -202,7 +202,7 @@ def test_batched_blocks_in_place_and_back_to_back(ctx, oracle):
 # ---------------------------------------------------------------------------------------------
 # Fused loopback on the bulk-async schedule
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 @pytest.mark.parametrize("n", [1, 2, 3, 2048, 2049, 4096 * 148 + 2, (1 << 22) + 1])
 def test_loopback_schedules(ctx, oracle, variant, n):
     ctx.set_option("loopback_variant", variant)

@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+T=d2
+timeout 1200 python -m pytest tests/test_gpu_bank.py tests/test_gpu_hook.py -m gpu -q -x -p no:cacheprovider > gpurun_out/${T}_pytest.log 2>&1
+echo "pytest exit $?" >> gpurun_out/${T}_pytest.log; tail -8 gpurun_out/${T}_pytest.log
+timeout 900 python tools/sweep_direct.py --only bank --tag ${T}_sweep_direct > gpurun_out/${T}_sweep.log 2>&1; echo "sweep exit $?"; tail -12 gpurun_out/${T}_sweep.log
