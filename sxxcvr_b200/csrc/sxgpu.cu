@@ -109,6 +109,7 @@ struct sxgpu_ctx {
     int64_t zero_copy_variant = 1;          // schedule of the zero-copy kernel (1 vec128, 2 vec256, 3 bulk)
     int64_t batch_variant = 0;              // blocks above 4096 frames: 0 auto, 1 = slices of CTAs on vector accesses, 2 = one chunk per CTA, 3 = bulk-async tiles
     int64_t loopback_variant = 0;           // 0 auto (= 2), 1 = vector accesses on a persistent grid, 2 = one tile per CTA, 3 = bulk-async
+    int64_t warp_ctas_per_sm = 0;           // grid cap of the warp-per-block / warp-per-stream kernels: N CTAs per SM (persistent), 0 = one CTA per eight blocks
     int64_t bank_pdl = 1;                   // the plan + data schedule launches its data kernel as a programmatic dependent
     int64_t bank_repeat_variant = 0;        // 0 auto; 1, 2, 4, 8 = K streams per warp round; 100 = 32 per CTA round
     int64_t bounce_threads = 0;             // threads copying a pageable caller's buffer: 0 auto, 1 = the caller alone
@@ -1187,7 +1188,8 @@ int convert_batch(sxgpu_ctx *ctx, const sxgpu_block *blocks, uint32_t nblocks, i
         // One warp per block: a 256-frame period is 128 x 16 bytes = 4 accesses per lane.
         int block = 256, warps = block / 32;
         uint64_t ctas = (uint64_t(nblocks) + warps - 1) / warps;
-        int grid = int(std::min<uint64_t>(ctas, uint64_t(sms) * 8));
+        int grid = ctx->warp_ctas_per_sm <= 0 ? int(std::min<uint64_t>(ctas, 0x7fffffffu))
+                                              : int(std::min<uint64_t>(ctas, uint64_t(sms) * uint64_t(ctx->warp_ctas_per_sm)));
         batch_warp_kernel<Op><<<grid, block, 0, st>>>(d_blocks, nblocks);
     } else if (batch_direct) {
         batch_direct_kernel<Op><<<unsigned(uint64_t(nblocks) * chunks_per_block), 256, 0, st>>>(d_blocks, nblocks,
@@ -1266,6 +1268,7 @@ int64_t *option_slot(sxgpu_ctx *ctx, const char *key)
         {"zero_copy_variant", &ctx->zero_copy_variant},
         {"bank_repeat_variant", &ctx->bank_repeat_variant},
         {"bank_pdl", &ctx->bank_pdl},
+        {"warp_ctas_per_sm", &ctx->warp_ctas_per_sm},
         {"batch_variant", &ctx->batch_variant},
         {"loopback_variant", &ctx->loopback_variant},
         {"bounce_threads", &ctx->bounce_threads},
@@ -1648,7 +1651,9 @@ int per_stream_grid(uint32_t nstreams, int block)
 int per_warp_grid(const sxgpu_ctx *ctx, uint32_t nstreams, int block)
 {
     uint64_t ctas = (uint64_t(nstreams) + block / 32 - 1) / (block / 32);
-    return int(std::min<uint64_t>(ctas, uint64_t(ctx->prop.multiProcessorCount) * 8));
+    if (ctx->warp_ctas_per_sm <= 0) // one CTA per eight streams, handed out in order by the hardware
+        return int(std::min<uint64_t>(ctas, 0x7fffffffu));
+    return int(std::min<uint64_t>(ctas, uint64_t(ctx->prop.multiProcessorCount) * uint64_t(ctx->warp_ctas_per_sm)));
 }
 
 template <class T>

@@ -37,7 +37,7 @@ if which in ("all", "loopback"):
         ctx.convert_loopback(src.data_ptr(), cf.data_ptr(), dst.data_ptr(), n, 1e-6, st)
 if which in ("all", "bank"):
     S, P = 65536, 256
-    for variant in (100, 300):
+    for variant in (0, 100):
         ctx.set_option("bank_repeat_variant", variant)
         with Bank(ctx, S, P, 75000.0, 0.0, 7) as bank:
             for _ in range(3):

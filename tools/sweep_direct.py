@@ -196,6 +196,37 @@ def sweep_bank(ctx, side, out):
     out["bank_repeat"] = rows
 
 
+def sweep_warp(ctx, side, out):
+    """Warp-per-stream kernels (the bank's separate read / write calls, batches of period-sized
+    blocks): persistent grid of 8 CTAs per SM against one CTA per eight streams."""
+    st = side.cuda_stream
+    P, rate = 256, 75000.0
+    lat = int(round(768 * 1e9 / rate))
+    rows = []
+    for S in (4096, 16384, 65536):
+        cf = torch.empty(S * P * 2, dtype=torch.float32, device="cuda")
+        src = torch.empty(S * P * 2, dtype=torch.int32, device="cuda")
+        ctx.synth_frames(src.data_ptr(), 0, S * P, 1, st)
+        blocks = [Block(src.data_ptr() + 8 * P * b, cf.data_ptr() + 8 * P * b, P, 0.0, 0) for b in range(S)]
+        d_list = torch.from_numpy(np.frombuffer(bytes((Block * S)(*blocks)), dtype=np.uint8).copy()).cuda()
+        row = {"streams": S}
+        for cap in (8, 4, 0):
+            ctx.set_option("warp_ctas_per_sm", cap)
+            with Bank(ctx, S, P, rate, 0.0, 7) as bank:
+                def two():
+                    bank.read(cf.data_ptr(), st)
+                    bank.write(cf.data_ptr(), 4, None, lat, st)
+                row[f"two_calls_cap{cap}_us"] = round(timed(two, side, 200, warm=5) * 1e6, 2)
+            sec = timed(lambda: ctx.convert_batch("rx", d_list.data_ptr(), on_device=True, max_length=P, stream=st, nblocks=S),
+                        side, 200, warm=5)
+            row[f"batch_rx_cap{cap}_us"] = round(sec * 1e6, 2)
+            row[f"batch_rx_cap{cap}_gbs"] = round(16 * S * P / sec / 1e9, 1)
+        ctx.set_option("warp_ctas_per_sm", 0)
+        rows.append(row)
+        print(json.dumps(row), flush=True)
+    out["warp_per_stream"] = rows
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="convert,ext,loopback,batched,bank")
@@ -207,7 +238,7 @@ def main():
     side = torch.cuda.Stream()
     torch.cuda.set_stream(side)
     for name, fn in (("convert", sweep_convert), ("ext", sweep_ext), ("loopback", sweep_loopback),
-                     ("batched", sweep_batched), ("bank", sweep_bank)):
+                     ("batched", sweep_batched), ("bank", sweep_bank), ("warp", sweep_warp)):
         if name in only:
             fn(ctx, side, out)
             torch.cuda.empty_cache()
