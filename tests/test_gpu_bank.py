@@ -383,3 +383,44 @@ def test_repeat_with_blocks_that_straddle_ring_slices(ctx, variant, latency_fram
         else:                       # a block timed before the end of its own read is late: dropped whole, every time
             assert (txp == 0).all() and (rxp == 300 * P).all()
     ctx.set_option("bank_repeat_variant", 0)
+
+
+@pytest.mark.parametrize("cap,pdl", [(0, 1), (8, 1), (0, 0)])
+def test_large_bank_default_schedule_and_grid_options(ctx, oracle, cap, pdl):
+    """The default schedule of a large bank (decisions by one kernel, samples by the next, launched
+    as its programmatic dependent) against the two separate calls, with the warp-per-stream kernels
+    of those calls on a persistent grid (cap 8) and on one CTA per eight streams (cap 0)."""
+    from sxxcvr_b200 import Bank
+    S, P, rate = 32768 + 37, 64, 75000.0
+    lat = int(round(768 * 1e9 / rate))
+    ctx.set_option("warp_ctas_per_sm", cap)
+    ctx.set_option("bank_pdl", pdl)
+    ctx.set_option("bank_repeat_variant", 0)
+    try:
+        with Bank(ctx, S, P, rate, 1.0e-6, 5) as two_calls, Bank(ctx, S, P, rate, 1.0e-6, 5) as fused:
+            cf_a = torch.zeros(S * P * 2, dtype=torch.float32, device="cuda")
+            cf_b = torch.zeros_like(cf_a)
+            for it, adv in enumerate((0, 0, 70000, 0, 13, 0)):   # an overrun and an out-of-step block on the way
+                if adv:
+                    two_calls.advance(adv)
+                    fused.advance(adv)
+                two_calls.read(cf_a.data_ptr())
+                two_calls.write(cf_a.data_ptr(), HAS_TIME, None, lat)
+                fused.repeat(cf_b.data_ptr(), lat)
+                assert torch.equal(cf_a.view(torch.int32), cf_b.view(torch.int32)), it
+                for x, y in zip(two_calls.positions(), fused.positions()):
+                    assert np.array_equal(x, y), it
+                for x, y in zip(two_calls.last_read(), fused.last_read()):
+                    assert np.array_equal(x, y), it
+                assert np.array_equal(two_calls.last_write(), fused.last_write()), it
+                _, _, txp = fused.positions()
+                for s in (0, 1, 31, 32, 4095, 32767, 32768, S - 1):
+                    end = int(txp[s])
+                    start = max(0, end - 4 * P)
+                    assert np.array_equal(two_calls.playback(s, start, end - start), fused.playback(s, start, end - start)), (it, s)
+            frames = sxtest.synth_frames(oracle, int(fused.positions()[1][S - 1]) - P, P, seed=5 + S - 1)
+            assert np.array_equal(cf_b.view(torch.int32).cpu().numpy().reshape(S, 2 * P)[S - 1].view(np.uint32),
+                                  sxtest.oracle_rx(oracle, frames).view(np.uint32))
+    finally:
+        ctx.set_option("warp_ctas_per_sm", 0)
+        ctx.set_option("bank_pdl", 1)

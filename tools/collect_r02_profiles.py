@@ -12,16 +12,16 @@ ROOT = Path(__file__).resolve().parent.parent
 OUT, PROF = ROOT / "gpurun_out", ROOT / "profiles"
 
 COPIES = {  # profiles name -> candidates under gpurun_out (first that exists wins)
-    "r02_bench_n1.json": ["f1_bench.json"],
-    "r02_bench_n1_steps20.json": ["f1_bench_steps20.json"],
-    "r02_bench_reference_arm.json": ["f1_bench_ref.json"],
-    "r02_bench_sweep.json": ["f1_bench_sweep.json"],
-    "r02_bench_group.json": ["f1_bench_group.json"],
-    "r02_bench_single_process.json": ["f1_bench_single.json"],
-    "r02_bench_bank_fused.json": ["f1_bench_bank_fused.json"],
-    "r02_bench_bank_fused_graph.json": ["f1_bench_bank_fused_graph.json"],
-    "r02_bench_bank_fused_graph_external.json": ["f1_bench_bank_fused_graph_external.json"],
-    "r02_bench_bank_two_calls.json": ["f1_bench_bank_two_calls.json"],
+    "r02_bench_n1.json": ["f2_bench.json"],
+    "r02_bench_n1_steps20.json": ["f2_bench_steps20.json"],
+    "r02_bench_reference_arm.json": ["f2_bench_ref.json"],
+    "r02_bench_sweep.json": ["f2_bench_sweep.json"],
+    "r02_bench_group.json": ["f2_bench_group.json"],
+    "r02_bench_single_process.json": ["f2_bench_single.json"],
+    "r02_bench_bank_fused.json": ["f2_bench_bank_fused.json"],
+    "r02_bench_bank_fused_graph.json": ["f2_bench_bank_fused_graph.json"],
+    "r02_bench_bank_fused_graph_external.json": ["f2_bench_bank_fused_graph_external.json"],
+    "r02_bench_bank_two_calls.json": ["f2_bench_bank_two_calls.json"],
     "r02_bench_n2.json": ["m2_bench.json"],
     "r02_bench_n2_single_process.json": ["m2_bench_single.json"],
     "r02_bench_n2_reference_arm.json": ["m2_bench_ref.json"],
@@ -30,17 +30,17 @@ COPIES = {  # profiles name -> candidates under gpurun_out (first that exists wi
     "r02_bench_n8_single_process.json": ["m8_bench_single.json"],
     "r02_bench_n8_reference_arm.json": ["m8_bench_ref.json"],
     "r02_bench_n8_sweep.json": ["m8_bench_sweep.json"],
-    "r02_launches.csv": ["f1_launches.csv"],
-    "r02_sweep_host_path_and_plugin_pairs.json": ["f1_sweep_host_plugin.json", "s3_sweep.json"],
-    "r02_sweep_bank_and_extensions.json": ["f1_sweep_bank_ext.json"],
+    "r02_launches.csv": ["f2_launches.csv"],
+    "r02_sweep_host_path_and_plugin_pairs.json": ["f2_sweep_host_plugin.json", "s3_sweep.json"],
+    "r02_sweep_direct_against_persistent.json": ["f2_sweep_direct.json"],
     "r02_sweep_batched_loopback.json": ["s4_sweep.json"],
     "r02_sweep_pipeline_modes.json": ["s3_sweep.json"],
     "r02_probe_batch_per_call.log": ["s4_probe_batch.log"],
     "r02_probe_batch_with_default_mempool.log": ["probe_batch.log"],
     "r02_probe_batch_with_default_mempool_ncu.csv": ["probe_batch_ncu.csv"],
-    "r02_sanitizer_memcheck.log": ["f1_sanitizer_memcheck.log"],
-    "r02_sanitizer_racecheck.log": ["f1_sanitizer_racecheck.log"],
-    "r02_final_gpu_pytest.log": ["f1_pytest.log"],
+    "r02_sanitizer_memcheck.log": ["f2_sanitizer_memcheck.log"],
+    "r02_sanitizer_racecheck.log": ["f2_sanitizer_racecheck.log"],
+    "r02_final_gpu_pytest.log": ["f2_pytest.log"],
 }
 
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__bytes.sum.per_second",
@@ -73,7 +73,7 @@ def main():
         else:
             print("missing:", srcs, file=sys.stderr)
     table, traffic = [], {}
-    for rep in sorted(list(OUT.glob("f1_ncu_*.ncu-rep")) + list(OUT.glob("s9a_ncu_*.ncu-rep"))):
+    for rep in sorted(OUT.glob("f2_ncu_*.ncu-rep")):
         rows, units = raw_rows(rep)
         seen = {}
         for d in rows:
@@ -81,6 +81,28 @@ def main():
             seen[name] = seen.get(name, 0) + 1
             if seen[name] > 2:
                 continue
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            t_scale = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "usecond": 1.0, "nsecond": 1e-3, "msecond": 1e3}
+            try:
+                nbytes = sum(float(d[k]) * scale[units[k]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+                us = float(d["gpu__time_duration.sum"]) * t_scale[units["gpu__time_duration.sum"]]
+                key = None
+                if "stream_convert_kernel<sx::RxCf32" in name or "stream_convert_kernel<RxCf32" in name:
+                    key = "rx"
+                elif "stream_convert_kernel<sx::TxCf32" in name or "stream_convert_kernel<TxCf32" in name:
+                    key = "tx"
+                elif "batch_direct_kernel" in name:
+                    key = "batch"
+                elif "loopback_kernel" in name and "bulk" not in name:
+                    key = "loopback"
+                elif "bank_repeat_data_kernel" in name:
+                    key = "bank_data"
+                elif "bank_plan_repeat_kernel" in name:
+                    key = "bank_plan"
+                if key and key not in traffic:
+                    traffic[key] = {"bytes": nbytes, "us": us, "kernel": name, "grid": d.get("Grid Size")}
+            except (KeyError, ValueError):
+                pass
             row = {"capture": rep.name, "kernel": name, "grid": d.get("Grid Size"), "block": d.get("Block Size")}
             for k in KEYS:
                 if k in d:
@@ -97,7 +119,72 @@ def main():
             w.writeheader()
             w.writerows(table)
         print(f"r02_ncu_full_metrics.csv: {len(table)} launches from {len(set(r['capture'] for r in table))} captures")
+    if "rx" in traffic and "tx" in traffic:
+        frames = 1 << 27
+        out = {"source": "ncu --set full --clock-control none, final binary of round 2 (profiles/r02_ncu_full_metrics.csv); "
+                         "one launch each, per-launch figures",
+               "frames_per_launch": frames,
+               "rx_kernel": traffic["rx"]["kernel"], "rx_bytes_per_launch": traffic["rx"]["bytes"],
+               "tx_bytes_per_launch": traffic["tx"]["bytes"], "algorithmic_bytes_per_launch": 16 * frames,
+               "rx_us": traffic["rx"]["us"], "tx_us": traffic["tx"]["us"]}
+        if "batch" in traffic:
+            out["batch_1024_x_1MiB"] = {"bytes_per_launch": traffic["batch"]["bytes"], "algorithmic_bytes_per_launch": 16 * frames,
+                                        "us": traffic["batch"]["us"], "kernel": traffic["batch"]["kernel"]}
+        if "loopback" in traffic:
+            out["loopback"] = {"bytes_per_launch": traffic["loopback"]["bytes"], "algorithmic_bytes_per_launch": 24 * frames,
+                               "us": traffic["loopback"]["us"], "kernel": traffic["loopback"]["kernel"]}
+        if "bank_data" in traffic:
+            plan = traffic.get("bank_plan", {"bytes": 0.0, "us": 0.0})
+            out["bank_repeat"] = {"streams": 65536, "frames_per_block": 256,
+                                  "kernel": "bank_plan_repeat_kernel + bank_repeat_data_kernel<2>",
+                                  "bytes_per_launch": traffic["bank_data"]["bytes"] + plan["bytes"],
+                                  "writes_24B_per_frame": 24 * 65536 * 256,
+                                  "us": traffic["bank_data"]["us"] + plan["us"],
+                                  "plan_us": plan["us"], "data_us": traffic["bank_data"]["us"]}
+        (PROF / "r02_traffic.json").write_text(json.dumps(out, indent=1) + "\n")
+        print("r02_traffic.json written")
+
+
+def summarize_launches():
+    """Per (kernel, grid) totals of the ncu launch list: the timed step's two big launches apart from
+    the chunk kernels of the plugin leg, which share their name."""
+    path = PROF / "r02_launches.csv"
+    if not path.exists():
+        return
+    import collections
+    rows = list(csv.reader(path.open()))
+    start = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
+    h = rows[start]
+    ki, gi, vi, ui = h.index("Kernel Name"), h.index("Grid Size"), h.index("Metric Value"), h.index("Metric Unit")
+    agg = collections.OrderedDict()
+    for r in rows[start + 1:]:
+        if len(r) <= vi:
+            continue
+        try:
+            v = float(r[vi].replace(",", ""))
+        except ValueError:
+            continue
+        v *= {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(r[ui], 1.0)
+        a = agg.setdefault((r[ki], r[gi]), [0, 0.0])
+        a[0] += 1
+        a[1] += v
+    total = sum(a[1] for a in agg.values())
+    out = [{"kernel": k, "grid": g, "launches": a[0], "total_us": round(a[1], 1), "avg_us": round(a[1] / a[0], 2),
+            "share_of_all_gpu_time": round(a[1] / total, 4)} for (k, g), a in sorted(agg.items(), key=lambda kv: -kv[1][1])]
+    big = [o for o in out if o["grid"].startswith("(131072")]
+    step = sum(o["total_us"] for o in big)
+    doc = {"command": "ncu --metrics gpu__time_duration.sum --clock-control none -c 600 python bench.py --steps 2 --warmup 1 "
+                      "--no-rows --no-cpu-baseline --min-seconds 0",
+           "note": "the device-resident step is the two launches with 131072 CTAs (one RX, one TX block of 2^27 frames); the "
+                   "smaller grids of the same kernels are the chunk kernels of the plugin (e2e) leg, flagged_convert_kernel its "
+                   "period-sized calls, stats/synth the set-up and the checksum",
+           "timed_step_kernels": big,
+           "share_of_the_timed_step": {o["kernel"]: round(o["total_us"] / step, 4) for o in big} if step else {},
+           "all": out}
+    (PROF / "r02_launches_summary.json").write_text(json.dumps(doc, indent=1) + "\n")
+    print("r02_launches_summary.json written")
 
 
 if __name__ == "__main__":
     main()
+    summarize_launches()
