@@ -161,6 +161,7 @@ __device__ __forceinline__ BankReadPlan bank_plan_read(const BankState &b, uint6
 // has already planned every stream with one thread each (many streams: keeps all lanes busy).
 __global__ void bank_plan_read_kernel(BankState b, char *cf32_out)
 {
+    pdl_launch_dependents(); // a data kernel launched as our programmatic dependent may set itself up now
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s < b.nstreams)
         bank_plan_read(b, s, cf32_out);
@@ -305,12 +306,33 @@ __device__ __forceinline__ void bank_play_block(const BankState &b, uint64_t s, 
     }
 }
 
+// `for_data_kernel`: the samples follow in bank_repeat_data_kernel<..., kBankModeWrite>, which wants
+// the block's place in the ring as a byte offset and the silence of a forwarded-over gap already
+// written (bank_tx_kernel, the warp-per-stream data side, does both itself).
 __global__ void bank_plan_write_kernel(BankState b, int flags, const long long *time_ns,
-                                       long long rx_time_offset_ns)
+                                       long long rx_time_offset_ns, bool for_data_kernel)
 {
+    pdl_launch_dependents();
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < b.nstreams)
-        bank_plan_write(b, s, flags, time_ns, rx_time_offset_ns);
+    if (s >= b.nstreams)
+        return;
+    const BankWritePlan w = bank_plan_write(b, s, flags, time_ns, rx_time_offset_ns);
+    if (!for_data_kernel)
+        return;
+    b.tx_ring_offset[s] = w.at >= 0 ? (long long)(ring_frame(b, s, uint64_t(w.at)) - b.playback_ring) +
+                                          (uint64_t(w.at) % b.period != 0 ? 1 : 0)
+                                    : -1;
+    if (w.at >= 0 && w.gap > 0) { // ALSA plays zeros for what the application skipped (:493-496)
+        long long gap = w.gap, start = w.start;
+        if (gap > (long long)b.ring) {
+            start += gap - (long long)b.ring;
+            gap = (long long)b.ring;
+        }
+        Pack<2> zero;
+        zero.w[0] = zero.w[1] = 0;
+        for (long long i = 0; i < gap; i++)
+            st_stream<8>(ring_frame(b, s, uint64_t(start + i)), zero);
+    }
 }
 
 // One warp per stream: lane 0 makes writeStream's decisions, then the warp writes silence for
@@ -1004,7 +1026,12 @@ __global__ void __launch_bounds__(256) bank_repeat_direct_kernel(BankState b, ch
 // longer than its stores take).  CTA c takes vectors [c * 256 * U, (c + 1) * 256 * U) of the flat
 // capture and CF32 arrays; its first threads fetch the streams' first-frame counters and ring
 // offsets into shared memory while the others already have the capture loads in flight.
-template <int U, class Hook>
+// MODE: the whole iteration, or one half of it for the separate calls (sxgpu_bank_read: capture
+// and RX conversion, 16 B/frame written, or 8 read + 8 written with ingested capture;
+// sxgpu_bank_write: the CF32 block loaded, TX conversion, 8 read + 8 written).
+constexpr int kBankModeRepeat = 0, kBankModeRead = 1, kBankModeWrite = 2;
+
+template <int U, class Hook, int MODE = kBankModeRepeat>
 __global__ void __launch_bounds__(256) bank_repeat_data_kernel(BankState b, char *cf32, bool capture_in_slot, Hook hook)
 {
     // streams a CTA can touch: 256 * U vectors of at least two vectors per stream (period >= 4,
@@ -1024,11 +1051,20 @@ __global__ void __launch_bounds__(256) bank_repeat_data_kernel(BankState b, char
     const uint32_t count = uint32_t((pow2 ? vlast >> log2v : vlast / nvec) - s0) + 1; // <= 256 * U / nvec + 1
     pdl_wait(); // the decisions (and, before them, the previous iteration's samples) are in memory
     for (uint32_t j = threadIdx.x; j < count; j += 256) {
-        s_first[j] = b.rx_first_frame[s0 + j];
-        s_off[j] = b.tx_ring_offset[s0 + j];
+        if (MODE != kBankModeWrite)
+            s_first[j] = b.rx_first_frame[s0 + j];
+        if (MODE != kBankModeRead)
+            s_off[j] = b.tx_ring_offset[s0 + j];
     }
     Pack<4> cap[U], mid[U], out[U];
-    if (capture_in_slot) {
+    if (MODE == kBankModeWrite) {
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint64_t v = v0 + u * 256 + threadIdx.x;
+            if (v < total)
+                mid[u] = ld_stream<16>(cf32 + v * 16);
+        }
+    } else if (capture_in_slot) {
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const uint64_t v = v0 + u * 256 + threadIdx.x;
@@ -1048,7 +1084,7 @@ __global__ void __launch_bounds__(256) bank_repeat_data_kernel(BankState b, char
         const uint32_t j = pow2 ? local >> log2v : local / nvec;
         jj[u] = v0 + u * 256 + threadIdx.x < total ? j : 0;
         kk[u] = pow2 ? local & (nvec - 1) : local - j * nvec;
-        if (!capture_in_slot) {
+        if (MODE != kBankModeWrite && !capture_in_slot) {
             const uint64_t first = uint64_t(s_first[jj[u]]);
             const uint64_t z0 = sx_synth_frame(b.seed + s0 + jj[u], first + 2 * uint64_t(kk[u]));
             const uint64_t z1 = sx_synth_frame(b.seed + s0 + jj[u], first + 2 * uint64_t(kk[u]) + 1);
@@ -1059,19 +1095,25 @@ __global__ void __launch_bounds__(256) bank_repeat_data_kernel(BankState b, char
 #pragma unroll
     for (int u = 0; u < U; u++) {
         const uint64_t v = v0 + u * 256 + threadIdx.x;
-        RxCf32::apply<2>(cap[u], mid[u], 0.0f);
-        if (v < total)
+        if (MODE != kBankModeWrite)
+            RxCf32::apply<2>(cap[u], mid[u], 0.0f);
+        if (MODE == kBankModeRepeat && v < total)
             hook(mid[u], s0 + jj[u], 2 * kk[u]); // user DSP between RX and TX, identity by default
-        TxCf32::apply<2>(mid[u], out[u], b.thr2);
+        if (MODE != kBankModeRead)
+            TxCf32::apply<2>(mid[u], out[u], b.thr2);
     }
 #pragma unroll
     for (int u = 0; u < U; u++) {
         const uint64_t v = v0 + u * 256 + threadIdx.x;
         if (v >= total)
             continue;
-        if (!capture_in_slot)
-            st_stream<16>(b.capture_stage + v * 16, cap[u]);
-        st_stream<16>(cf32 + v * 16, mid[u]);
+        if (MODE != kBankModeWrite) {
+            if (!capture_in_slot)
+                st_stream<16>(b.capture_stage + v * 16, cap[u]);
+            st_stream<16>(cf32 + v * 16, mid[u]);
+        }
+        if (MODE == kBankModeRead)
+            continue;
         const long long off = s_off[jj[u]];
         if (off < 0)
             continue; // discarded as late
@@ -1112,6 +1154,34 @@ inline cudaError_t launch_bank_repeat_planned(const BankState &b, char *cf32, lo
     cfg.attrs = attr;
     cfg.numAttrs = programmatic ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, bank_repeat_data_kernel<U, Hook>, b, cf32, capture_in_slot, hook);
+}
+
+// One half of the iteration (sxgpu_bank_read / sxgpu_bank_write on a large bank): the matching
+// plan kernel, then the data kernel in that mode as its programmatic dependent.
+template <int MODE>
+inline cudaError_t launch_bank_half_planned(const BankState &b, char *cf32, bool capture_in_slot, int flags,
+                                            const long long *time_ns, long long rx_time_offset_ns, cudaStream_t st,
+                                            bool programmatic = true)
+{
+    if (MODE == kBankModeRead)
+        bank_plan_read_kernel<<<(b.nstreams + 63) / 64, 64, 0, st>>>(b, cf32);
+    else
+        bank_plan_write_kernel<<<(b.nstreams + 63) / 64, 64, 0, st>>>(b, flags, time_ns, rx_time_offset_ns, true);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess)
+        return e;
+    constexpr int U = 4;
+    const uint64_t vectors = uint64_t(b.nstreams) * (b.period / 2);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(unsigned((vectors + 256 * U - 1) / (256 * U)));
+    cfg.blockDim = dim3(256);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = programmatic ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, bank_repeat_data_kernel<U, IdentityHook, MODE>, b, cf32, capture_in_slot, IdentityHook());
 }
 
 __global__ void bank_advance_kernel(BankState b, long long frames)

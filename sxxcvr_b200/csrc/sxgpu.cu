@@ -110,6 +110,7 @@ struct sxgpu_ctx {
     int64_t batch_variant = 0;              // blocks above 4096 frames: 0 auto, 1 = slices of CTAs on vector accesses, 2 = one chunk per CTA, 3 = bulk-async tiles
     int64_t loopback_variant = 0;           // 0 auto (= 2), 1 = vector accesses on a persistent grid, 2 = one tile per CTA, 3 = bulk-async
     int64_t warp_ctas_per_sm = 0;           // grid cap of the warp-per-block / warp-per-stream kernels: N CTAs per SM (persistent), 0 = one CTA per eight blocks
+    int64_t bank_split_variant = 0;         // sxgpu_bank_read / _write on large banks: 0 auto (plan + data kernels), 1 = warp-per-stream kernels
     int64_t bank_pdl = 1;                   // the plan + data schedule launches its data kernel as a programmatic dependent
     int64_t bank_repeat_variant = 0;        // 0 auto; 1, 2, 4, 8 = K streams per warp round; 100 = 32 per CTA round
     int64_t bounce_threads = 0;             // threads copying a pageable caller's buffer: 0 auto, 1 = the caller alone
@@ -1268,6 +1269,7 @@ int64_t *option_slot(sxgpu_ctx *ctx, const char *key)
         {"zero_copy_variant", &ctx->zero_copy_variant},
         {"bank_repeat_variant", &ctx->bank_repeat_variant},
         {"bank_pdl", &ctx->bank_pdl},
+        {"bank_split_variant", &ctx->bank_split_variant},
         {"warp_ctas_per_sm", &ctx->warp_ctas_per_sm},
         {"batch_variant", &ctx->batch_variant},
         {"loopback_variant", &ctx->loopback_variant},
@@ -1656,6 +1658,14 @@ int per_warp_grid(const sxgpu_ctx *ctx, uint32_t nstreams, int block)
     return int(std::min<uint64_t>(ctas, uint64_t(ctx->prop.multiProcessorCount) * uint64_t(ctx->warp_ctas_per_sm)));
 }
 
+// The separate read / write calls of a large bank go through the plan + data kernels too
+// (option bank_split_variant: 0 auto, 1 = always the warp-per-stream kernels).
+bool bank_split_direct(const sxgpu_ctx *ctx, const BankState &b, const void *d_cf32)
+{
+    return ctx->bank_split_variant != 1 && b.nstreams >= 32768 && b.period % 2 == 0 && b.period >= 4 &&
+           reinterpret_cast<uintptr_t>(d_cf32) % 16 == 0;
+}
+
 template <class T>
 int copy_out(sxgpu_bank *bank, T *h_dst, const void *d_src, cudaStream_t st)
 {
@@ -1783,6 +1793,15 @@ int sxgpu_bank_read(sxgpu_bank *bank, void *d_cf32, sxgpu_stream stream)
     SX_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = bank_stream(bank, stream);
     const BankState &b = bank->st;
+    if (bank_split_direct(ctx, b, d_cf32)) {
+        // large banks: decisions by a thread per stream, then capture and RX conversion by CTAs that
+        // take one chunk each (sx_bank.cuh, bank_repeat_data_kernel in read mode)
+        SX_CUDA(ctx, launch_bank_half_planned<kBankModeRead>(b, static_cast<char *>(d_cf32), bank->external_capture, 0, nullptr,
+                                                             0, st, ctx->bank_pdl != 0));
+        ctx->launches += 2;
+        ctx->frames_rx += uint64_t(b.nstreams) * b.period;
+        return SXGPU_OK;
+    }
     const bool fused = b.nstreams <= kBankFusedPlanStreams;
     if (!fused)
         bank_plan_read_kernel<<<per_stream_grid(b.nstreams, 256), 256, 0, st>>>(b, static_cast<char *>(d_cf32));
@@ -1806,10 +1825,17 @@ int sxgpu_bank_write(sxgpu_bank *bank, const void *d_cf32, int flags, const long
     SX_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = bank_stream(bank, stream);
     const BankState &b = bank->st;
+    if (bank_split_direct(ctx, b, d_cf32)) {
+        SX_CUDA(ctx, launch_bank_half_planned<kBankModeWrite>(b, const_cast<char *>(static_cast<const char *>(d_cf32)), false,
+                                                              flags, d_time_ns, rx_time_offset_ns, st, ctx->bank_pdl != 0));
+        ctx->launches += 2;
+        ctx->frames_tx += uint64_t(b.nstreams) * b.period;
+        return SXGPU_OK;
+    }
     const bool fused = b.nstreams <= kBankFusedPlanStreams;
     if (!fused)
         bank_plan_write_kernel<<<per_stream_grid(b.nstreams, 256), 256, 0, st>>>(b, flags, d_time_ns,
-                                                                             rx_time_offset_ns);
+                                                                             rx_time_offset_ns, false);
     bank_tx_kernel<<<per_warp_grid(ctx, b.nstreams, 256), 256, 0, st>>>(
         b, static_cast<const char *>(d_cf32), flags, d_time_ns, rx_time_offset_ns, fused);
     SX_CUDA(ctx, cudaGetLastError());

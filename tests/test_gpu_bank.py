@@ -386,10 +386,11 @@ def test_repeat_with_blocks_that_straddle_ring_slices(ctx, variant, latency_fram
 
 
 @pytest.mark.parametrize("cap,pdl", [(0, 1), (8, 1), (0, 0)])
-def test_large_bank_default_schedule_and_grid_options(ctx, oracle, cap, pdl):
-    """The default schedule of a large bank (decisions by one kernel, samples by the next, launched
-    as its programmatic dependent) against the two separate calls, with the warp-per-stream kernels
-    of those calls on a persistent grid (cap 8) and on one CTA per eight streams (cap 0)."""
+def test_large_bank_default_schedules_and_grid_options(ctx, oracle, cap, pdl):
+    """A large bank's default schedules -- decisions by one kernel, samples by the next, launched as
+    its programmatic dependent -- for the fused iteration and for the separate read / write calls,
+    against the warp-per-stream kernels (bank_split_variant = 1; persistent grid with cap 8, one
+    CTA per eight streams with cap 0)."""
     from sxxcvr_b200 import Bank
     S, P, rate = 32768 + 37, 64, 75000.0
     lat = int(round(768 * 1e9 / rate))
@@ -397,30 +398,53 @@ def test_large_bank_default_schedule_and_grid_options(ctx, oracle, cap, pdl):
     ctx.set_option("bank_pdl", pdl)
     ctx.set_option("bank_repeat_variant", 0)
     try:
-        with Bank(ctx, S, P, rate, 1.0e-6, 5) as two_calls, Bank(ctx, S, P, rate, 1.0e-6, 5) as fused:
-            cf_a = torch.zeros(S * P * 2, dtype=torch.float32, device="cuda")
-            cf_b = torch.zeros_like(cf_a)
-            for it, adv in enumerate((0, 0, 70000, 0, 13, 0)):   # an overrun and an out-of-step block on the way
+        with Bank(ctx, S, P, rate, 1.0e-6, 5) as ref, Bank(ctx, S, P, rate, 1.0e-6, 5) as split, \
+                Bank(ctx, S, P, rate, 1.0e-6, 5) as fused:
+            cf = [torch.zeros(S * P * 2, dtype=torch.float32, device="cuda") for _ in range(3)]
+            for it, adv in enumerate((0, 0, 70000, 0, 13, 0)):   # an overrun and a clock jump on the way
                 if adv:
-                    two_calls.advance(adv)
-                    fused.advance(adv)
-                two_calls.read(cf_a.data_ptr())
-                two_calls.write(cf_a.data_ptr(), HAS_TIME, None, lat)
-                fused.repeat(cf_b.data_ptr(), lat)
-                assert torch.equal(cf_a.view(torch.int32), cf_b.view(torch.int32)), it
-                for x, y in zip(two_calls.positions(), fused.positions()):
-                    assert np.array_equal(x, y), it
-                for x, y in zip(two_calls.last_read(), fused.last_read()):
-                    assert np.array_equal(x, y), it
-                assert np.array_equal(two_calls.last_write(), fused.last_write()), it
-                _, _, txp = fused.positions()
-                for s in (0, 1, 31, 32, 4095, 32767, 32768, S - 1):
+                    for bank in (ref, split, fused):
+                        bank.advance(adv)
+                ctx.set_option("bank_split_variant", 1)
+                ref.read(cf[0].data_ptr())
+                ref.write(cf[0].data_ptr(), HAS_TIME, None, lat)
+                ctx.set_option("bank_split_variant", 0)
+                split.read(cf[1].data_ptr())
+                split.write(cf[1].data_ptr(), HAS_TIME, None, lat)
+                fused.repeat(cf[2].data_ptr(), lat)
+                _, _, txp = ref.positions()
+                for other, c in ((split, cf[1]), (fused, cf[2])):
+                    assert torch.equal(cf[0].view(torch.int32), c.view(torch.int32)), it
+                    for x, y in zip(ref.positions(), other.positions()):
+                        assert np.array_equal(x, y), it
+                    for x, y in zip(ref.last_read(), other.last_read()):
+                        assert np.array_equal(x, y), it
+                    assert np.array_equal(ref.last_write(), other.last_write()), it
+                    for s in (0, 1, 31, 32, 4095, 32767, 32768, S - 1):
+                        end = int(txp[s])
+                        start = max(0, end - 4 * P)
+                        assert np.array_equal(ref.playback(s, start, end - start), other.playback(s, start, end - start)), (it, s)
+            frames = sxtest.synth_frames(oracle, int(fused.positions()[1][S - 1]) - P, P, seed=5 + S - 1)
+            assert np.array_equal(cf[2].view(torch.int32).cpu().numpy().reshape(S, 2 * P)[S - 1].view(np.uint32),
+                                  sxtest.oracle_rx(oracle, frames).view(np.uint32))
+            # the separate calls with an untimed write and with per-stream timestamps, ingested capture
+            t_ns = torch.full((S,), lat, dtype=torch.int64, device="cuda") + torch.arange(S, device="cuda") % 3 * 1_000_000
+            for flags, times in ((0, None), (HAS_TIME, t_ns.data_ptr())):
+                for variant, bank, c in ((1, ref, cf[0]), (0, split, cf[1])):
+                    ctx.set_option("bank_split_variant", variant)
+                    bank.ingest(0, 0, None)
+                    bank.read(c.data_ptr())
+                    bank.write(c.data_ptr(), flags, times, 0)
+                assert torch.equal(cf[0].view(torch.int32), cf[1].view(torch.int32))
+                for x, y in zip(ref.positions(), split.positions()):
+                    assert np.array_equal(x, y)
+                assert np.array_equal(ref.last_write(), split.last_write())
+                _, _, txp = ref.positions()
+                for s in (0, 1, 2, 4095, S - 1):
                     end = int(txp[s])
                     start = max(0, end - 4 * P)
-                    assert np.array_equal(two_calls.playback(s, start, end - start), fused.playback(s, start, end - start)), (it, s)
-            frames = sxtest.synth_frames(oracle, int(fused.positions()[1][S - 1]) - P, P, seed=5 + S - 1)
-            assert np.array_equal(cf_b.view(torch.int32).cpu().numpy().reshape(S, 2 * P)[S - 1].view(np.uint32),
-                                  sxtest.oracle_rx(oracle, frames).view(np.uint32))
+                    assert np.array_equal(ref.playback(s, start, end - start), split.playback(s, start, end - start)), s
     finally:
         ctx.set_option("warp_ctas_per_sm", 0)
         ctx.set_option("bank_pdl", 1)
+        ctx.set_option("bank_split_variant", 0)

@@ -21,7 +21,6 @@ COPIES = {  # profiles name -> candidates under gpurun_out (first that exists wi
     "r02_bench_bank_fused.json": ["f2_bench_bank_fused.json"],
     "r02_bench_bank_fused_graph.json": ["f2_bench_bank_fused_graph.json"],
     "r02_bench_bank_fused_graph_external.json": ["f2_bench_bank_fused_graph_external.json"],
-    "r02_bench_bank_two_calls.json": ["f2_bench_bank_two_calls.json"],
     "r02_bench_n2.json": ["m2_bench.json"],
     "r02_bench_n2_single_process.json": ["m2_bench_single.json"],
     "r02_bench_n2_reference_arm.json": ["m2_bench_ref.json"],
