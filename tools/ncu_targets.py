@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """A few launches of each kernel worth profiling, for `ncu --set full` (run under ncu with
---kernel-name / --launch-skip filters; see tools/gpu_session4.sh).  Arguments: which group."""
+--kernel-name / --launch-skip filters; see tools/gpu_final_1gpu.sh).  Arguments: which group."""
 import sys
 from pathlib import Path
 
