@@ -25,6 +25,8 @@ COPIES = {  # profiles name -> candidates under gpurun_out (first that exists wi
     "r02_bench_n2_single_process.json": ["m2_bench_single.json"],
     "r02_bench_n2_reference_arm.json": ["m2_bench_ref.json"],
     "r02_bench_n4.json": ["m4_bench.json"],
+    "r02_bench_n4_single_process.json": ["m4_bench_single.json"],
+    "r02_bench_n4_reference_arm.json": ["m4_bench_ref.json"],
     "r02_bench_n8.json": ["m8_bench.json"],
     "r02_bench_n8_single_process.json": ["m8_bench_single.json"],
     "r02_bench_n8_reference_arm.json": ["m8_bench_ref.json"],
