@@ -807,7 +807,8 @@ def run_bank_arm(args, rank: int, local_rank: int, world: int):
     # separate calls on a large bank (plan + data kernels per half): the read half writes slot and CF32
     # block from registers (16 W), the write half reads the block and writes the ring (8 R + 8 W);
     # the warp-per-stream kernels of smaller banks re-read the slot too (40 B/frame)
-    hbm_bytes = 24 if args.fused else (32 if S >= 32768 else 40)
+    large_bank = S >= 16384 and S * P >= (1 << 21)      # sx::bank_is_large
+    hbm_bytes = 24 if args.fused else (32 if large_bank else 40)
     traffic = None      # DRAM bytes per launch from the committed ncu capture, when it is of this shape
     traffic_source = None
     for name in ("r02_traffic.json", "r01_traffic.json"):
@@ -844,10 +845,10 @@ def run_bank_arm(args, rank: int, local_rank: int, world: int):
                                    if args.fused else
                                    "bank iteration, separate calls: plan + data kernels per call (read: capture and CF32 block "
                                    "written from registers, 16 W; write: 8 R + 8 W per frame)",
-                         "hbm_bytes_per_frame": hbm_bytes, "bytes_moved_per_frame": 40 if args.fused or S < 32768 else 32,
+                         "hbm_bytes_per_frame": hbm_bytes, "bytes_moved_per_frame": 40 if args.fused or not large_bank else 32,
                          "bound": "hbm", "achieved": hbm_bytes * S * P / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": hbm_bytes * S * P / (ms * 1e-3) / 1e9 / peak,
-                         "moved_gbs": (40 if args.fused or S < 32768 else 32) * S * P / (ms * 1e-3) / 1e9,
+                         "moved_gbs": (40 if args.fused or not large_bank else 32) * S * P / (ms * 1e-3) / 1e9,
                          "algorithmic_bytes_per_launch": hbm_bytes * S * P,
                          "traffic": traffic, "traffic_source": traffic_source, "peak_source": peak_src,
                          "frac_of_write_only_ceiling": hbm_bytes * S * P / (ms * 1e-3) / 1e9 / 7139.0,

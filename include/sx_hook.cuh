@@ -66,7 +66,7 @@ inline int bank_repeat_with(sxgpu_bank *bank, void *d_cf32, long long rx_time_of
         kernel<<<grid, 256, 0, stream>>>(view, static_cast<char *>(d_cf32), rx_time_offset_ns, external != 0, hook);
         return cudaGetLastError() == cudaSuccess ? SXGPU_OK : SXGPU_ERR_CUDA;
     };
-    if (view.nstreams >= 32768 && view.period >= 4) // the library's own choice for large banks: decisions first, then the samples
+    if (bank_is_large(view)) // the library's own choice for large banks: decisions first, then the samples
         return launch_bank_repeat_planned<2>(view, static_cast<char *>(d_cf32), rx_time_offset_ns, external != 0, stream, hook) ==
                        cudaSuccess
                    ? SXGPU_OK

@@ -100,6 +100,14 @@ __device__ __forceinline__ char *ring_frame(const BankState &b, uint64_t s, uint
 
 constexpr int SX_HAS_TIME = 1 << 2; // SOAPY_SDR_HAS_TIME
 
+// From here up a bank's iteration is bound by HBM, not by launch latency, and runs as a plan
+// kernel plus a data kernel of hardware-scheduled CTAs (measured crossover: equal at 4096 x 256
+// frames, 10 % ahead at 16384 x 256, 13 % at 65536 x 256; profiles/r02_summary.md section 5).
+inline bool bank_is_large(const BankState &b)
+{
+    return b.nstreams >= 16384 && uint64_t(b.nstreams) * b.period >= (uint64_t(1) << 21) && b.period % 2 == 0 && b.period >= 4;
+}
+
 // readStream(stream, buf, period, timeoutUs > 0) for stream s: SoapySX.cpp:897-959.
 // Run by one lane of the warp that owns the stream.  The counters come in as values and the
 // decisions go out as values (and to the state arrays), so that a caller which goes on to plan

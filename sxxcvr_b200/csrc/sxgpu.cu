@@ -1662,8 +1662,7 @@ int per_warp_grid(const sxgpu_ctx *ctx, uint32_t nstreams, int block)
 // (option bank_split_variant: 0 auto, 1 = always the warp-per-stream kernels).
 bool bank_split_direct(const sxgpu_ctx *ctx, const BankState &b, const void *d_cf32)
 {
-    return ctx->bank_split_variant != 1 && b.nstreams >= 32768 && b.period % 2 == 0 && b.period >= 4 &&
-           reinterpret_cast<uintptr_t>(d_cf32) % 16 == 0;
+    return ctx->bank_split_variant != 1 && bank_is_large(b) && reinterpret_cast<uintptr_t>(d_cf32) % 16 == 0;
 }
 
 template <class T>
@@ -1880,7 +1879,7 @@ int sxgpu_bank_repeat(sxgpu_bank *bank, void *d_cf32, long long rx_time_offset_n
     if (k == 0) {
         if (b.nstreams <= 2048)
             k = reg_ok ? 201 : 1;
-        else if (b.nstreams < 32768 || !reg_ok || b.period < 4)
+        else if (!bank_is_large(b) || !reg_ok)
             k = b.nstreams <= 8192 ? 2 : b.nstreams <= 32768 ? 4 : 100;
         else
             k = ext ? 604 : 600; // decisions first, then the samples by hardware-scheduled CTAs
