@@ -314,6 +314,30 @@ __device__ __forceinline__ void bank_play_block(const BankState &b, uint64_t s, 
     }
 }
 
+// Silence for the forwarded-over regions of a warp's 32 streams (ALSA plays zeros for what the
+// application skipped, :493-496), written by the whole warp stream after stream: 32 frames per
+// store instruction, side by side, instead of one thread per stream walking its gap alone.  Every
+// lane of the warp must call this (lanes without a stream or without a gap pass gap = 0).
+__device__ __forceinline__ void bank_silence_by_warp(const BankState &b, uint64_t s, long long start, long long gap)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    if (gap > (long long)b.ring) { // older than one lap: only the last lap is still in the ring
+        start += gap - (long long)b.ring;
+        gap = (long long)b.ring;
+    }
+    unsigned pending = __ballot_sync(0xffffffffu, gap > 0);
+    while (pending) {
+        const int j = __ffs(pending) - 1;
+        pending &= pending - 1;
+        const uint64_t sj = __shfl_sync(0xffffffffu, s, j);
+        const long long start_j = __shfl_sync(0xffffffffu, start, j), gap_j = __shfl_sync(0xffffffffu, gap, j);
+        Pack<2> zero;
+        zero.w[0] = zero.w[1] = 0;
+        for (long long i = lane; i < gap_j; i += 32)
+            st_stream<8>(ring_frame(b, sj, uint64_t(start_j + i)), zero);
+    }
+}
+
 // `for_data_kernel`: the samples follow in bank_repeat_data_kernel<..., kBankModeWrite>, which wants
 // the block's place in the ring as a byte offset and the silence of a forwarded-over gap already
 // written (bank_tx_kernel, the warp-per-stream data side, does both itself).
@@ -321,26 +345,17 @@ __global__ void bank_plan_write_kernel(BankState b, int flags, const long long *
                                        long long rx_time_offset_ns, bool for_data_kernel)
 {
     pdl_launch_dependents();
-    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= b.nstreams)
-        return;
-    const BankWritePlan w = bank_plan_write(b, s, flags, time_ns, rx_time_offset_ns);
-    if (!for_data_kernel)
-        return;
-    b.tx_ring_offset[s] = w.at >= 0 ? (long long)(ring_frame(b, s, uint64_t(w.at)) - b.playback_ring) +
-                                          (uint64_t(w.at) % b.period != 0 ? 1 : 0)
-                                    : -1;
-    if (w.at >= 0 && w.gap > 0) { // ALSA plays zeros for what the application skipped (:493-496)
-        long long gap = w.gap, start = w.start;
-        if (gap > (long long)b.ring) {
-            start += gap - (long long)b.ring;
-            gap = (long long)b.ring;
-        }
-        Pack<2> zero;
-        zero.w[0] = zero.w[1] = 0;
-        for (long long i = 0; i < gap; i++)
-            st_stream<8>(ring_frame(b, s, uint64_t(start + i)), zero);
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    BankWritePlan w = {-1, 0, 0};
+    if (s < b.nstreams) {
+        w = bank_plan_write(b, s, flags, time_ns, rx_time_offset_ns);
+        if (for_data_kernel)
+            b.tx_ring_offset[s] = w.at >= 0 ? (long long)(ring_frame(b, s, uint64_t(w.at)) - b.playback_ring) +
+                                                  (uint64_t(w.at) % b.period != 0 ? 1 : 0)
+                                            : -1;
     }
+    if (for_data_kernel) // (uniform over the grid: every lane gets here)
+        bank_silence_by_warp(b, s, w.start, (s < b.nstreams && w.at >= 0) ? w.gap : 0);
 }
 
 // One warp per stream: lane 0 makes writeStream's decisions, then the warp writes silence for
@@ -685,25 +700,15 @@ __global__ void bank_plan_repeat_kernel(BankState b, char *cf32, long long rx_ti
 {
     pdl_launch_dependents(); // the data kernel may take its place on the SMs now; it waits for us before it reads
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= b.nstreams)
-        return;
-    long long first;
-    BankWritePlan w;
-    bank_plan_repeat(b, s, cf32, rx_time_offset_ns, first, w);
-    b.tx_ring_offset[s] = w.at >= 0 ? (long long)(ring_frame(b, s, uint64_t(w.at)) - b.playback_ring) +
-                                          (uint64_t(w.at) % b.period != 0 ? 1 : 0)
-                                    : -1;
-    if (w.at >= 0 && w.gap > 0) { // ALSA plays zeros for what the application skipped (:493-496)
-        long long gap = w.gap, start = w.start;
-        if (gap > (long long)b.ring) {
-            start += gap - (long long)b.ring;
-            gap = (long long)b.ring;
-        }
-        Pack<2> zero;
-        zero.w[0] = zero.w[1] = 0;
-        for (long long i = 0; i < gap; i++)
-            st_stream<8>(ring_frame(b, s, uint64_t(start + i)), zero);
+    BankWritePlan w = {-1, 0, 0};
+    if (s < b.nstreams) {
+        long long first;
+        bank_plan_repeat(b, s, cf32, rx_time_offset_ns, first, w);
+        b.tx_ring_offset[s] = w.at >= 0 ? (long long)(ring_frame(b, s, uint64_t(w.at)) - b.playback_ring) +
+                                              (uint64_t(w.at) % b.period != 0 ? 1 : 0)
+                                        : -1;
     }
+    bank_silence_by_warp(b, s, w.start, (s < b.nstreams && w.at >= 0) ? w.gap : 0);
 }
 
 constexpr int kBankTile = 2048; // frames per tile of the bulk schedule
