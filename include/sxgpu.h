@@ -331,9 +331,7 @@ int sxgpu_multi_sync(sxgpu_multi *m);
  *                               200 + K, K in {1, 2, 4} = a warp takes K streams per round and
  *                               keeps every intermediate in registers (stores only); 300, 302,
  *                               303 = the same with a CTA's first warp deciding for 32 streams;
- *                               400 = decisions by a thread-per-stream kernel, samples on the
- *                               bulk-async schedule; 500, 502 = one launch, one chunk of streams
- *                               per CTA; 600, 604 = decisions by a thread-per-stream kernel, then
+ *                               600, 604 = decisions by a thread-per-stream kernel, then
  *                               the samples by CTAs that take one chunk each (2 or 4 vectors per
  *                               thread), the second kernel a programmatic dependent of the first
  *                               ("bank_pdl" = 0 turns that off)

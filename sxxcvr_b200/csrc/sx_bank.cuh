@@ -677,24 +677,15 @@ __global__ void bank_gather_kernel(BankState b, uint32_t stream, long long posit
 }
 
 // ---------------------------------------------------------------------------------------
-// The repeater iteration on the bulk-async schedule (two launches: decisions, then data).
+// The repeater iteration as two launches: decisions, then data.
 //
 // bank_plan_repeat_kernel: one thread per stream takes readStream's and the timed
-// writeStream's decisions (bank_plan_repeat: same stores, same order as every other schedule)
-// and writes the silence of a forwarded-over gap itself -- rare, and off the data kernel's path.
-//
-// bank_repeat_bulk_kernel: the samples.  The streams' periods lie side by side in the capture
-// slots and in the caller's CF32 buffer, so the bank is one flat array of nstreams x period
-// frames and the iteration is the fused loopback over it: persistent CTAs, tiles of whole
-// streams (2048 frames: 8 streams of 256), three shared-memory buffers per stage.  The capture
-// tile is either produced in shared memory by all threads (synthetic stand-in for the I2S DMA)
-// and bulk-stored to the capture slots, or bulk-loaded from them (frames from outside,
-// sxgpu_bank_ingest); RX and TX conversions run shared -> shared; the CF32 tile leaves as one
-// bulk store, and the I2S tile as one bulk store per stream, to wherever that stream's write
-// position puts it in the time-major ring (two when the block straddles a period boundary; by
-// frame-wide thread stores when it starts on an odd frame).  No stage reads back what another
-// wrote, no warp waits on a dependent round trip: what is left is the 24 B/frame of HBM traffic.
-// Needs: period even, 2048 % period == 0, 16-byte aligned CF32 buffer.
+// writeStream's decisions (bank_plan_repeat: same stores, same order as every other schedule),
+// leaves the block's place in the ring as a byte offset for the data kernel and, warp by warp,
+// writes the silence of forwarded-over gaps -- rare, and off the data kernel's path.
+// The data kernel is bank_repeat_data_kernel, further down.  (A data kernel on the bulk-async
+// schedule of round 1 -- persistent CTAs, 2048-frame tiles through shared memory, bulk stores --
+// was measured at 125 us for 65536 streams against 61 and is gone: commit 354f3f1 has it.)
 // ---------------------------------------------------------------------------------------
 __global__ void bank_plan_repeat_kernel(BankState b, char *cf32, long long rx_time_offset_ns)
 {
@@ -711,332 +702,25 @@ __global__ void bank_plan_repeat_kernel(BankState b, char *cf32, long long rx_ti
     bank_silence_by_warp(b, s, w.start, (s < b.nstreams && w.at >= 0) ? w.gap : 0);
 }
 
-constexpr int kBankTile = 2048; // frames per tile of the bulk schedule
-
-struct BankTileMeta {
-    long long first[32]; // counter value of each stream's first captured frame (synthetic capture)
-    long long at[32];    // counter value its block is written at; -1: discarded as late
-};
-
-template <int STAGES, int BLOCK, class Hook>
-__global__ void __launch_bounds__(BLOCK) bank_repeat_bulk_kernel(BankState b, char *cf32, bool capture_in_slot, Hook hook,
-                                                                int load_policy, int store_policy)
-{
-    constexpr size_t STAGE = size_t(kBankTile) * 8;
-    extern __shared__ __align__(128) unsigned char smem[];
-    unsigned char *in_buf = smem;
-    unsigned char *mid_buf = smem + size_t(STAGES) * STAGE;
-    unsigned char *out_buf = smem + 2 * size_t(STAGES) * STAGE;
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + 3 * size_t(STAGES) * STAGE);
-    BankTileMeta *meta = reinterpret_cast<BankTileMeta *>(full + STAGES); // [2], alternating by tile
-
-    const uint32_t P = b.period;
-    const uint32_t spt = kBankTile / P; // streams per tile (host guarantees P divides the tile, spt <= 32 for P >= 64)
-    // P divides 2048, so it is a power of two, and so is the number of period slices in the ring
-    // (65536 / P): every division on this path is a shift or a mask.
-    const uint32_t log2p = 31 - __clz(P);
-    const uint64_t slice_mask = b.ring / P - 1;
-    auto ring_at = [&](uint64_t stream, uint64_t pos) -> char * {
-        return b.playback_ring + ((((pos >> log2p) & slice_mask) * b.nstreams + stream) * P + (pos & (P - 1))) * 8;
-    };
-    const uint64_t ntiles = (uint64_t(b.nstreams) + spt - 1) / spt;
-    const uint64_t first_tile = blockIdx.x, stride = gridDim.x;
-    if (first_tile >= ntiles)
-        return;
-    const uint64_t mine = (ntiles - first_tile + stride - 1) / stride;
-    const uint64_t pol = bulk::make_policy(load_policy), pol_store = bulk::make_policy(store_policy);
-    auto tile_streams = [&](uint64_t i) -> uint32_t {
-        const uint64_t s0 = (first_tile + i * stride) * spt;
-        return uint32_t(b.nstreams - s0 < spt ? b.nstreams - s0 : spt);
-    };
-    auto load_meta = [&](uint64_t i) { // threads 0..spt-1: the decisions of tile i's streams
-        if (threadIdx.x < tile_streams(i)) {
-            const uint64_t s = (first_tile + i * stride) * spt + threadIdx.x;
-            meta[i & 1].first[threadIdx.x] = b.rx_first_frame[s];
-            meta[i & 1].at[threadIdx.x] = b.tx_write_position[s];
-        }
-    };
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; s++)
-            bulk::mbar_init(&full[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    load_meta(0);
-    __syncthreads();
-    if (capture_in_slot && threadIdx.x == 0) {
-        for (uint64_t i = 0; i < uint64_t(STAGES) && i < mine; i++) {
-            const uint32_t bytes = tile_streams(i) * P * 8;
-            bulk::mbar_expect_tx(&full[i], bytes);
-            bulk::load_g2s(in_buf + i * STAGE, b.capture_stage + (first_tile + i * stride) * spt * P * 8, bytes, &full[i], pol);
-        }
-    }
-
-    for (uint64_t i = 0; i < mine; i++) {
-        const int s = int(i % STAGES);
-        const uint32_t ns = tile_streams(i), nf = ns * P;
-        const uint64_t s0 = (first_tile + i * stride) * spt;
-        // the three buffers of stage s were last read by the stores of tile i - STAGES (every lane
-        // of the first warp issues stores and commits one group per tile, see below)
-        if (threadIdx.x < 32)
-            bulk::wait_group_read<STAGES - 1>();
-        __syncthreads();
-        // The next tile's decisions: requested now into registers, parked in the other half of
-        // `meta` after the conversion (its last readers -- tile i - 1, up to the first warp's store
-        // issue -- are all behind the barrier above, its next readers two barriers ahead), so the
-        // round trip to memory runs under the conversion instead of in front of it.
-        long long next_first = 0, next_at = -1;
-        const bool fetch_next = i + 1 < mine && threadIdx.x < tile_streams(i + 1);
-        if (fetch_next) {
-            const uint64_t sn = (first_tile + (i + 1) * stride) * spt + threadIdx.x;
-            next_first = b.rx_first_frame[sn];
-            next_at = b.tx_write_position[sn];
-        }
-        const BankTileMeta &m = meta[i & 1];
-
-        uint4 *ip = reinterpret_cast<uint4 *>(in_buf + size_t(s) * STAGE);
-        uint4 *mp = reinterpret_cast<uint4 *>(mid_buf + size_t(s) * STAGE);
-        uint4 *op = reinterpret_cast<uint4 *>(out_buf + size_t(s) * STAGE);
-        if (capture_in_slot)
-            bulk::mbar_wait(&full[s], uint32_t(i / STAGES) & 1u);
-        for (uint32_t v = threadIdx.x; v * 2 < nf; v += blockDim.x) {
-            const uint32_t j = (2 * v) >> log2p, k = (2 * v) & (P - 1); // stream within the tile, frame within its block
-            Pack<4> in, mid, out;
-            if (capture_in_slot) {
-                const uint4 t = ip[v];
-                in.w[0] = t.x, in.w[1] = t.y, in.w[2] = t.z, in.w[3] = t.w;
-            } else {
-                const uint64_t z0 = sx_synth_frame(b.seed + s0 + j, uint64_t(m.first[j]) + k);
-                const uint64_t z1 = sx_synth_frame(b.seed + s0 + j, uint64_t(m.first[j]) + k + 1);
-                in.w[0] = uint32_t(z0), in.w[1] = uint32_t(z0 >> 32), in.w[2] = uint32_t(z1), in.w[3] = uint32_t(z1 >> 32);
-                ip[v] = make_uint4(in.w[0], in.w[1], in.w[2], in.w[3]);
-            }
-            RxCf32::apply<2>(in, mid, 0.0f);
-            hook(mid, s0 + j, k);
-            TxCf32::apply<2>(mid, out, b.thr2);
-            mp[v] = make_uint4(mid.w[0], mid.w[1], mid.w[2], mid.w[3]);
-            op[v] = make_uint4(out.w[0], out.w[1], out.w[2], out.w[3]);
-        }
-        if (fetch_next) {
-            meta[(i + 1) & 1].first[threadIdx.x] = next_first;
-            meta[(i + 1) & 1].at[threadIdx.x] = next_at;
-        }
-        bulk::fence_async_smem();
-        __syncthreads();
-
-        // A block that starts on an odd frame of the ring cannot be moved by 16-byte bulk copies:
-        // its frames go out one by one (all threads), straight from the output buffer.
-        for (uint32_t j = 0; j < ns; j++) {
-            const long long at = m.at[j];
-            if (at >= 0 && (at & 1)) {
-                const unsigned char *src = out_buf + size_t(s) * STAGE + size_t(j) * P * 8;
-                for (uint32_t f = threadIdx.x; f < P; f += blockDim.x) {
-                    Pack<2> w;
-                    const uint2 t = *reinterpret_cast<const uint2 *>(src + size_t(f) * 8);
-                    w.w[0] = t.x, w.w[1] = t.y;
-                    st_stream<8>(ring_at(s0 + j, uint64_t(at) + f), w);
-                }
-            }
-        }
-
-        // Stores: the first warp, one stream per lane for the ring (where a block lands takes a
-        // couple of 64-bit divisions per stream: side by side on the lanes they cost what one
-        // does; on one thread they were six times the tile's transfer time), lane 0 for the two
-        // flat tiles and the next load.  Bulk groups are per thread: every lane commits one.
-        if (threadIdx.x < 32) {
-            if (threadIdx.x == 0) {
-                const size_t flat = s0 * P * 8;
-                if (!capture_in_slot)
-                    bulk::store_s2g(b.capture_stage + flat, in_buf + size_t(s) * STAGE, nf * 8, pol_store);
-                bulk::store_s2g(cf32 + flat, mid_buf + size_t(s) * STAGE, nf * 8, pol_store);
-            }
-            // Streams in lock-step (the normal case: one sample clock, period-aligned writes) land side
-            // by side in one slice of the time-major ring: one store for the whole tile.
-            const uint32_t j = threadIdx.x;
-            const long long my_at = j < ns ? m.at[j] : m.at[0];
-            const bool lockstep = __all_sync(0xffffffffu, my_at == m.at[0]) && m.at[0] >= 0 && (uint64_t(m.at[0]) & (P - 1)) == 0;
-            if (lockstep) {
-                if (threadIdx.x == 0)
-                    bulk::store_s2g(ring_at(s0, uint64_t(m.at[0])), out_buf + size_t(s) * STAGE, nf * 8, pol_store);
-            } else if (j < ns) {
-                const long long at = my_at;
-                if (at >= 0 && !(at & 1)) {
-                    const unsigned char *src = out_buf + size_t(s) * STAGE + size_t(j) * P * 8;
-                    const uint32_t into = uint32_t(uint64_t(at) & (P - 1));
-                    const uint32_t span = into ? P - into : P;
-                    bulk::store_s2g(ring_at(s0 + j, uint64_t(at)), src, span * 8, pol_store);
-                    if (span < P)
-                        bulk::store_s2g(ring_at(s0 + j, uint64_t(at) + span), src + size_t(span) * 8, (P - span) * 8, pol_store);
-                }
-            }
-            bulk::commit_group();
-            const uint64_t nxt = i + STAGES;
-            if (threadIdx.x == 0 && capture_in_slot && nxt < mine) {
-                const uint32_t bytes = tile_streams(nxt) * P * 8;
-                bulk::mbar_expect_tx(&full[s], bytes);
-                bulk::load_g2s(in_buf + size_t(s) * STAGE, b.capture_stage + (first_tile + nxt * stride) * spt * P * 8, bytes,
-                               &full[s], pol);
-            }
-        }
-    }
-    if (threadIdx.x < 32)
-        bulk::wait_group_all();
-}
-
 // ---------------------------------------------------------------------------------------
-// The repeater iteration, one launch, hardware-scheduled CTAs ("direct" schedule).
+// The data side: hardware-scheduled CTAs.
 //
-// Every schedule above runs a persistent grid, and every one of them -- memory-staged, register-
-// resident, bulk-async -- lands within a few percent of what *plain stores of the same bytes from
-// a persistent grid* reach (tools/experiments/bank_limits.cu: 65.6 us for the 402 MB of 65536
+// Every one-launch schedule above runs a persistent grid, and every one of them -- memory-staged,
+// register-resident -- lands within a few percent of what *plain stores of the same bytes from a
+// persistent grid* reach (tools/experiments/bank_limits.cu: 65.6 us for the 402 MB of 65536
 // streams x 256 frames, exactly cudaMemset's time over the same three regions).  The same bytes
 // written by CTAs that each take one chunk and leave -- handed out in index order by the hardware,
 // so that the addresses in flight form one compact window moving through each region -- take
-// 56-58 us, arithmetic included.  Hence this kernel: CTA c owns streams [c * G, (c + 1) * G), G
-// chosen so that they make up 256 * U 16-byte vectors; its first G threads take those streams'
-// decisions side by side (bank_plan_repeat: same stores, same order as every other schedule) and
-// park what the data phase needs in shared memory; then all threads produce (or load) the
-// capture frames, convert RX, apply the hook, convert TX and issue the three stores, U vectors
-// per thread in flight, nothing read back.  The streams' periods lie side by side in the capture
-// slots and in the caller's CF32 buffer, so those two are flat arrays; the ring side is flat too
-// whenever a block starts on a period boundary of the ring (two spans, frame-wide stores,
-// otherwise).  Needs an even period and a 16-byte aligned CF32 buffer.
+// 56-58 us, arithmetic included.  The streams' periods lie side by side in the capture slots and
+// in the caller's CF32 buffer, so those two are flat arrays; the ring side is flat too whenever a
+// block starts on a period boundary of the ring (frame-wide stores otherwise).
 // ---------------------------------------------------------------------------------------
-struct BankDirectPlan {
-    long long first; // counter value of the stream's first captured frame
-    char *span1;     // where its block starts in the ring; nullptr: discarded as late
-    char *span2;     // where frame span1_frames of the block goes (blocks that straddle a slice boundary)
-    uint32_t span1_frames;
-    uint32_t vector_ok; // the whole block is one 16-byte aligned span
-};
-
-constexpr int kBankDirectMaxGroup = 256;
-
-__host__ __device__ inline uint32_t bank_direct_group(uint32_t period, int U)
-{
-    const uint32_t nvec = period / 2;
-    uint32_t g = nvec ? uint32_t(256 * U) / nvec : 1;
-    return g < 1 ? 1 : (g > uint32_t(kBankDirectMaxGroup) ? uint32_t(kBankDirectMaxGroup) : g);
-}
-
-template <int U, class Hook>
-__global__ void __launch_bounds__(256) bank_repeat_direct_kernel(BankState b, char *cf32, long long rx_time_offset_ns,
-                                                                 bool capture_in_slot, Hook hook)
-{
-    __shared__ BankDirectPlan s_plan[kBankDirectMaxGroup];
-    __shared__ long long s_gap[kBankDirectMaxGroup], s_start[kBankDirectMaxGroup];
-
-    const uint32_t nvec = b.period / 2;
-    const uint32_t G = bank_direct_group(b.period, U);
-    const uint64_t s0 = uint64_t(blockIdx.x) * G;
-    if (s0 >= b.nstreams)
-        return;
-    const uint32_t count = uint32_t(b.nstreams - s0 < G ? b.nstreams - s0 : G);
-
-    bool my_gap = false;
-    if (threadIdx.x < count) {
-        const uint64_t s = s0 + threadIdx.x;
-        long long first;
-        BankWritePlan w;
-        bank_plan_repeat(b, s, cf32, rx_time_offset_ns, first, w);
-        BankDirectPlan p;
-        p.first = first;
-        p.span1 = p.span2 = nullptr;
-        p.span1_frames = b.period;
-        p.vector_ok = 0;
-        if (w.at >= 0) {
-            const uint32_t into = uint32_t(uint64_t(w.at) % b.period);
-            p.span1 = ring_frame(b, s, uint64_t(w.at));
-            p.span1_frames = b.period - into;
-            p.span2 = into ? ring_frame(b, s, uint64_t(w.at) + p.span1_frames) : nullptr;
-            p.vector_ok = into == 0;
-            my_gap = w.gap > 0;
-        }
-        s_plan[threadIdx.x] = p;
-        s_gap[threadIdx.x] = w.at >= 0 ? w.gap : 0;
-        s_start[threadIdx.x] = w.start;
-    }
-    // One barrier hands the plans over and tells every thread whether any stream of the CTA has
-    // a forwarded-over region to silence (rare: late start, underrun).
-    if (__syncthreads_or(my_gap)) {
-        for (uint32_t j = 0; j < count; j++) {
-            long long gap = s_gap[j], start = s_start[j];
-            if (gap <= 0)
-                continue;
-            if (gap > (long long)b.ring) { // older than one lap: only the last lap is still in the ring
-                start += gap - (long long)b.ring;
-                gap = (long long)b.ring;
-            }
-            Pack<2> zero;
-            zero.w[0] = zero.w[1] = 0;
-            for (long long i = threadIdx.x; i < gap; i += blockDim.x)
-                st_stream<8>(ring_frame(b, s0 + j, uint64_t(start + i)), zero);
-        }
-        __syncthreads(); // a gap of a lap or more silences the slots the blocks are about to take
-    }
-
-    const bool pow2 = (nvec & (nvec - 1)) == 0;
-    const uint32_t log2v = 31 - __clz(nvec);
-    const uint32_t total = count * nvec; // vectors of this CTA
-    char *slot = b.capture_stage + s0 * b.period * 8;
-    char *cf = cf32 + s0 * b.period * 8;
-
-    for (uint32_t base = 0; base < total; base += 256 * U) {
-        Pack<4> cap[U], mid[U], out[U];
-        uint32_t jj[U], kk[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const uint32_t idx = base + u * 256 + threadIdx.x;
-            jj[u] = pow2 ? idx >> log2v : idx / nvec;
-            kk[u] = pow2 ? idx & (nvec - 1) : idx - jj[u] * nvec;
-            if (capture_in_slot) {
-                if (idx < total)
-                    cap[u] = ld_stream<16>(slot + size_t(idx) * 16);
-            } else {
-                const uint32_t j = idx < total ? jj[u] : 0;
-                const uint64_t first = uint64_t(s_plan[j].first);
-                const uint64_t z0 = sx_synth_frame(b.seed + s0 + j, first + 2 * uint64_t(kk[u]));
-                const uint64_t z1 = sx_synth_frame(b.seed + s0 + j, first + 2 * uint64_t(kk[u]) + 1);
-                cap[u].w[0] = uint32_t(z0), cap[u].w[1] = uint32_t(z0 >> 32);
-                cap[u].w[2] = uint32_t(z1), cap[u].w[3] = uint32_t(z1 >> 32);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const uint32_t idx = base + u * 256 + threadIdx.x;
-            RxCf32::apply<2>(cap[u], mid[u], 0.0f);
-            if (idx < total)
-                hook(mid[u], s0 + jj[u], 2 * kk[u]); // user DSP between RX and TX, identity by default
-            TxCf32::apply<2>(mid[u], out[u], b.thr2);
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const uint32_t idx = base + u * 256 + threadIdx.x;
-            if (idx >= total)
-                continue;
-            if (!capture_in_slot)
-                st_stream<16>(slot + size_t(idx) * 16, cap[u]);
-            st_stream<16>(cf + size_t(idx) * 16, mid[u]);
-            const BankDirectPlan &p = s_plan[jj[u]];
-            if (p.vector_ok) {
-                st_stream<16>(p.span1 + size_t(kk[u]) * 16, out[u]);
-            } else if (p.span1) {
-                Pack<2> f0, f1;
-                f0.w[0] = out[u].w[0], f0.w[1] = out[u].w[1], f1.w[0] = out[u].w[2], f1.w[1] = out[u].w[3];
-                const uint32_t fr = 2 * kk[u];
-                st_stream<8>(fr < p.span1_frames ? p.span1 + size_t(fr) * 8 : p.span2 + size_t(fr - p.span1_frames) * 8, f0);
-                st_stream<8>(fr + 1 < p.span1_frames ? p.span1 + size_t(fr + 1) * 8 : p.span2 + size_t(fr + 1 - p.span1_frames) * 8, f1);
-            }
-        }
-    }
-}
-
-// The data side of the same schedule with the decisions taken beforehand by
-// bank_plan_repeat_kernel (one thread per stream, every stream of the bank side by side: the
-// decisions are a chain of dependent 64-bit divisions and double-precision operations, a few
-// microseconds of latency per stream however few lanes run it, so inside the data CTAs -- as in
-// bank_repeat_direct_kernel above -- they hold a whole CTA's registers and threads idle for
-// longer than its stores take).  CTA c takes vectors [c * 256 * U, (c + 1) * 256 * U) of the flat
+// The decisions are taken beforehand by bank_plan_repeat_kernel (one thread per stream, every
+// stream of the bank side by side): they are a chain of dependent 64-bit divisions and
+// double-precision operations, a few microseconds of latency per stream however few lanes run it,
+// so taken inside the data CTAs they hold a whole CTA's registers and threads idle for longer than
+// its stores take (that one-launch form was measured at 75.8 us against 61.3 and is gone: commit
+// 354f3f1 has it as bank_repeat_direct_kernel).  CTA c takes vectors [c * 256 * U, (c + 1) * 256 * U) of the flat
 // capture and CF32 arrays; its first threads fetch the streams' first-frame counters and ring
 // offsets into shared memory while the others already have the capture loads in flight.
 // MODE: the whole iteration, or one half of it for the separate calls (sxgpu_bank_read: capture

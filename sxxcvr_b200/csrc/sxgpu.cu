@@ -1397,11 +1397,6 @@ int sxgpu_init(int device, sxgpu_ctx **out)
         uint64_t keep = UINT64_MAX;
         cudaMemPoolSetAttribute(ctx->scratch_pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
-    if (cudaFuncSetAttribute(bank_repeat_bulk_kernel<3, 256, IdentityHook>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             int(3 * size_t(3) * kBankTile * 8 + 3 * 8 + 2 * sizeof(BankTileMeta))) != cudaSuccess ||
-        cudaFuncSetAttribute(bank_repeat_bulk_kernel<3, 1024, IdentityHook>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             int(3 * size_t(3) * kBankTile * 8 + 3 * 8 + 2 * sizeof(BankTileMeta))) != cudaSuccess)
-        return bail(SXGPU_ERR_CUDA);
     for (const LoopShape &shape : kLoopShapes)
         if (cudaFuncSetAttribute(shape.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  int(loop_smem_bytes(shape))) != cudaSuccess)
@@ -1636,9 +1631,6 @@ template <class T> T *carve(char *&cursor, size_t count)
 // separate thread-per-stream plan kernels are 20 % faster.
 constexpr uint32_t kBankFusedPlanStreams = 8192;
 
-// The bulk schedule of the fused iteration: three 16 KiB buffers per stage, three stages.
-constexpr int kBankStages = 3;
-constexpr size_t kBankSmem = 3 * size_t(kBankStages) * kBankTile * 8 + size_t(kBankStages) * 8 + 2 * sizeof(BankTileMeta);
 
 cudaStream_t bank_stream(sxgpu_bank *bank, sxgpu_stream stream)
 {
@@ -1874,7 +1866,6 @@ int sxgpu_bank_repeat(sxgpu_bank *bank, void *d_cf32, long long rx_time_offset_n
     // (each stage reading from L2 what the previous one wrote); 201/202/204 keep the stages'
     // intermediates in registers and only store.  Measured crossovers: profiles/r02_summary.md.
     const bool reg_ok = (b.period % 2 == 0) && reinterpret_cast<uintptr_t>(d_cf32) % 16 == 0;
-    const bool bulk_ok = reg_ok && b.period >= 64 && kBankTile % b.period == 0;
     int64_t k = ctx->bank_repeat_variant;
     if (k == 0) {
         if (b.nstreams <= 2048)
@@ -1910,19 +1901,6 @@ int sxgpu_bank_repeat(sxgpu_bank *bank, void *d_cf32, long long rx_time_offset_n
             go(bank_repeat_group_reg_kernel<2, 4, IdentityHook>);
         break;
     }
-    case 500:   // one launch, hardware-scheduled CTAs: a CTA plans its streams, then stores only (four vectors per thread)
-    case 502: { // ... two vectors per thread
-        if (k == 500) {
-            auto kernel = bank_repeat_direct_kernel<4, IdentityHook>;
-            const uint32_t g = bank_direct_group(b.period, 4);
-            kernel<<<(b.nstreams + g - 1) / g, 256, 0, st>>>(b, cf, rx_time_offset_ns, ext, IdentityHook());
-        } else {
-            auto kernel = bank_repeat_direct_kernel<2, IdentityHook>;
-            const uint32_t g = bank_direct_group(b.period, 2);
-            kernel<<<(b.nstreams + g - 1) / g, 256, 0, st>>>(b, cf, rx_time_offset_ns, ext, IdentityHook());
-        }
-        break;
-    }
     case 600:   // decisions by a thread-per-stream kernel, then the samples by hardware-scheduled CTAs (two vectors per thread)
     case 604: { // ... four vectors per thread
         if (b.period < 4)
@@ -1932,27 +1910,7 @@ int sxgpu_bank_repeat(sxgpu_bank *bank, void *d_cf32, long long rx_time_offset_n
         ctx->launches++;
         break;
     }
-    case 400: { // decisions by a thread-per-stream kernel, samples on the bulk-async schedule
-        if (!bulk_ok)
-            return ctx->invalid("the bulk schedule needs an even period that divides 2048, at least 64, and a 16-byte aligned CF32 buffer");
-        bank_plan_repeat_kernel<<<per_stream_grid(b.nstreams, 128), 128, 0, st>>>(b, cf, rx_time_offset_ns);
-        SX_CUDA(ctx, cudaGetLastError());
-        ctx->launches++;
-        const uint64_t tiles = (uint64_t(b.nstreams) + kBankTile / b.period - 1) / (kBankTile / b.period);
-        // Synthetic capture is ~170 instructions per pair of frames: 32 warps per SM to get through
-        // them; ingested capture is a plain conversion: 8 warps, like the loopback kernel.
-        if (ext && ctx->block != 1024) {
-            auto kernel = bank_repeat_bulk_kernel<kBankStages, 256, IdentityHook>;
-            kernel<<<persistent_grid(ctx, kernel, 256, kBankSmem, tiles), 256, kBankSmem, st>>>(
-                b, cf, ext, IdentityHook(), int(ctx->bulk_load_policy), int(ctx->bulk_store_policy));
-        } else {
-            auto kernel = bank_repeat_bulk_kernel<kBankStages, 1024, IdentityHook>;
-            kernel<<<persistent_grid(ctx, kernel, 1024, kBankSmem, tiles), 1024, kBankSmem, st>>>(
-                b, cf, ext, IdentityHook(), int(ctx->bulk_load_policy), int(ctx->bulk_store_policy));
-        }
-        break;
-    }
-    default: return ctx->invalid("bank_repeat_variant must be 0 (auto), 1, 2, 4, 8, 100, 201, 202, 204, 300, 302, 303, 400, 500, 502, 600 or 604");
+    default: return ctx->invalid("bank_repeat_variant must be 0 (auto), 1, 2, 4, 8, 100, 201, 202, 204, 300, 302, 303, 600 or 604");
     }
     SX_CUDA(ctx, cudaGetLastError());
     ctx->launches += 1;

@@ -237,7 +237,7 @@ def assert_same(a, b, where):
     (70, 3, 600000.0, 0.0),          # odd ring, tiny blocks: frame-wide accesses only
     (2, 4096, 32.0e6 / 1536, 0.25),
 ])
-@pytest.mark.parametrize("variant", [0, 1, 2, 4, 8, 100, 201, 202, 204, 300, 302, 303, 400, 500, 502, 600, 604])
+@pytest.mark.parametrize("variant", [0, 1, 2, 4, 8, 100, 201, 202, 204, 300, 302, 303, 600, 604])
 def test_repeat_is_read_then_write(ctx, nstreams, period, rate, thr2, variant):
     """sxgpu_bank_repeat against the two calls it fuses, through overruns, late (discarded)
     bursts, far-ahead bursts (forward-and-wait with silence) and interleaved separate calls."""
@@ -247,8 +247,6 @@ def test_repeat_is_read_then_write(ctx, nstreams, period, rate, thr2, variant):
     steps += [(0, int(2.5e9)), (0, lat), (5, lat), (100000, lat), (0, lat)]
     if variant >= 200 and period % 2:
         pytest.skip("the register schedules need an even period")
-    if variant == 400 and (period < 64 or 2048 % period):
-        pytest.skip("the bulk schedule needs a period that divides 2048")
     if variant >= 600 and period < 4:
         pytest.skip("the plan + data schedules need a period of at least four frames")
     ctx.set_option("bank_repeat_variant", variant)
@@ -272,7 +270,7 @@ def test_repeat_is_read_then_write(ctx, nstreams, period, rate, thr2, variant):
     ctx.set_option("bank_repeat_variant", 0)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 4, 8, 100, 201, 202, 204, 300, 302, 303, 400, 500, 502, 600, 604])
+@pytest.mark.parametrize("variant", [0, 1, 2, 4, 8, 100, 201, 202, 204, 300, 302, 303, 600, 604])
 def test_repeat_large_bank_against_oracle(ctx, oracle, variant):
     from sxxcvr_b200 import Bank
     S, P = 16384 + 5, 256
@@ -314,7 +312,7 @@ def test_far_future_timestamp_costs_nothing(ctx):
         assert (clock == txp - bank.ring).all()             # the clock ran until the block fitted the ring
 
 
-@pytest.mark.parametrize("variant", [0, 4, 100, 202, 400, 500, 502, 600, 604])
+@pytest.mark.parametrize("variant", [0, 4, 100, 202, 600, 604])
 def test_ingested_frames_replace_the_synthetic_capture(ctx, oracle, variant):
     """sxgpu_bank_ingest / sxgpu_bank_drain: frames handed in from outside go through the same
     bookkeeping and come out of the rings converted; values against the oracle."""
@@ -360,7 +358,7 @@ def test_ingested_frames_replace_the_synthetic_capture(ctx, oracle, variant):
 
 
 @pytest.mark.parametrize("latency_frames", [769, 770, 1023, 1])
-@pytest.mark.parametrize("variant", [2, 100, 202, 300, 303, 400, 500, 502, 600, 604])
+@pytest.mark.parametrize("variant", [2, 100, 202, 300, 303, 600, 604])
 def test_repeat_with_blocks_that_straddle_ring_slices(ctx, variant, latency_frames):
     """Write positions that are not multiples of the period (odd, and even but inside a slice of
     the time-major ring): every schedule against the two calls it fuses."""

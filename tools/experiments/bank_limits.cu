@@ -646,7 +646,6 @@ int main(int argc, char **argv)
             CK(cudaGraphInstantiate(&exec, graph, 0));
             report("plan_then_data_u2_graph", time_us([&](int) { CK(cudaGraphLaunch(exec, 0)); }, 50), bytes3);
         }
-        report("direct_kernel_u2", time_us([&](int) { bank_repeat_direct_kernel<2, IdentityHook><<<(S + 3) / 4, 256>>>(b, cf, lat, false, IdentityHook()); }, 50), bytes3);
         report("group_kernel_v100", time_us([&](int) { bank_repeat_kernel<<<740, 256>>>(b, cf, lat, false); }, 50), bytes3);
         return 0;
     }
