@@ -540,7 +540,7 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
     e2e_streams = args.e2e_streams or max(1, min(8, threads_here // 2))
     e2e_frames = min(1 << args.e2e_log2_frames, frames)
     bounce = max(1, threads_here // e2e_streams - 1)
-    dev_args = f", gpu={local_rank}, sxgpu.bounce_threads={bounce}"
+    dev_args = f", gpu={local_rank}, sxgpu.bounce_threads={bounce}" + (args.e2e_dev_args and ", " + args.e2e_dev_args)
     def plugin_leg(kind):
         streams = PluginStreams(product, e2e_frames, e2e_streams, kind, dev_args, ctx, SEED + rank)
         try:
@@ -1121,6 +1121,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log2-frames", type=int, default=27, help="frames per block per GPU (2^27 = 1 GiB in)")
     ap.add_argument("--e2e-log2-frames", type=int, default=27, help="frames per block of the plugin leg (capped at --log2-frames)")
+    ap.add_argument("--e2e-dev-args", default="", help="extra device arguments of the plugin leg, e.g. sxgpu.host_chunk_frames=1048576")
     ap.add_argument("--e2e-streams", type=int, default=0, help="devices (caller threads) per GPU in the plugin leg; 0 = auto")
     ap.add_argument("--e2e-buffers", default="pinned", choices=["pageable", "pin", "pinned"],
                     help="caller buffers of the headline plugin leg: sxgpu_malloc_host memory (default: the contract's "

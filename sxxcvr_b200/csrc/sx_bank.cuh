@@ -24,6 +24,12 @@
 //                             registers, then the warp takes each stream through the three
 //                             stages back to back, each stage reading from L2 what the previous
 //                             one has just written
+// Large banks (bank_is_large: bound by HBM, not by launch latency) run every call -- the fused
+// iteration and the separate read and write -- as two kernels instead:
+//     bank_plan_{repeat,read,write}_kernel   the decisions, one thread per stream
+//     bank_repeat_data_kernel<U, Hook, MODE> the samples: one chunk of vectors per CTA, CTAs handed
+//                             out in order by the hardware, every intermediate in registers,
+//                             launched as a programmatic dependent of the plan kernel
 // The virtual clock follows the same rule as the host-side ALSA stand-in: it moves when a
 // blocking transfer must wait (by exactly the deficit) or when the owner advances it.
 #pragma once
