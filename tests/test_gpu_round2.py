@@ -184,6 +184,35 @@ def test_batched_mid_size_blocks(ctx, oracle, variant, shape):
     assert (goti[~covered] == 0).all()
 
 
+@pytest.mark.parametrize("variant", [0, 2, 3])
+def test_batched_device_list_with_an_understated_max_length(ctx, oracle, variant):
+    """max_length only sizes the grid: a device-resident list whose longest block is longer than the
+    caller said is still converted whole (the last CTA of a block takes what is left of it)."""
+    from sxxcvr_b200.capi import Block
+    lengths = [70001, 5000, 8192, 123457, 6]
+    offsets, at = [], 2
+    for n in lengths:
+        offsets.append(at)
+        at += n + 2
+    total = at
+    words = sxtest.rx_uniform(total, seed=77)
+    src = dev(words)
+    dst = torch.zeros(2 * total, dtype=torch.float32, device="cuda")
+    blocks = make_blocks(src.data_ptr(), dst.data_ptr(), lengths, offsets, [0.0] * len(lengths))
+    arr = (Block * len(blocks))(*blocks)
+    d_list = torch.from_numpy(np.frombuffer(bytes(arr), dtype=np.uint8).copy()).cuda()
+    ctx.set_option("batch_variant", variant)
+    ctx.convert_batch("rx", d_list.data_ptr(), on_device=True, max_length=8192, nblocks=len(blocks))
+    ctx.stream_sync()
+    ctx.set_option("batch_variant", 0)
+    got, want = host(dst), sxtest.oracle_rx(oracle, words)
+    covered = np.zeros(2 * total, bool)
+    for n, o in zip(lengths, offsets):
+        assert np.array_equal(bits(got[2 * o: 2 * (o + n)]), bits(want[2 * o: 2 * (o + n)])), (n, o)
+        covered[2 * o: 2 * (o + n)] = True
+    assert (got[~covered] == 0).all()
+
+
 def test_batched_blocks_in_place_and_back_to_back(ctx, oracle):
     """In place (src == dest, allowed for the equal-width conversions) and several batches queued
     back to back on one stream, each with its own host-resident descriptor list."""
