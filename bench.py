@@ -566,6 +566,43 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
     e2e_link_gbs = [v * 1e6 * 8 / 1e9 for v in e2e_per_rank]
     frac_of_link = [a / b if b else None for a, b in zip(e2e_link_gbs, link["both_each_way_gbs"])]
 
+    # ---- the same bytes through the C ABI alone (no plugin, no ALSA stand-in): D threads, each with
+    # a context of its own, alternate sxgpu_convert_rx_buffer_host / _tx_buffer_host on pinned
+    # buffers.  What separates this figure from the plugin leg is the stand-in's own copies (the
+    # "hardware" side of the I/O model, which the reference arm pays too), not the library.
+    c_abi = None
+    if world == 1 and not args.no_rows:
+        from sxxcvr_b200 import Context
+        D, n_call, iters = e2e_streams, e2e_frames // e2e_streams, 6
+        ctxs = [Context(local_rank) for _ in range(D)]
+        bufs = [[c.malloc_host(8 * n_call) for _ in range(3)] for c in ctxs]
+        secs, gate = [0.0] * D, threading.Barrier(D)
+
+        def abi_work(k):
+            c, (a, b, d) = ctxs[k], bufs[k]
+            c.convert_rx_buffer_host(a, 0, b, 0, n_call)
+            c.convert_tx_buffer_host(b, 0, d, 0, n_call, THR2)
+            gate.wait()
+            t0 = time.perf_counter()
+            for _ in range(iters):
+                c.convert_rx_buffer_host(a, 0, b, 0, n_call)
+                c.convert_tx_buffer_host(b, 0, d, 0, n_call, THR2)
+            secs[k] = time.perf_counter() - t0
+
+        ts = [threading.Thread(target=abi_work, args=(k,)) for k in range(D)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        for c, three in zip(ctxs, bufs):
+            for ptr in three:
+                c.free_host(ptr)
+            c.close()
+        abi_msps = D * iters * 2 * n_call / max(secs) / 1e6
+        c_abi = {"value": round(abi_msps, 1), "unit": UNIT, "threads": D, "frames_per_call": n_call,
+                 "frac_of_link": round(abi_msps * 1e6 * 8 / 1e9 / link["both_each_way_gbs"][0], 3),
+                 "api": "sxgpu_convert_rx_buffer_host + sxgpu_convert_tx_buffer_host on sxgpu_malloc_host memory, one context per thread"}
+
     # ---- one stream at a time: frames per call x caller buffer, product beside the reference -----
     rows = []
     if rank == 0 and not args.no_rows:
@@ -710,6 +747,7 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
                                              "frac_of_link": [round(x * 1e6 * 8 / 1e9 / l, 3) if l else None
                                                               for x, l in zip(v["per_rank"], link["both_each_way_gbs"])]}
                                          for k, v in legs.items()},
+                    "c_abi_host_calls": c_abi,
                     "plugin_rows": rows},
             "gpu_launches": launches, "clocks": clocks, "cpu_baseline": cpu, "small_blocks": small,
             "checksums": {"fields": list(sharding.STATS_FIELDS), "per_rank": checks,
