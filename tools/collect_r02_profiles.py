@@ -12,15 +12,15 @@ ROOT = Path(__file__).resolve().parent.parent
 OUT, PROF = ROOT / "gpurun_out", ROOT / "profiles"
 
 COPIES = {  # profiles name -> candidates under gpurun_out (first that exists wins)
-    "r02_bench_n1.json": ["f2_bench.json"],
-    "r02_bench_n1_steps20.json": ["f2_bench_steps20.json"],
-    "r02_bench_reference_arm.json": ["f2_bench_ref.json"],
-    "r02_bench_sweep.json": ["f2_bench_sweep.json"],
-    "r02_bench_group.json": ["f2_bench_group.json"],
-    "r02_bench_single_process.json": ["f2_bench_single.json"],
-    "r02_bench_bank_fused.json": ["f2_bench_bank_fused.json"],
-    "r02_bench_bank_fused_graph.json": ["f2_bench_bank_fused_graph.json"],
-    "r02_bench_bank_fused_graph_external.json": ["f2_bench_bank_fused_graph_external.json"],
+    "r02_bench_n1.json": ["f6_bench.json", "f2_bench.json"],
+    "r02_bench_n1_steps20.json": ["f6_bench_steps20.json", "f2_bench_steps20.json"],
+    "r02_bench_reference_arm.json": ["f6_bench_ref.json", "f2_bench_ref.json"],
+    "r02_bench_sweep.json": ["f6_bench_sweep.json", "f2_bench_sweep.json"],
+    "r02_bench_group.json": ["f6_bench_group.json", "f2_bench_group.json"],
+    "r02_bench_single_process.json": ["f6_bench_single.json", "f2_bench_single.json"],
+    "r02_bench_bank_fused.json": ["f6_bench_bank_fused.json", "f2_bench_bank_fused.json"],
+    "r02_bench_bank_fused_graph.json": ["f6_bench_bank_fused_graph.json", "f2_bench_bank_fused_graph.json"],
+    "r02_bench_bank_fused_graph_external.json": ["f6_bench_bank_fused_graph_external.json", "f2_bench_bank_fused_graph_external.json"],
     "r02_bench_n2.json": ["m2_bench.json"],
     "r02_bench_n2_single_process.json": ["m2_bench_single.json"],
     "r02_bench_n2_reference_arm.json": ["m2_bench_ref.json"],
@@ -31,17 +31,17 @@ COPIES = {  # profiles name -> candidates under gpurun_out (first that exists wi
     "r02_bench_n8_single_process.json": ["m8_bench_single.json"],
     "r02_bench_n8_reference_arm.json": ["m8_bench_ref.json"],
     "r02_bench_n8_sweep.json": ["m8_bench_sweep.json"],
-    "r02_launches.csv": ["f2_launches.csv"],
-    "r02_sweep_host_path_and_plugin_pairs.json": ["f2_sweep_host_plugin.json", "s3_sweep.json"],
-    "r02_sweep_direct_against_persistent.json": ["f2_sweep_direct.json"],
+    "r02_launches.csv": ["f6_launches.csv", "f2_launches.csv"],
+    "r02_sweep_host_path_and_plugin_pairs.json": ["f6_sweep_host_plugin.json", "f2_sweep_host_plugin.json", "s3_sweep.json"],
+    "r02_sweep_direct_against_persistent.json": ["f6_sweep_direct.json", "f2_sweep_direct.json"],
     "r02_sweep_batched_loopback.json": ["s4_sweep.json"],
     "r02_sweep_pipeline_modes.json": ["s3_sweep.json"],
     "r02_probe_batch_per_call.log": ["s4_probe_batch.log"],
     "r02_probe_batch_with_default_mempool.log": ["probe_batch.log"],
     "r02_probe_batch_with_default_mempool_ncu.csv": ["probe_batch_ncu.csv"],
-    "r02_sanitizer_memcheck.log": ["f2_sanitizer_memcheck.log"],
-    "r02_sanitizer_racecheck.log": ["f2_sanitizer_racecheck.log"],
-    "r02_final_gpu_pytest.log": ["f2_pytest.log"],
+    "r02_sanitizer_memcheck.log": ["f6_sanitizer_memcheck.log", "f2_sanitizer_memcheck.log"],
+    "r02_sanitizer_racecheck.log": ["f6_sanitizer_racecheck.log", "f2_sanitizer_racecheck.log"],
+    "r02_final_gpu_pytest.log": ["f6_pytest.log", "f2_pytest.log"],
 }
 
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__bytes.sum.per_second",
@@ -74,7 +74,8 @@ def main():
         else:
             print("missing:", srcs, file=sys.stderr)
     table, traffic = [], {}
-    for rep in sorted(OUT.glob("f2_ncu_*.ncu-rep")):
+    reps = sorted(OUT.glob("f6_ncu_*.ncu-rep")) or sorted(OUT.glob("f2_ncu_*.ncu-rep"))
+    for rep in reps:
         rows, units = raw_rows(rep)
         seen = {}
         for d in rows:
