@@ -228,6 +228,15 @@ int sxgpu_bank_ring_frames(sxgpu_bank *bank, uint64_t *ring_frames);
  * and the kernel uses the buffer directly. */
 int sxgpu_convert_rx_buffer_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset,
                                  void *h_dest, size_t dest_offset, size_t length);
+/* The same while the source is still being filled (a readStream of many ALSA rings' worth of frames:
+ * snd_pcm_readi copies piece by piece, SoapySX.cpp:948, and the conversion of the first pieces need
+ * not wait for the last).  *frames_ready = frames of the block in place so far, written by the
+ * filling thread with release semantics; bit 63 set = that count is final, the block ends there.
+ * No chunk of the pipeline is touched before its frames are in place.  Returns when everything
+ * that came is converted; *converted (may be NULL) = how many frames that was. */
+int sxgpu_convert_rx_buffer_host_gated(sxgpu_ctx *ctx, const void *h_src, size_t src_offset, void *h_dest,
+                                       size_t dest_offset, size_t length, const volatile uint64_t *frames_ready,
+                                       size_t *converted);
 int sxgpu_convert_tx_buffer_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset,
                                  void *h_dest, size_t dest_offset, size_t length,
                                  float tx_threshold2);

@@ -80,6 +80,7 @@ SIGNATURES = {
     "sxgpu_bank_playback": (C.c_int, [_P, C.c_uint32, C.c_int64, _S, _P, _P]),
     "sxgpu_bank_ring_frames": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "sxgpu_convert_rx_buffer_host": (C.c_int, [_P, _P, _S, _P, _S, _S]),
+    "sxgpu_convert_rx_buffer_host_gated": (C.c_int, [_P, _P, _S, _P, _S, _S, _P, _P]),
     "sxgpu_convert_tx_buffer_host": (C.c_int, [_P, _P, _S, _P, _S, _S, _F]),
     "sxgpu_convert_rx_buffer_cs16_host": (C.c_int, [_P, _P, _S, _P, _S, _S]),
     "sxgpu_convert_tx_buffer_cs16_host": (C.c_int, [_P, _P, _S, _P, _S, _S, _F]),

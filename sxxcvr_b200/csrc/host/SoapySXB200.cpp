@@ -19,6 +19,10 @@
 
 namespace sxhost {
 
+// Blocking reads of this many frames and more run their conversion under the read itself (see
+// readStream); the read then proceeds in pieces of kGatedReadPiece frames.
+constexpr size_t kGatedReadFrames = size_t(1) << 22, kGatedReadPiece = size_t(1) << 20;
+
 namespace {
 
 // SX1255 sample-rate dividers that work over I2S with 32-bit slots (reference table,
@@ -203,6 +207,7 @@ SoapySXB200::SoapySXB200(const SoapySDR::Kwargs &args)
     setFrequency(SOAPY_SDR_RX, 0, 433.92e6, SoapySDR::Kwargs());
     setFrequency(SOAPY_SDR_TX, 0, 433.92e6, SoapySDR::Kwargs());
 
+    overlap_reads_ = kwarg(args, "overlap", "1") != "0";
     stage_rx_ = std::make_unique<PinnedFrames>(gpu_);
     stage_tx_ = std::make_unique<PinnedFrames>(gpu_);
     try {
@@ -224,7 +229,8 @@ SoapySXB200::~SoapySXB200()
     SoapySDR_logf(SOAPY_SDR_INFO, "Uninitializing SoapySX (B200 stream path)");
     unpin_all(rx_);
     unpin_all(tx_);
-    stage_rx_.reset(); // pinned memory goes back before the context that owns it
+    rx_helper_.reset(); // its thread is idle between calls; gone before the context it calls into
+    stage_rx_.reset();  // pinned memory goes back before the context that owns it
     stage_tx_.reset();
     sxgpu_destroy(gpu_);
 }
@@ -405,6 +411,53 @@ int SoapySXB200::readStream(SoapySDR::Stream *stream, void *const *buffs, const 
     flags = 0;
     if (ep.is_tx())
         throw std::runtime_error("Wrong direction");
+
+    // A long blocking read: the stand-in (like the kernel behind a real snd_pcm_readi) copies ring
+    // after ring into the staging buffer, and nothing makes the conversion of the first pieces wait
+    // for the last.  The conversion is started on a helper thread before the read and gated by how
+    // far the read has come; this thread reads piece by piece and says so.
+    if (overlap_reads_ && !ep.cs16 && numElems >= kGatedReadFrames && timeoutUs > 0 && ep.active) {
+        pin_if_asked(ep, buffs[0], numElems * 8);
+        stage_rx_->reserve(numElems);
+        if (!rx_helper_)
+            rx_helper_ = std::make_unique<Sidekick>();
+        rx_ready_.store(0, std::memory_order_relaxed);
+        int conv_rc = SXGPU_OK;
+        size_t converted = 0;
+        void *const stage = stage_rx_->data();
+        void *const dest = buffs[0];
+        rx_helper_->start([&, stage, dest] {
+            conv_rc = sxgpu_convert_rx_buffer_host_gated(gpu_, stage, 0, dest, 0, numElems,
+                                                         reinterpret_cast<const volatile uint64_t *>(&rx_ready_), &converted);
+        });
+        struct Release { // whatever happens to the read, the helper is told where the block ends and waited for
+            SoapySXB200 *self;
+            uint64_t got = 0;
+            ~Release()
+            {
+                self->rx_ready_.store(got | (uint64_t(1) << 63), std::memory_order_release);
+                self->rx_helper_->finish();
+            }
+        };
+        RxOutcome rx;
+        {
+            Release release{this};
+            rx = rx_before_convert(
+                ep, sample_rate_, numElems, timeoutUs, [stage](size_t) { return stage; }, kGatedReadPiece,
+                [this](size_t first, size_t frames) { rx_ready_.store(first + frames, std::memory_order_release); });
+            release.got = rx.ret > 0 ? uint64_t(rx.ret) : 0;
+        }
+        if (rx.time_valid)
+            timeNs = rx.time_ns;
+        flags |= rx.flags;
+        if (rx.ret <= 0)
+            return rx.ret;
+        if (conv_rc != SXGPU_OK || converted != size_t(rx.ret)) {
+            SoapySDR_logf(SOAPY_SDR_ERROR, "rx GPU conversion failed: %s (%s)", sxgpu_strerror(conv_rc), sxgpu_last_error(gpu_));
+            return SOAPY_SDR_STREAM_ERROR;
+        }
+        return rx.ret;
+    }
 
     // Everything up to the conversion (csrc/host/stream_ops.hpp): pending frames, overrun skip,
     // non-blocking trim, snd_pcm_readi into pinned staging, timestamp, frame counter.

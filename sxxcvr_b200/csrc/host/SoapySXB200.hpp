@@ -27,6 +27,9 @@
 #include <utility>
 #include <vector>
 
+#include <atomic>
+
+#include "par_copy.hpp"
 #include "stream_plan.hpp"
 
 struct sxgpu_ctx;
@@ -161,6 +164,11 @@ private:
     float tx_threshold2_ = 0.0f;
     bool linked_ = false;
 
+    // Long blocking reads (kGatedReadFrames and more): the conversion runs on a helper thread while
+    // this one is still reading, gated by how far the read has come (sxgpu_convert_rx_buffer_host_gated).
+    std::unique_ptr<Sidekick> rx_helper_;
+    alignas(64) std::atomic<uint64_t> rx_ready_{0};
+    bool overlap_reads_ = true; // device argument overlap=0 turns it off
     std::unique_ptr<PinnedFrames> stage_rx_;
     std::unique_ptr<PinnedFrames> stage_tx_;
 };

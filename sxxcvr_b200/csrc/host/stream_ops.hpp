@@ -45,8 +45,14 @@ struct RxOutcome {
     bool time_valid = false; // time_ns was set (the reference leaves timeNs untouched otherwise)
 };
 
-template <class Staging>
-inline RxOutcome rx_before_convert(Endpoint &ep, double sample_rate, size_t numElems, long timeoutUs, Staging &&staging)
+// `piece` > 0: a transfer longer than that is read piece by piece -- what snd_pcm_readi does inside
+// anyway, a ring (at most 65536 frames) at a time -- and on_piece(first, frames) is told about
+// every piece as it lands, so that its conversion need not wait for the last one.  A piece that
+// fails after others have landed ends the call with the frames read so far, as a failing
+// snd_pcm_readi does; the error resurfaces on the next call.
+template <class Staging, class OnPiece>
+inline RxOutcome rx_before_convert(Endpoint &ep, double sample_rate, size_t numElems, long timeoutUs, Staging &&staging,
+                                   size_t piece, OnPiece &&on_piece)
 {
     RxOutcome out;
     if (!ep.active)
@@ -77,10 +83,33 @@ inline RxOutcome rx_before_convert(Endpoint &ep, double sample_rate, size_t numE
     if (length == 0)
         return out;
 
-    snd_pcm_sframes_t got = snd_pcm_readi(ep.pcm, staging(size_t(length)), length);
-    if (got < 0) {
-        out.ret = stream_error_from_alsa(ep, got);
-        return out;
+    snd_pcm_sframes_t got = 0;
+    if (piece == 0 || length <= piece) {
+        got = snd_pcm_readi(ep.pcm, staging(size_t(length)), length);
+        if (got < 0) {
+            out.ret = stream_error_from_alsa(ep, got);
+            return out;
+        }
+        if (got > 0)
+            on_piece(size_t(0), size_t(got));
+    } else {
+        char *base = static_cast<char *>(staging(size_t(length)));
+        while ((unsigned long)got < length) {
+            const unsigned long want = std::min<unsigned long>(piece, length - (unsigned long)got);
+            const snd_pcm_sframes_t r = snd_pcm_readi(ep.pcm, base + size_t(got) * 8, want);
+            if (r < 0) {
+                if (got == 0) {
+                    out.ret = stream_error_from_alsa(ep, r);
+                    return out;
+                }
+                break;
+            }
+            if (r > 0)
+                on_piece(size_t(got), size_t(r));
+            got += r;
+            if ((unsigned long)r < want)
+                break;
+        }
     }
 
     // The block's timestamp is the counter value of its first frame.
@@ -90,6 +119,12 @@ inline RxOutcome rx_before_convert(Endpoint &ep, double sample_rate, size_t numE
     ep.position += got;
     out.ret = int(got);
     return out;
+}
+
+template <class Staging>
+inline RxOutcome rx_before_convert(Endpoint &ep, double sample_rate, size_t numElems, long timeoutUs, Staging &&staging)
+{
+    return rx_before_convert(ep, sample_rate, numElems, timeoutUs, staging, size_t(0), [](size_t, size_t) {});
 }
 
 // writeStream up to the conversion: where the block lands, the forward over the gap, the

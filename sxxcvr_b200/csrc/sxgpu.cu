@@ -849,9 +849,33 @@ template <class Op> constexpr int lane_of()
                : 0;
 }
 
+// A gated call (sxgpu_convert_rx_buffer_host_gated): the source buffer is still being filled while
+// the conversion runs.  *gate = frames of the block that are in place so far; bit 63 set = that
+// count is final (no more will come: the block ends there, possibly short of `length`).
+constexpr uint64_t kGateFinal = uint64_t(1) << 63;
+// Waits until `need` frames are in place or the count is final; returns the frames that may be
+// touched, at most `need`.
+inline uint64_t gate_wait(const volatile uint64_t *gate, uint64_t need)
+{
+    if (!gate)
+        return need;
+    unsigned spins = 0;
+    for (;;) {
+        const uint64_t v = __atomic_load_n(const_cast<const uint64_t *>(gate), __ATOMIC_ACQUIRE);
+        const uint64_t have = v & ~kGateFinal;
+        if (have >= need)
+            return need;
+        if (v & kGateFinal)
+            return have;
+        if (++spins > 4000)
+            std::this_thread::yield();
+    }
+}
+
 template <class Op>
 int convert_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset, void *h_dest,
-                 size_t dest_offset, size_t length, float thr2, int64_t variant)
+                 size_t dest_offset, size_t length, float thr2, int64_t variant,
+                 const volatile uint64_t *gate = nullptr, size_t *converted = nullptr)
 {
     constexpr size_t SFB = Op::kSrcWords * 4, DFB = Op::kDstWords * 4; // frame bytes on each side
     if (!ctx)
@@ -881,7 +905,16 @@ int convert_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset, void *h_d
     const bool both_on_device = si.on_device && di.on_device;
     const bool small = ctx->host_mode == 2 ||
                        (ctx->host_mode == 0 && length <= size_t(ctx->zero_copy_max_frames));
+    if (converted)
+        *converted = length;
     if (both_on_device || small) {
+        if (gate) { // one kernel over the whole block: it has to be there
+            length = size_t(gate_wait(gate, length));
+            if (converted)
+                *converted = length;
+            if (length == 0)
+                return SXGPU_OK;
+        }
         const bool bounce_in = !si.device_alias, bounce_out = !di.device_alias;
         SX_TRY(ensure_ring(ctx, lane, (bounce_in || bounce_out) ? length : 0, bounce_in, bounce_out));
         const void *kernel_in = si.device_alias;
@@ -929,7 +962,7 @@ int convert_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset, void *h_d
     // + 128: the cap is rounded up to 64 frames and the last chunk carries the ragged end (< 64)
     SX_TRY(ensure_ring(ctx, lane, c_max + 128, bounce_in, bounce_out));
     HostRing &r = lane.ring;
-    const std::vector<sxhost::ChunkSpan> chunks =
+    std::vector<sxhost::ChunkSpan> chunks = // (a gated call that ends short trims them as it goes)
         sxhost::plan_chunks(length, size_t(ctx->host_chunk_min_frames), std::min(c_max, r.chunk_frames - 128));
     const size_t nchunks = chunks.size();
 
@@ -997,7 +1030,23 @@ int convert_host(sxgpu_ctx *ctx, const void *h_src, size_t src_offset, void *h_d
         for (size_t i = 0; i < nchunks; i++) {
             const int slot = int(i % kRingSlots);
             SX_TRY(wait_slot_free(i));
-            const size_t first = chunks[i].first, n = chunks[i].frames;
+            const size_t first = chunks[i].first;
+            size_t n = chunks[i].frames;
+            if (gate) { // the source is still being filled: this chunk's frames, or what the block ends with
+                const uint64_t have = gate_wait(gate, first + n);
+                if (have < first + n) { // final and short: the block ends inside (or before) this chunk
+                    n = have > first ? size_t(have - first) : 0;
+                    chunks[i].frames = n;
+                    for (size_t j = i + 1; j < nchunks; j++)
+                        chunks[j].frames = 0;
+                    if (converted)
+                        *converted = std::min<size_t>(*converted, first + n);
+                }
+                if (n == 0) { // nothing of this chunk exists: no work, the slot's events keep their last (completed) state
+                    lane.issued.publish(i + 1);
+                    continue;
+                }
+            }
 
             // Input side: the caller's device buffer as it is; or pinned host memory (the caller's,
             // or the bounce slot) either copied in by the copy engine or read by the kernel itself.
@@ -2125,6 +2174,22 @@ int sxgpu_convert_rx_buffer_host(sxgpu_ctx *ctx, const void *h_src, size_t src_o
                                  ctx ? ctx->rx_variant : 0);
     if (r == SXGPU_OK)
         ctx->frames_rx += length;
+    return r;
+}
+
+int sxgpu_convert_rx_buffer_host_gated(sxgpu_ctx *ctx, const void *h_src, size_t src_offset, void *h_dest,
+                                       size_t dest_offset, size_t length, const volatile uint64_t *frames_ready,
+                                       size_t *converted)
+{
+    if (!frames_ready)
+        return ctx ? ctx->invalid("gated conversion needs a progress counter") : SXGPU_ERR_INVALID;
+    size_t done = 0;
+    int r = convert_host<RxCf32>(ctx, h_src, src_offset, h_dest, dest_offset, length, 0.0f, ctx ? ctx->rx_variant : 0,
+                                 frames_ready, &done);
+    if (converted)
+        *converted = done;
+    if (r == SXGPU_OK)
+        ctx->frames_rx += done;
     return r;
 }
 

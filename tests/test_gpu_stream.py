@@ -67,6 +67,51 @@ def test_read_values_are_the_oracle_of_the_synthetic_frames(product, oracle):
             assert np.array_equal(buf.view(np.uint32), want.view(np.uint32)), (k, n)
 
 
+@pytest.mark.parametrize("dev_args", ["driver=sx", "driver=sx, overlap=0"])
+def test_long_reads_convert_under_the_read(product, oracle, dev_args):
+    """Blocking reads of 2^22 frames and more are read piece by piece with the conversion running
+    behind the read (sxgpu_convert_rx_buffer_host_gated): same values, timestamps, counters and
+    return codes as the one-piece path (overlap=0) and as the reference driver."""
+    sizes = ((1 << 22) + 3, 1 << 22, 3 * (1 << 21) + 1, 70000)
+    ref = sxstream.Harness(sxstream.REF_LIB) if sxstream.REF_LIB.exists() else None
+    with product.device(dev_args) as d:
+        d.set_rate(300000.0)
+        rx = d.setup(sxstream.RX, args="period=4096")
+        d.activate(rx)
+        got = []
+        for n in sizes:
+            before = d.pointers()[1]
+            r, fl, t, buf = d.read(rx, n)
+            assert r == n and fl == sxstream.HAS_TIME
+            want = sxtest.oracle_rx(oracle, sxtest.synth_frames(oracle, before, n))
+            assert np.array_equal(buf.view(np.uint32), want.view(np.uint32)), n
+            got.append((r, fl, t, d.pointers()))
+    if ref is not None:
+        with ref.device() as d:
+            d.set_rate(300000.0)
+            rx = d.setup(sxstream.RX, args="period=4096")
+            d.activate(rx)
+            for n, g in zip(sizes, got):
+                r, fl, t, _ = d.read(rx, n)
+                assert (r, fl, t, d.pointers()) == g, n
+
+
+def test_long_read_that_ends_in_an_error_returns_what_was_read(product, oracle):
+    """A capture error injected into a later piece of a long read: the frames read so far come back
+    converted (as a failing snd_pcm_readi returns them), the error on the next call."""
+    n = (1 << 22) + 5
+    with product.device() as d:
+        d.set_rate(300000.0)
+        rx = d.setup(sxstream.RX, args="period=4096")
+        d.activate(rx)
+        before = d.pointers()[1]
+        d.inject(True, sxstream.OP_READI, -32, 2)            # the third snd_pcm_readi of the stream fails with -EPIPE
+        r, fl, t, buf = d.read(rx, n)
+        assert r == 2 << 20 and fl == sxstream.HAS_TIME      # two pieces of 2^20 frames landed
+        want = sxtest.oracle_rx(oracle, sxtest.synth_frames(oracle, before, r))
+        assert np.array_equal(buf[: 2 * r].view(np.uint32), want.view(np.uint32))
+
+
 def test_capture_table_known_answers_through_readstream(product):
     kat = {0: 0x00000000, 1: 0x30000000, -1: 0xB0000000, 2**31 - 1: 0x3F800000, -2**31: 0xBF800000,
            0x7FFFFF80: 0x3F7FFFFF, 0x7FFFFFC0: 0x3F800000, 0x12345678: 0x3E11A2B4}
